@@ -1,0 +1,81 @@
+"""ctypes binding of libbnerv_b200.so (the C-ABI declared in include/bnerv_b200.h).
+
+There is deliberately no fallback here: if the shared library is missing the import of this
+module raises, and every wrapper raises BnervError on a non-zero return code.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libbnerv_b200.so")
+
+ACT_NONE, ACT_SIN, ACT_GELU, ACT_RELU, ACT_TANH01 = 0, 1, 2, 3, 4
+ACT_CODES = {"none": ACT_NONE, "sin": ACT_SIN, "gelu": ACT_GELU, "relu": ACT_RELU, "tanh01": ACT_TANH01}
+
+EXPORTS = [
+    "bnerv_abi_version", "bnerv_last_error", "bnerv_launch_count", "bnerv_pack_conv_weight", "bnerv_conv_fused",
+    "bnerv_conv_fused_f32", "bnerv_sft_affine", "bnerv_linear_act", "bnerv_nchw_to_c8", "bnerv_c8_to_nchw",
+    "bnerv_pixel_shuffle", "bnerv_c8_numel", "bnerv_packed_weight_numel", "bnerv_packed_bias_numel",
+]
+
+
+class BnervError(RuntimeError):
+    def __init__(self, fn, code, text):
+        super().__init__(f"{fn} failed with code {code}: {text}")
+        self.code = code
+
+
+class SftLayer(ctypes.Structure):
+    """struct bnerv_sft_layer"""
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("ws0", "bs0", "ws1", "bs1", "wh0", "bh0", "wh1", "bh1", "g1p", "beta")] + \
+               [("C", ctypes.c_int), ("Cp", ctypes.c_int)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the bnerv_b200 CUDA extension is not built "
+            "(run `python boosting-nerv_b200/build.py`); there is no fallback path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.bnerv_abi_version.restype = i
+    lib.bnerv_last_error.restype = ctypes.c_char_p
+    lib.bnerv_launch_count.restype = ctypes.c_uint64
+    lib.bnerv_pack_conv_weight.argtypes = [vp, vp, i, i, i, i, vp, vp, vp]
+    lib.bnerv_conv_fused.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
+    lib.bnerv_conv_fused_f32.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp, i, vp, vp, vp]
+    lib.bnerv_sft_affine.argtypes = [vp, i, vp, i, i, vp]
+    lib.bnerv_linear_act.argtypes = [vp, i, i, vp, vp, i, i, vp, vp]
+    lib.bnerv_nchw_to_c8.argtypes = [vp, i, i, i, i, vp, vp]
+    lib.bnerv_c8_to_nchw.argtypes = [vp, i, i, i, i, vp, vp]
+    lib.bnerv_pixel_shuffle.argtypes = [vp, i, i, i, i, i, vp, vp]
+    for name in ("bnerv_c8_numel",):
+        getattr(lib, name).argtypes = [i, i, i, i]
+        getattr(lib, name).restype = ctypes.c_size_t
+    lib.bnerv_packed_weight_numel.argtypes = [i, i, i, i]
+    lib.bnerv_packed_weight_numel.restype = ctypes.c_size_t
+    lib.bnerv_packed_bias_numel.argtypes = [i, i]
+    lib.bnerv_packed_bias_numel.restype = ctypes.c_size_t
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is ctypes.c_int and name != "bnerv_abi_version":
+            pass
+    return lib
+
+
+lib = _load()
+
+
+def check(fn_name, rc):
+    if rc != 0:
+        raise BnervError(fn_name, rc, lib.bnerv_last_error().decode("utf-8", "replace"))
+
+
+def launch_count():
+    return int(lib.bnerv_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())

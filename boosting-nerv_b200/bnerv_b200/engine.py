@@ -1,0 +1,227 @@
+"""Decode engine: walks a *_Boost model's parameter tree once, packs weights into kernel layout, owns the
+activation workspaces, and runs the block cascade with three fused-conv launches per NeRVBlock:
+
+    up-conv (+PixelShuffle +sin)  -> x0 (kept for the residual)  and  u = x0*(g0+1)+b0
+    conv0   (+GELU)               -> w = gelu(.)*(g1+1)+b1
+    conv1   (+residual x0)        -> block output
+
+plus ONE launch that evaluates every SFT layer's (scale, shift) MLP for the frame(s), and the head conv
+(+tanh*0.5+0.5) that writes the NCHW f32 image.  (model_blocks.py:34-46, 74-105; model_*.py forward.)
+
+Weights are re-packed only when the effective tensor (``dequant_w ?? weight``) changed — detected through
+tensor identity + in-place version counters, so optimiser steps and ``cal_params`` invalidate the cache.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .layers import (Conv_Up_Block, CustomConv2d, DownConv, NeRVBlock, UpConv, act_name, effective_weight)
+
+
+class Unsupported(RuntimeError):
+    pass
+
+
+def _tensor_key(t):
+    return None if t is None else (id(t), t._version, t.data_ptr())
+
+
+class _ConvSlot:
+    """One conv of the cascade: module + geometry + lazily (re)packed weights."""
+
+    def __init__(self, module, s=1):
+        if not isinstance(module, nn.Conv2d) or module.stride != (1, 1) or module.dilation != (1, 1) or module.groups != 1:
+            raise Unsupported(f"conv {module} is not a stride-1 dense conv")
+        k = module.kernel_size[0]
+        if module.kernel_size != (k, k) or k not in (1, 3) or module.padding != ((k - 1) // 2,) * 2:
+            raise Unsupported(f"conv {module}: only 1x1 / 3x3 'same' convs are accelerated")
+        self.m, self.k, self.s = module, k, s
+        self.cin, self.cout = module.in_channels, module.out_channels // (s * s)
+        self.key, self.pc = None, None
+
+    def packed(self):
+        w, b = effective_weight(self.m)
+        key = (_tensor_key(w), _tensor_key(b))
+        if key != self.key:
+            if self.pc is None:
+                self.pc = ops.PackedConv(w, b, self.s)
+            else:
+                self.pc.repack(w, b)
+            self.key = key
+        return self.pc
+
+
+def _upconv_slot(conv):
+    """(slot) for an UpConv / DownConv wrapper in one of the accelerated forms."""
+    if isinstance(conv, UpConv):
+        if conv.kind not in ("pshuffel", "pshuffel_3x3"):
+            raise Unsupported(f"UpConv conv_type {conv.kind!r} (no shipped script selects it)")
+        shuffle = conv.upconv[1]
+        s = shuffle.upscale_factor if isinstance(shuffle, nn.PixelShuffle) else 1
+        return _ConvSlot(conv.upconv[0], s)
+    if isinstance(conv, DownConv):
+        if conv.kind != "conv":
+            raise Unsupported(f"DownConv conv_type {conv.kind!r}")
+        return _ConvSlot(conv.downconv, 1)      # HNeRV_Boost decoder[0]: 1x1, stride 1 (model_blocks.py:185)
+    if isinstance(conv, nn.Conv2d):
+        return _ConvSlot(conv, 1)
+    raise Unsupported(f"unknown conv wrapper {type(conv).__name__}")
+
+
+class _BlockPlan:
+    def __init__(self, blk):
+        if not isinstance(blk.norm, nn.Identity):
+            raise Unsupported("norm layers other than 'none' are not accelerated (no shipped script selects them)")
+        self.act = act_name(blk.act)
+        if self.act is None:
+            raise Unsupported(f"activation {blk.act} is not accelerated")
+        if isinstance(blk, Conv_Up_Block):
+            self.pre = _upconv_slot(blk.conv1)
+            self.up = _upconv_slot(blk.conv2)
+        elif isinstance(blk, NeRVBlock):
+            if not blk.dec_block:
+                raise Unsupported("NeRVBlock without dec_block (un-boosted HNeRV stem) is out of scope")
+            self.pre = None
+            self.up = _upconv_slot(blk.conv)
+        else:
+            raise Unsupported(f"block type {type(blk).__name__}")
+        rb = blk.sft_block
+        self.inner_act = act_name(rb.act)
+        if self.inner_act is None:
+            raise Unsupported(f"activation {rb.act} is not accelerated")
+        self.c0, self.c1 = _ConvSlot(rb.conv0), _ConvSlot(rb.conv1)
+        self.sfts = [rb.sft0, rb.sft1]
+        for sft in self.sfts:
+            if act_name(sft.act) != "relu":
+                raise Unsupported("SFT inner activation other than relu")
+        self.cout = self.up.cout
+        self.scale = (self.pre.s if self.pre else 1) * self.up.s
+
+
+def _sft_tensors(sft):
+    """The eight effective tensors of one SFTLayer in bnerv_sft_layer order (raw, for identity keys)."""
+    out = []
+    for conv in (sft.SFT_scale_conv0, sft.SFT_scale_conv1, sft.SFT_shift_conv0, sft.SFT_shift_conv1):
+        out += list(effective_weight(conv))
+    return out
+
+
+class DecoderEngine:
+    def __init__(self, model):
+        self.model = model
+        name = type(model).__name__
+        if name == "HNeRV_Boost":
+            blocks, self.t_mlp = list(model.decoder), model.stem_t
+        elif name in ("NeRV_Boost", "ENeRV_Boost"):
+            blocks, self.t_mlp = list(model.layers), (model.stem_t if name == "NeRV_Boost" else None)
+        else:
+            raise Unsupported(f"model {name}")
+        if model.out_bias != "tanh":
+            raise Unsupported(f"out_bias {model.out_bias!r}: only 'tanh' is accelerated")
+        self.blocks = [_BlockPlan(b) for b in blocks]
+        self.head = _ConvSlot(model.head_layer)
+        self._ws = {}          # workspaces per (B, h, w)
+        self._sft = {}         # SftTable per B
+        self._sft_key = None
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _mlp(self, seq, x):
+        """NeRV_MLP on a [B, C] vector (1x1 convs + activation after every layer), model_blocks.py:66-71."""
+        mods = list(seq)
+        i = 0
+        while i < len(mods):
+            conv = mods[i]
+            act = act_name(mods[i + 1]) if i + 1 < len(mods) else "none"
+            if not isinstance(conv, nn.Conv2d) or conv.kernel_size != (1, 1) or act is None:
+                raise Unsupported(f"stem layer {conv} / {mods[i + 1] if i + 1 < len(mods) else None}")
+            w, b = effective_weight(conv)
+            x = ops.linear_act(x, w.detach().contiguous(), None if b is None else b.detach(), act)
+            i += 2
+        return x
+
+    def _sft_table(self, B, device):
+        tensors = [_sft_tensors(s) for blk in self.blocks for s in blk.sfts]
+        key = tuple(_tensor_key(t) for l in tensors for t in l)
+        if key != self._sft_key:
+            self._sft.clear()
+            self._sft_key = key
+        tab = self._sft.get(B)
+        if tab is None:
+            tab = ops.SftTable([tuple(t.detach().reshape(t.shape[0], -1).contiguous().float() if t.dim() == 4
+                                      else t.detach().contiguous().float() for t in l) for l in tensors], B, device)
+            self._sft[B] = tab
+        return tab
+
+    def _workspace(self, B, h, w, device):
+        ws = self._ws.get((B, h, w))
+        if ws is None:
+            sizes = {"cur": 0, "x0": 0, "u": 0, "w": 0, "nxt": 0}
+            H, W = h, w
+            for blk in self.blocks:
+                if blk.pre is not None:
+                    H, W = H * blk.pre.s, W * blk.pre.s
+                    sizes["w"] = max(sizes["w"], B * ops.round_up(blk.pre.cout, 16) * H * W)
+                H, W = H * blk.up.s, W * blk.up.s
+                n = B * ops.round_up(blk.cout, 16) * H * W
+                for kname in ("cur", "x0", "u", "w", "nxt"):
+                    sizes[kname] = max(sizes[kname], n)
+            ws = {kname: torch.empty(max(n, 8), dtype=torch.float16, device=device) for kname, n in sizes.items()}
+            ws["out_hw"] = (H, W)
+            self._ws[(B, h, w)] = ws
+        return ws
+
+    # -- entry points ------------------------------------------------------------------------------
+    def run_hnerv(self, img_embed, pe, keep=False):
+        """HNeRV_Boost.forward_decoder body (model_hnerv.py:264-277)."""
+        t_embed = self._mlp(self.t_mlp, pe.flatten(1).float())
+        return self.run_cascade(img_embed.float().contiguous(), t_embed, keep)
+
+    def run_nerv(self, pe, keep=False):
+        """NeRV_Boost.forward body after the position encoding (model_nerv.py:48-57)."""
+        m = self.model
+        v = pe.flatten(1).float()
+        x = self._mlp(m.stem, v).view(v.size(0), m.fc_dim, m.fc_h, m.fc_w)
+        t_embed = self._mlp(m.stem_t, v)
+        return self.run_cascade(x, t_embed, keep)
+
+    def run_cascade(self, x, t_embed, keep=False):
+        """x: [B, C, h, w] f32 NCHW stem output; t_embed: [B, ch_t] f32.  Returns (img, [block outputs]).
+        keep: True = every block output as NCHW f32, "first" = only block 0's, False = none."""
+        if not x.is_cuda:
+            raise RuntimeError("bnerv_b200 engine needs CUDA tensors (no CPU path)")
+        B, C, h, w = x.shape
+        dev = x.device
+        ws = self._workspace(B, h, w, dev)
+        tab = self._sft_table(B, dev)
+        tab.run(t_embed)
+
+        def view(buf, c, H, W):
+            shp = ops.c8_shape(B, c, H, W)
+            return buf[:shp[0] * shp[1] * shp[2] * shp[3] * shp[4]].view(shp)
+
+        cur_buf, nxt_buf = ws["cur"], ws["nxt"]
+        cur = ops.nchw_to_c8(x)
+        cin, H, W = C, h, w
+        outs = []
+        for bi, blk in enumerate(self.blocks):
+            g0, b0 = tab.g1p[2 * bi], tab.beta[2 * bi]
+            g1, b1 = tab.g1p[2 * bi + 1], tab.beta[2 * bi + 1]
+            if blk.pre is not None:         # E-NeRV stage 0: conv1 (no activation) feeds conv2
+                mid = view(ws["w"], blk.pre.cout, H * blk.pre.s, W * blk.pre.s)
+                ops.conv_fused(cur, blk.pre.packed(), cin, H, W, act="none", out_pre=mid)
+                cur, cin, H, W = mid, blk.pre.cout, H * blk.pre.s, W * blk.pre.s
+            Ho, Wo = H * blk.up.s, W * blk.up.s
+            x0 = view(ws["x0"], blk.cout, Ho, Wo)
+            u = view(ws["u"], blk.cout, Ho, Wo)
+            ops.conv_fused(cur, blk.up.packed(), cin, H, W, act=blk.act, g1p=g0, beta=b0, out_pre=x0, out_aff=u)
+            wbuf = view(ws["w"], blk.cout, Ho, Wo)
+            ops.conv_fused(u, blk.c0.packed(), blk.cout, Ho, Wo, act=blk.inner_act, g1p=g1, beta=b1, out_aff=wbuf)
+            out = view(nxt_buf, blk.cout, Ho, Wo)
+            ops.conv_fused(wbuf, blk.c1.packed(), blk.cout, Ho, Wo, act="none", resid=x0, out_pre=out)
+            if keep is True or (keep == "first" and bi == 0):
+                outs.append(ops.c8_to_nchw(out, blk.cout))
+            cur, cin, H, W = out, blk.cout, Ho, Wo
+            cur_buf, nxt_buf = nxt_buf, cur_buf
+        img = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+        ops.conv_fused(cur, self.head.packed(), cin, H, W, act="tanh01", out_nchw=img)
+        return img, outs

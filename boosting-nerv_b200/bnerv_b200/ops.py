@@ -1,0 +1,157 @@
+"""Thin torch-tensor wrappers over the C-ABI (one function per entry point of include/bnerv_b200.h).
+
+torch is used for device memory and the current stream only; every computation below happens inside
+libbnerv_b200.so.  All functions raise on CPU tensors — there is no fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _capi
+from ._capi import ACT_CODES, lib, check, ptr
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("bnerv_b200 ops need CUDA tensors (no CPU path)")
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def c8_shape(B, C, H, W):
+    return (B, round_up(C, 16) // 8, H, W, 8)
+
+
+def nchw_to_c8(x):
+    """[B,C,H,W] f32 -> C8 f16 tensor of shape [B, Cp/8, H, W, 8]."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 4
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    y = torch.empty(c8_shape(B, C, H, W), dtype=torch.float16, device=x.device)
+    check("bnerv_nchw_to_c8", lib.bnerv_nchw_to_c8(ptr(x), B, C, H, W, ptr(y), _stream()))
+    return y
+
+
+def c8_to_nchw(y, C):
+    _need_cuda(y)
+    assert y.dtype == torch.float16 and y.dim() == 5 and y.is_contiguous()
+    B, _, H, W, _ = y.shape
+    x = torch.empty((B, C, H, W), dtype=torch.float32, device=y.device)
+    check("bnerv_c8_to_nchw", lib.bnerv_c8_to_nchw(ptr(y), B, C, H, W, ptr(x), _stream()))
+    return x
+
+
+def pixel_shuffle(x, s):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 4
+    x = x.contiguous()
+    B, Cs, H, W = x.shape
+    assert Cs % (s * s) == 0
+    C = Cs // (s * s)
+    y = torch.empty((B, C, H * s, W * s), dtype=torch.float32, device=x.device)
+    check("bnerv_pixel_shuffle", lib.bnerv_pixel_shuffle(ptr(x), B, C, H, W, s, ptr(y), _stream()))
+    return y
+
+
+class PackedConv:
+    """Kernel-layout copy of one conv's effective weight: f16 [taps][Kp/8][Np][8] + f32 bias [Np]."""
+
+    def __init__(self, weight, bias, s=1):
+        _need_cuda(weight, bias)
+        co_s2, self.cin, k, k2 = weight.shape
+        assert k == k2 and co_s2 % (s * s) == 0
+        self.k, self.s, self.cout = k, s, co_s2 // (s * s)
+        dev = weight.device
+        self.w = torch.empty(lib.bnerv_packed_weight_numel(self.cout, self.cin, k, s), dtype=torch.float16, device=dev)
+        self.b = torch.empty(lib.bnerv_packed_bias_numel(self.cout, s), dtype=torch.float32, device=dev)
+        self.repack(weight, bias)
+
+    def repack(self, weight, bias):
+        w = weight.detach().contiguous().float()
+        b = None if bias is None else bias.detach().contiguous().float()
+        check("bnerv_pack_conv_weight",
+              lib.bnerv_pack_conv_weight(ptr(w), ptr(b), self.cout, self.cin, self.k, self.s, ptr(self.w), ptr(self.b), _stream()))
+
+
+def conv_fused(x_c8, pc, cin, H, W, act="none", resid=None, g1p=None, beta=None, out_pre=None, out_aff=None,
+               out_nchw=None):
+    """Launch the tcgen05 fused conv.  Output tensors are caller-provided (see bnerv_conv_fused)."""
+    _need_cuda(x_c8)
+    B = x_c8.shape[0]
+    assert cin == pc.cin
+    check("bnerv_conv_fused",
+          lib.bnerv_conv_fused(ptr(x_c8), B, cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, pc.k, pc.s, ACT_CODES[act],
+                               ptr(resid), ptr(g1p), ptr(beta), ptr(out_pre), ptr(out_aff), ptr(out_nchw), _stream()))
+
+
+def conv_fused_f32(x, weight, bias, s=1, act="none", resid=None, g1p=None, beta=None, want_pre=True):
+    """f32 CUDA-core fused conv on NCHW / OIHW.  Returns (out_pre or None, out_aff or None)."""
+    _need_cuda(x, weight)
+    x, weight = x.contiguous(), weight.contiguous()
+    B, cin, H, W = x.shape
+    co_s2, cin_w, k, _ = weight.shape
+    assert cin_w == cin
+    cout = co_s2 // (s * s)
+    out_pre = torch.empty((B, cout, H * s, W * s), dtype=torch.float32, device=x.device) if want_pre else None
+    out_aff = torch.empty((B, cout, H * s, W * s), dtype=torch.float32, device=x.device) if g1p is not None else None
+    ldg = 0 if g1p is None else g1p.shape[-1]
+    check("bnerv_conv_fused_f32",
+          lib.bnerv_conv_fused_f32(ptr(x), B, cin, H, W, ptr(weight), ptr(bias), cout, k, s, ACT_CODES[act], ptr(resid),
+                                   ptr(g1p), ptr(beta), ldg, ptr(out_pre), ptr(out_aff), _stream()))
+    return out_pre, out_aff
+
+
+def linear_act(x, weight, bias, act="none"):
+    """y = act(W x + b); x [B,Cin] f32, weight [Cout,Cin(,1,1)] f32."""
+    _need_cuda(x, weight)
+    x = x.contiguous()
+    B, cin = x.shape
+    cout = weight.shape[0]
+    assert weight.numel() == cout * cin and weight.is_contiguous()
+    y = torch.empty((B, cout), dtype=torch.float32, device=x.device)
+    check("bnerv_linear_act", lib.bnerv_linear_act(ptr(x), B, cin, ptr(weight), ptr(bias), cout, ACT_CODES[act], ptr(y), _stream()))
+    return y
+
+
+class SftTable:
+    """Device-side array of bnerv_sft_layer descriptors + the g1p/beta output tables for a batch size."""
+
+    def __init__(self, layers, B, device):
+        """layers: list of (ws0, bs0, ws1, bs1, wh0, bh0, wh1, bh1) f32 CUDA tensors."""
+        self.B = B
+        self.keep = layers
+        self.C = [l[2].shape[0] for l in layers]
+        self.Cp = [round_up(c, 16) for c in self.C]
+        self.ch_t = layers[0][0].shape[1]
+        offs, tot = [], 0
+        for cp in self.Cp:
+            offs.append(tot)
+            tot += B * cp
+        self.g1p_all = torch.empty(max(tot, 1), dtype=torch.float32, device=device)
+        self.beta_all = torch.empty(max(tot, 1), dtype=torch.float32, device=device)
+        self.g1p = [self.g1p_all[o:o + B * cp].view(B, cp) for o, cp in zip(offs, self.Cp)]
+        self.beta = [self.beta_all[o:o + B * cp].view(B, cp) for o, cp in zip(offs, self.Cp)]
+        arr = (_capi.SftLayer * len(layers))()
+        for i, l in enumerate(layers):
+            for name, t in zip(("ws0", "bs0", "ws1", "bs1", "wh0", "bh0", "wh1", "bh1"), l):
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                setattr(arr[i], name, t.data_ptr())
+            arr[i].g1p, arr[i].beta = self.g1p[i].data_ptr(), self.beta[i].data_ptr()
+            arr[i].C, arr[i].Cp = self.C[i], self.Cp[i]
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.desc = host.to(device)
+
+    def run(self, e):
+        """e: [B, ch_t] f32.  Fills every layer's g1p/beta with one launch."""
+        _need_cuda(e)
+        e = e.contiguous()
+        assert e.shape == (self.B, self.ch_t)
+        check("bnerv_sft_affine", lib.bnerv_sft_affine(ptr(self.desc), len(self.C), ptr(e), self.B, self.ch_t, _stream()))

@@ -1,0 +1,191 @@
+// Shared device helpers for the bnerv_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/bnerv_b200.h"
+
+namespace bnerv {
+
+// ---------------------------------------------------------------------------------------------
+// host-side error plumbing (definitions in capi.cu)
+// ---------------------------------------------------------------------------------------------
+int  set_error(int code, const char* fmt, ...);
+int  check_launch(const char* what);      // cudaGetLastError -> return code (+ bumps launch counter)
+void count_launch();
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------------
+// epilogue math.  All in f32; accuracy targets are << the 1e-3 parity budget.
+// ---------------------------------------------------------------------------------------------
+// sin with explicit two-constant Cody-Waite reduction to [-pi, pi] followed by MUFU.SIN
+// (abs error 2^-21.4 on that interval).  Pre-activations are O(1..1e3); k stays exact in f32.
+__device__ __forceinline__ float fast_sin(float x) {
+    const float inv2pi = 0.15915494309189535f;
+    const float c_hi   = 6.2831854820251465f;        // float(2*pi)
+    const float c_lo   = -1.7484555314695172e-07f;   // 2*pi - c_hi
+    float k = rintf(x * inv2pi);
+    float r = fmaf(-k, c_hi, x);
+    r = fmaf(-k, c_lo, r);
+    return __sinf(r);
+}
+
+// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), branch-free: 2 MUFU + ~10 FMA.
+__device__ __forceinline__ float fast_erf(float x) {
+    float ax = fabsf(x);
+    float t  = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float p  = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    float e = __expf(-ax * ax);
+    float r = fmaf(-p, e, 1.0f);
+    return copysignf(r, x);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {       // nn.GELU() default (exact erf form)
+    return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
+}
+
+__device__ __forceinline__ float tanh01(float x) {         // OutImg 'tanh': tanh(x)*0.5+0.5 == sigmoid(2x)
+    float xc = fminf(fmaxf(x, -15.0f), 15.0f);
+    float e  = __expf(-2.0f * xc);
+    return __fdividef(1.0f, 1.0f + e);
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    switch (act) {
+        case BNERV_ACT_SIN:    return fast_sin(x);
+        case BNERV_ACT_GELU:   return gelu_erf(x);
+        case BNERV_ACT_RELU:   return fmaxf(x, 0.0f);
+        case BNERV_ACT_TANH01: return tanh01(x);
+        default:               return x;
+    }
+}
+
+// precise variants for the f32 cross-check kernel (libdevice sinf/erff/tanhf)
+__device__ __forceinline__ float apply_act_precise(float x, int act) {
+    switch (act) {
+        case BNERV_ACT_SIN:    return sinf(x);
+        case BNERV_ACT_GELU:   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+        case BNERV_ACT_RELU:   return fmaxf(x, 0.0f);
+        case BNERV_ACT_TANH01: return tanhf(x) * 0.5f + 0.5f;
+        default:               return x;
+    }
+}
+
+// saturating f32x2 -> f16x2 (never produces inf from a finite f32)
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+    lo = fminf(fmaxf(lo, -65504.0f), 65504.0f);
+    hi = fminf(fmaxf(hi, -65504.0f), 65504.0f);
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t v) {
+    __half2 h = *reinterpret_cast<__half2*>(&v);
+    return __half22float2(h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier, TMA, tcgen05
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a pipeline bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a
+// hung GPU.  ~2 s at 2 GHz.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {   // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {    // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], f16 operands, f32 accumulate.  One thread issues.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 16 consecutive f32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, K-major, no swizzle ("interleave" canonical layout):
+//   core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes;
+//   LBO = byte distance between core matrices adjacent in K, SBO = between 8-row groups in M/N.
+// (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor; version field = 1 on sm_100.)
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswz(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4)
+         | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16)
+         | (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32)
+         | (1ull << 46);
+}
+// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n (cute UMMA::InstrDescriptor)
+__device__ __host__ __forceinline__ uint32_t umma_idesc_f16_m128(int n) {
+    return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+}  // namespace bnerv

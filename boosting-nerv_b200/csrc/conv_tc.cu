@@ -1,0 +1,426 @@
+// Fused implicit-GEMM conv for sm_100a: TMA-staged halo tiles -> tcgen05.mma (f16 x f16 -> f32 in TMEM)
+// -> in-register epilogue (bias, sin/GELU, residual, TAT affine, PixelShuffle addressing) -> 16-byte
+// vector stores.  Replaces CustomConv2d.forward + PixelShuffle + Sin/GELU + SFTLayer affine + residual
+// (lib/quant_ops.py:39-41, model_blocks.py:37,86-89,105,204,217) with one launch.
+//
+// GEMM view (per image):  D[pixels, n'] = sum_{tap, c} X[pixel + tap, c] * Wp[tap][c][n']
+//   M: a CTA works on a 16-row x 16-col pixel super-tile = MT(2) UMMA tiles of 16 rows x 8 cols (M=128)
+//   N: N_ACC <= 128 packed output rows per CTA (n' = PixelShuffle-major, see bnerv_b200.h)
+//   K: 9 taps x Cin_p channels, consumed 16 channels (one UMMA K step) per pipeline stage.
+//
+// Shared-memory operand layout is the UMMA "no-swizzle, K-major" canonical form: a core matrix is
+// 8 rows x 16 B = 128 contiguous bytes.  The activation layout in HBM ([Cp/8][H][W][8] f16) makes one
+// TMA box {18 px, 18 rows, 2 channel groups} land as [group][row][px][16 B]: 8 neighbouring pixels of
+// one image row ARE a core matrix, so the A operand of tap (r,s) is simply the same halo tile read
+// at start address + (r*18 + s)*16 B with SBO = one halo row (288 B).  The halo tile is fetched once
+// and reused by all 9 taps (no im2col materialisation, no 9x re-fetch).
+//
+// Warp roles (320 threads): warp 0 = TMA producer (1 lane), warp 1 = TMEM owner + MMA issuer (1 lane),
+// warps 2..9 = epilogue (two groups of 4 warps, one group per UMMA tile; warp%4 selects its TMEM lane
+// quarter).  Two TMEM accumulator buffers (2 x 2 x 128 columns = all 512) let the epilogue of tile i
+// overlap the MMAs of tile i+1.  Persistent grid: one CTA per SM, static round-robin tile order.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace bnerv {
+
+constexpr int MT          = 2;                    // UMMA tiles (128 px each) per CTA super-tile
+constexpr int TILE_H      = 16;                   // pixel rows per super-tile
+constexpr int TILE_W      = 8 * MT;               // pixel cols per super-tile
+constexpr int HALO_W      = TILE_W + 2;           // 18
+constexpr int HALO_H      = TILE_H + 2;           // 18
+constexpr int A_GROUP_B   = HALO_H * HALO_W * 16; // bytes of one 8-channel group of the halo tile (5184)
+constexpr int A_STAGE_B   = 2 * A_GROUP_B;        // one K step = 16 channels = 2 groups (10368, 128-aligned)
+constexpr int ACC_COLS    = 128;                  // TMEM columns reserved per accumulator
+constexpr int TMEM_COLS   = 512;
+constexpr int N_EPI_WARPS = 4 * MT;
+constexpr int N_THREADS   = 64 + 32 * N_EPI_WARPS;
+constexpr int MAX_STAGES  = 8;
+constexpr int SMEM_LIMIT  = 227 * 1024;
+
+struct ConvTcArgs {
+    int B, H, W;            // conv-resolution geometry (input == pre-shuffle output)
+    int cin_groups;         // Cin_p / 8
+    int ksteps;             // Cin_p / 16
+    int taps;               // 1 or 9
+    int n_total;            // s*s*Cout_p
+    int n_acc;              // packed rows per CTA (multiple of 16, <= 128)
+    int n_tiles;            // ceil(n_total / n_acc)
+    int cout, cout_p;       // real / padded output channels
+    int s;                  // PixelShuffle factor
+    int act;
+    int tiles_x, tiles_y;
+    int total_tiles;
+    int stages;
+    int b_stage_bytes;      // taps * 2 * n_acc * 16
+    const float* bias;      // [n_total]
+    const float* g1p;       // [B][cout_p] or null
+    const float* beta;      // [B][cout_p] or null
+    const __half* resid;    // C8 at output resolution or null
+    __half* out_pre;        // C8 or null
+    __half* out_aff;        // C8 or null
+    float* out_nchw;        // NCHW f32 or null
+};
+
+struct TileCoord { int n0, b, h0, w0; };
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcArgs& a, int tile) {
+    TileCoord t;
+    int nt   = tile % a.n_tiles;
+    int rest = tile / a.n_tiles;
+    int tx   = rest % a.tiles_x;
+    rest /= a.tiles_x;
+    int ty = rest % a.tiles_y;
+    t.b    = rest / a.tiles_y;
+    t.n0   = nt * a.n_acc;
+    t.h0   = ty * TILE_H;
+    t.w0   = tx * TILE_W;
+    return t;
+}
+
+__global__ void __launch_bounds__(N_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int stage_bytes = A_STAGE_B + a.b_stage_bytes;
+    uint8_t* bar_base     = smem + static_cast<size_t>(a.stages) * stage_bytes;
+    uint64_t* full_bar    = reinterpret_cast<uint64_t*>(bar_base);
+    uint64_t* empty_bar   = full_bar + MAX_STAGES;
+    uint64_t* tfull_bar   = empty_bar + MAX_STAGES;   // [2]
+    uint64_t* tempty_bar  = tfull_bar + 2;            // [2]
+    uint32_t* tmem_slot   = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.stages; ++i) {
+            mbar_init(smem_u32(&full_bar[i]), 1);
+            mbar_init(smem_u32(&empty_bar[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&tfull_bar[i]), 1);
+            mbar_init(smem_u32(&tempty_bar[i]), N_EPI_WARPS);
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = A_STAGE_B + a.b_stage_bytes;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(a, tile);
+                for (int kc = 0; kc < a.ksteps; ++kc) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    mbar_expect_tx(fb, tx_bytes);
+                    // activations viewed as u64 elements: 2 per pixel-group -> x coordinate = 2*w
+                    tma_load_3d(sa, &tmA, fb, 2 * (t.w0 - 1), t.h0 - 1, t.b * a.cin_groups + 2 * kc);
+                    tma_load_3d(sa + A_STAGE_B, &tmB, fb, 2 * t.n0, 2 * kc, 0);
+                    if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int abuf = 0;
+            uint32_t aphase = 0;
+            const uint32_t idesc     = umma_idesc_f16_m128(a.n_acc);
+            const uint32_t b_tap_b   = 2u * a.n_acc * 16u;      // bytes of one tap's [2 groups][n_acc][16B]
+            const uint32_t b_lbo     = a.n_acc * 16u;
+            // 1x1 conv: the single tap reads the centre of the halo tile
+            const int tap_lo = (a.taps == 1) ? 4 : 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                mbar_wait(smem_u32(&tempty_bar[abuf]), aphase ^ 1);
+                tc_fence_after();
+                for (int kc = 0; kc < a.ksteps; ++kc) {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * stage_bytes;
+                    const uint32_t sb = sa + A_STAGE_B;
+                    for (int tp = 0; tp < a.taps; ++tp) {
+                        const int tap = tp + tap_lo;
+                        const int r = tap / 3, s = tap - 3 * r;
+                        const uint64_t bdesc = umma_desc_kmajor_noswz(sb + tp * b_tap_b, b_lbo, 128u);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint32_t a_addr = sa + (r * HALO_W + s + mt * 8) * 16;
+                            const uint64_t adesc  = umma_desc_kmajor_noswz(a_addr, A_GROUP_B, HALO_W * 16);
+                            umma_f16(tmem_base + (abuf * MT + mt) * ACC_COLS, adesc, bdesc, idesc,
+                                     (kc > 0 || tp > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(smem_u32(&empty_bar[stage]));
+                    if (kc == a.ksteps - 1) umma_commit(smem_u32(&tfull_bar[abuf]));
+                    if (++stage == a.stages) { stage = 0; phase ^= 1; }
+                }
+                abuf ^= 1;
+                if (abuf == 0) aphase ^= 1;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue =====================
+        const int e  = warp - 2;
+        const int mt = e >> 2;
+        const int q  = warp & 3;                     // TMEM lane quarter this warp may access
+        const int m  = q * 32 + lane;                // row of the UMMA tile == pixel
+        int abuf = 0;
+        uint32_t aphase = 0;
+        const int s  = a.s;
+        const int Ho = a.H * s, Wo = a.W * s;
+        const int cout_groups = a.cout_p >> 3;
+        const bool has_aff = (a.g1p != nullptr);
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(a, tile);
+            const int h = t.h0 + (m >> 3);
+            const int w = t.w0 + mt * 8 + (m & 7);
+            const bool valid = (h < a.H) && (w < a.W);
+            // packed-row bookkeeping of the first group handled by this CTA
+            int sub = t.n0 / a.cout_p;               // PixelShuffle sub-position index i*s+j
+            int cc  = t.n0 - sub * a.cout_p;         // channel within the sub-position block
+
+            // Residual prefetch: issued before waiting for the accumulator so the HBM latency hides
+            // behind the MMAs of this tile.
+            uint4 rres[ACC_COLS / 8];
+            if (a.resid != nullptr) {
+                int sub2 = sub, cc2 = cc;
+#pragma unroll
+                for (int g = 0; g < ACC_COLS / 8; ++g) {
+                    rres[g] = make_uint4(0, 0, 0, 0);
+                    if (g * 8 < a.n_acc && t.n0 + g * 8 < a.n_total) {
+                        const int i = sub2 / s, j = sub2 - i * s;
+                        if (valid) {
+                            const size_t off = ((static_cast<size_t>(t.b * cout_groups + (cc2 >> 3)) * Ho + (h * s + i)) * Wo + (w * s + j)) * 8;
+                            rres[g] = __ldg(reinterpret_cast<const uint4*>(a.resid + off));
+                        }
+                        cc2 += 8;
+                        if (cc2 >= a.cout_p) { cc2 = 0; ++sub2; }
+                    }
+                }
+            }
+
+            mbar_wait(smem_u32(&tfull_bar[abuf]), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (abuf * MT + mt) * ACC_COLS;
+
+#pragma unroll
+            for (int g16 = 0; g16 < ACC_COLS / 16; ++g16) {
+                if (g16 * 16 < a.n_acc && t.n0 + g16 * 16 < a.n_total) {     // CTA-uniform
+                    uint32_t v[16];
+                    tmem_ld16(taddr + g16 * 16, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int g  = g16 * 2 + hh;
+                        const int nn = t.n0 + g * 8;                          // packed row of element 0
+                        const int i = sub / s, j = sub - i * s;
+                        const int ho = h * s + i, wo = w * s + j;
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + nn));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + nn + 4));
+                        float x[8];
+                        x[0] = __uint_as_float(v[hh * 8 + 0]) + b0.x;
+                        x[1] = __uint_as_float(v[hh * 8 + 1]) + b0.y;
+                        x[2] = __uint_as_float(v[hh * 8 + 2]) + b0.z;
+                        x[3] = __uint_as_float(v[hh * 8 + 3]) + b0.w;
+                        x[4] = __uint_as_float(v[hh * 8 + 4]) + b1.x;
+                        x[5] = __uint_as_float(v[hh * 8 + 5]) + b1.y;
+                        x[6] = __uint_as_float(v[hh * 8 + 6]) + b1.z;
+                        x[7] = __uint_as_float(v[hh * 8 + 7]) + b1.w;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) x[k] = apply_act(x[k], a.act);
+                        if (a.resid != nullptr) {
+                            const float2 r0 = unpack_h2(rres[g].x), r1 = unpack_h2(rres[g].y);
+                            const float2 r2 = unpack_h2(rres[g].z), r3 = unpack_h2(rres[g].w);
+                            x[0] += r0.x; x[1] += r0.y; x[2] += r1.x; x[3] += r1.y;
+                            x[4] += r2.x; x[5] += r2.y; x[6] += r3.x; x[7] += r3.y;
+                        }
+                        if (valid) {
+                            const size_t off = ((static_cast<size_t>(t.b * cout_groups + (cc >> 3)) * Ho + ho) * Wo + wo) * 8;
+                            if (a.out_pre != nullptr) {
+                                uint4 o;
+                                o.x = pack_h2_sat(x[0], x[1]); o.y = pack_h2_sat(x[2], x[3]);
+                                o.z = pack_h2_sat(x[4], x[5]); o.w = pack_h2_sat(x[6], x[7]);
+                                *reinterpret_cast<uint4*>(a.out_pre + off) = o;
+                            }
+                            if (a.out_nchw != nullptr) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const int ch = cc + k;
+                                    if (ch < a.cout)
+                                        a.out_nchw[(static_cast<size_t>(t.b * a.cout + ch) * Ho + ho) * Wo + wo] = x[k];
+                                }
+                            }
+                            if (has_aff) {
+                                const float* gp = a.g1p + static_cast<size_t>(t.b) * a.cout_p + cc;
+                                const float* bp = a.beta + static_cast<size_t>(t.b) * a.cout_p + cc;
+                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
+                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + 4));
+                                const float4 e0 = __ldg(reinterpret_cast<const float4*>(bp));
+                                const float4 e1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+                                uint4 o;
+                                o.x = pack_h2_sat(fmaf(x[0], g0.x, e0.x), fmaf(x[1], g0.y, e0.y));
+                                o.y = pack_h2_sat(fmaf(x[2], g0.z, e0.z), fmaf(x[3], g0.w, e0.w));
+                                o.z = pack_h2_sat(fmaf(x[4], g1.x, e1.x), fmaf(x[5], g1.y, e1.y));
+                                o.w = pack_h2_sat(fmaf(x[6], g1.z, e1.z), fmaf(x[7], g1.w, e1.w));
+                                *reinterpret_cast<uint4*>(a.out_aff + off) = o;
+                            }
+                        }
+                        cc += 8;
+                        if (cc >= a.cout_p) { cc = 0; ++sub; }
+                    }
+                }
+            }
+            // all TMEM reads of this warp for this buffer are complete -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[abuf]));
+            abuf ^= 1;
+            if (abuf == 0) aphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+static int make_map_u64_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                           uint64_t stride1_b, uint64_t stride2_b, uint32_t b0, uint32_t b1, uint32_t b2) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return set_error(BNERV_E_NODRIVER, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3]    = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_b, stride2_b};
+    cuuint32_t box[3]     = {b0, b1, b2};
+    cuuint32_t estr[3]    = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(static_cast<int>(r), "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+    return 0;
+}
+
+static int g_num_sms = 0;
+
+int choose_n_acc(int n_total) {
+    // fewest N tiles with N_ACC <= 128, then the smallest multiple of 16 that covers them evenly
+    int tiles = (n_total + 127) / 128;
+    int per   = (n_total + tiles - 1) / tiles;
+    return round_up(per, 16);
+}
+
+}  // namespace bnerv
+
+using namespace bnerv;
+
+extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, const void* w_packed,
+                                const float* bias_packed, int Cout, int k, int s, int act, const void* resid,
+                                const float* g1p, const float* beta, void* out_pre, void* out_aff, float* out_nchw,
+                                void* stream) {
+    if (!x || !w_packed || !bias_packed) return set_error(BNERV_E_BADARG, "conv_fused: null operand");
+    if (B <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || s <= 0) return set_error(BNERV_E_BADARG, "conv_fused: non-positive size");
+    if (k != 1 && k != 3) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: kernel size %d (only 1 and 3)", k);
+    if ((g1p == nullptr) != (beta == nullptr)) return set_error(BNERV_E_BADARG, "conv_fused: g1p and beta must both be given");
+    if ((g1p != nullptr) != (out_aff != nullptr)) return set_error(BNERV_E_BADARG, "conv_fused: out_aff requires g1p/beta and vice versa");
+    if (!out_pre && !out_aff && !out_nchw) return set_error(BNERV_E_BADARG, "conv_fused: no output");
+    if (act < BNERV_ACT_NONE || act > BNERV_ACT_TANH01) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: act %d", act);
+    const uintptr_t align_or = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) |
+                               reinterpret_cast<uintptr_t>(bias_packed) | reinterpret_cast<uintptr_t>(resid) |
+                               reinterpret_cast<uintptr_t>(g1p) | reinterpret_cast<uintptr_t>(beta) |
+                               reinterpret_cast<uintptr_t>(out_pre) | reinterpret_cast<uintptr_t>(out_aff);
+    if (align_or & 15) return set_error(BNERV_E_BADARG, "conv_fused: pointers must be 16-byte aligned");
+
+    const int cin_p = round_up(Cin, 16), cout_p = round_up(Cout, 16);
+    ConvTcArgs a{};
+    a.B = B; a.H = H; a.W = W;
+    a.cin_groups = cin_p / 8;
+    a.ksteps     = cin_p / 16;
+    a.taps       = k * k;
+    a.n_total    = s * s * cout_p;
+    a.n_acc      = choose_n_acc(a.n_total);
+    a.n_tiles    = (a.n_total + a.n_acc - 1) / a.n_acc;
+    a.cout = Cout; a.cout_p = cout_p; a.s = s; a.act = act;
+    a.tiles_x = (W + TILE_W - 1) / TILE_W;
+    a.tiles_y = (H + TILE_H - 1) / TILE_H;
+    const long long total = 1LL * a.n_tiles * B * a.tiles_x * a.tiles_y;
+    if (total > 0x7fffffffLL) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: too many tiles");
+    a.total_tiles   = static_cast<int>(total);
+    a.b_stage_bytes = a.taps * 2 * a.n_acc * 16;
+    const int stage_bytes = A_STAGE_B + a.b_stage_bytes;
+    const int bar_bytes   = (2 * MAX_STAGES + 4) * 8 + 16;
+    int stages = (SMEM_LIMIT - bar_bytes - 1024) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: stage of %d bytes does not fit twice", stage_bytes);
+    a.stages = stages;
+    a.bias = bias_packed; a.g1p = g1p; a.beta = beta;
+    a.resid = static_cast<const __half*>(resid);
+    a.out_pre = static_cast<__half*>(out_pre);
+    a.out_aff = static_cast<__half*>(out_aff);
+    a.out_nchw = out_nchw;
+
+    CUtensorMap tmA, tmB;
+    // activations as u64: dims {2W, H, B*cin_groups}; strides {W*16, H*W*16} bytes
+    int rc = make_map_u64_3d(&tmA, x, 2ull * W, H, 1ull * B * a.cin_groups, 16ull * W, 16ull * W * H,
+                             2 * HALO_W, HALO_H, 2);
+    if (rc) return rc;
+    // packed weights as u64: dims {2*Np, Kp/8, taps}; strides {Np*16, Np*16*Kp/8}
+    rc = make_map_u64_3d(&tmB, w_packed, 2ull * a.n_total, a.cin_groups, a.taps, 16ull * a.n_total,
+                         16ull * a.n_total * a.cin_groups, 2 * a.n_acc, 2, a.taps);
+    if (rc) return rc;
+
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + bar_bytes;
+    static size_t smem_set = 0;
+    if (smem_bytes > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) return set_error(static_cast<int>(e), "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+        smem_set = SMEM_LIMIT;
+    }
+    const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
+    conv_tc_kernel<<<grid, N_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, a);
+    return check_launch("conv_tc_kernel");
+}

@@ -1,0 +1,134 @@
+/*
+ * bnerv_b200.h — C-ABI of the B200-native Boosting-NeRV conditional-decoder hot path.
+ *
+ * Every entry point takes plain device pointers, integer shapes and a CUDA stream handle
+ * (passed as void* so the header needs no CUDA include), allocates nothing, and returns
+ *      0   on success,
+ *     <0   BNERV_E_* : the arguments are outside what the kernel supports (nothing launched),
+ *     >0   a cudaError_t / CUresult value from the launch.
+ * bnerv_last_error() returns a thread-local, human-readable description of the last non-zero return.
+ *
+ * The reference (Xinjie-Q/Boosting-NeRV) is pure Python/PyTorch and has no FFI; the functions below
+ * replace what its modules do through torch ops.  Citations are `file:line` in the reference tree.
+ *
+ * Data layouts
+ *   NCHW f32 : the reference's layout, [B][C][H][W] float (model boundary only).
+ *   C8  f16  : this library's activation layout between kernels, [B][Cp/8][H][W][8] __half with
+ *              Cp = round_up(C, 16).  Channels >= C hold exact zeros.  One 16-byte group holds 8
+ *              consecutive channels of one pixel, so a pixel row of one group is a dense run in HBM
+ *              (TMA-friendly) and 8 neighbouring pixels of one group form one UMMA core matrix.
+ *   packed conv weight : [taps][Kp/8][Np][8] __half (taps = k*k, Kp = round_up(Cin,16),
+ *              Np = s*s*round_up(Cout,16)); row n' = (i*s + j)*Cout_p + c holds reference output
+ *              channel c*s*s + i*s + j, i.e. PixelShuffle (model_blocks.py:204,217) is folded into
+ *              the row order.  Rows/cols of padding are zero.
+ */
+#ifndef BNERV_B200_H_
+#define BNERV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNERV_ABI_VERSION 1
+
+/* error codes (negative) */
+#define BNERV_E_BADARG      (-1)   /* null pointer / non-positive size / misaligned pointer          */
+#define BNERV_E_UNSUPPORTED (-2)   /* shape or option outside what the kernels implement             */
+#define BNERV_E_NODRIVER    (-3)   /* CUDA driver entry point (cuTensorMapEncodeTiled) not available  */
+
+/* activation codes (model_blocks.py:136-158 — only the ones the shipped scripts select) */
+#define BNERV_ACT_NONE   0
+#define BNERV_ACT_SIN    1   /* Sin,  model_blocks.py:129-134                      */
+#define BNERV_ACT_GELU   2   /* nn.GELU() exact-erf, model_blocks.py:146           */
+#define BNERV_ACT_RELU   3   /* nn.ReLU, used inside SFTLayer, model_blocks.py:99   */
+#define BNERV_ACT_TANH01 4   /* OutImg 'tanh': tanh(x)*0.5+0.5, model_blocks.py:61 */
+
+int         bnerv_abi_version(void);
+const char* bnerv_last_error(void);
+/* Number of kernel launches issued by this library in the calling process since load (monotonic). */
+uint64_t    bnerv_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight packing.  Replaces nothing in the reference (it feeds F.conv2d OIHW weights directly,
+ * lib/quant_ops.py:39-41) — this is the "effective weight" ingest: pass `dequant_w ?? weight`.
+ *   w_oihw  : [Cout*s*s][Cin][k][k] f32     bias : [Cout*s*s] f32 or NULL (treated as zeros)
+ *   w_packed: [k*k][Kp/8][Np][8] f16        bias_packed : [Np] f32 (n' order)
+ * k in {1,3}; s >= 1 is the PixelShuffle factor folded into the row order (s = 1: plain conv).
+ * ---------------------------------------------------------------------------------------------- */
+int bnerv_pack_conv_weight(const float* w_oihw, const float* bias, int Cout, int Cin, int k, int s,
+                           void* w_packed, float* bias_packed, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused conv (the hot op).  One launch computes, for a stride-1 'same' conv with k in {1,3}:
+ *     y   = conv_k(x; W, b)                        CustomConv2d.forward, lib/quant_ops.py:39-41
+ *     y   = PixelShuffle_s(y)                      UpConv, model_blocks.py:213-220
+ *     x0  = act(y)                                 NeRVBlock.forward, model_blocks.py:37
+ *     x0 += resid                                  ResBlock_SFT.forward, model_blocks.py:89
+ *     u   = x0 * g1p + beta                        SFTLayer.forward, model_blocks.py:105 (g1p = scale+1)
+ * and writes x0 and/or u (C8 f16), or an NCHW f32 image for the head (model_blocks.py:57-63).
+ *   x        : C8 f16 [B][Cin_p/8][H][W][8]
+ *   w_packed, bias_packed : from bnerv_pack_conv_weight (same k, s)
+ *   resid    : C8 f16 at the OUTPUT resolution [B][Cout_p/8][H*s][W*s][8], or NULL
+ *   g1p,beta : f32 [B][Cout_p] (from bnerv_sft_affine), or both NULL for no affine
+ *   out_pre  : C8 f16, receives x0 (may be NULL when out_aff is given)
+ *   out_aff  : C8 f16, receives u  (NULL when g1p is NULL)
+ *   out_nchw : f32 [B][Cout][H*s][W*s], receives x0 (after act) in the reference layout, or NULL
+ * Computation: f16 operands, f32 accumulation (tcgen05.mma kind::f16, accumulators in TMEM).
+ * ---------------------------------------------------------------------------------------------- */
+int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W,
+                     const void* w_packed, const float* bias_packed, int Cout, int k, int s,
+                     int act, const void* resid, const float* g1p, const float* beta,
+                     void* out_pre, void* out_aff, float* out_nchw, void* stream);
+
+/* Same contract and operand layouts as bnerv_conv_fused, computed by an f32 CUDA-core kernel on the
+ * reference's own layouts (NCHW f32 activations, OIHW f32 weights) — the exact-arithmetic path used
+ * for tiny layers and as the on-device cross-check of the tensor-core kernel.
+ *   x: [B][Cin][H][W] f32; w: [Cout*s*s][Cin][k][k] f32; bias: [Cout*s*s] or NULL;
+ *   resid/out_pre/out_aff: [B][Cout][H*s][W*s] f32; g1p/beta: [B][ldg] f32 with row stride `ldg`. */
+int bnerv_conv_fused_f32(const float* x, int B, int Cin, int H, int W,
+                         const float* w, const float* bias, int Cout, int k, int s,
+                         int act, const float* resid, const float* g1p, const float* beta, int ldg,
+                         float* out_pre, float* out_aff, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * TAT affine parameters for one SFTLayer (model_blocks.py:92-105):
+ *     g1p  = Ws1 · relu(Ws0 · e + bs0) + bs1 + 1 ;   beta = Wh1 · relu(Wh0 · e + bh0) + bh1
+ *   e: [B][ch_t] f32; Ws0/Wh0: [ch_t][ch_t]; Ws1/Wh1: [C][ch_t]; biases f32.
+ *   g1p, beta: [B][Cp] f32 with Cp = round_up(C,16); entries >= C are written as 0.
+ * `n_layers` SFT layers are evaluated by ONE launch: every pointer argument is a device array of
+ * n_layers pointers / ints (built once per model by the caller).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bnerv_sft_layer {
+    const float *ws0, *bs0, *ws1, *bs1;   /* scale branch  SFT_scale_conv0/1 */
+    const float *wh0, *bh0, *wh1, *bh1;   /* shift branch  SFT_shift_conv0/1 */
+    float *g1p, *beta;                    /* outputs [B][Cp]                  */
+    int C, Cp;
+} bnerv_sft_layer;
+int bnerv_sft_affine(const bnerv_sft_layer* layers_dev, int n_layers, const float* e, int B, int ch_t,
+                     void* stream);
+
+/* 1x1-conv / linear layer on a [B][Cin] vector with activation: y = act(W x + b)
+ * (NeRV_MLP, model_blocks.py:66-71).  W: [Cout][Cin] f32 (a 1x1 OIHW weight is the same memory). */
+int bnerv_linear_act(const float* x, int B, int Cin, const float* w, const float* bias, int Cout,
+                     int act, float* y, void* stream);
+
+/* Layout conversion at the model boundary. */
+int bnerv_nchw_to_c8(const float* x, int B, int C, int H, int W, void* y_c8, void* stream);
+int bnerv_c8_to_nchw(const void* x_c8, int B, int C, int H, int W, float* y, void* stream);
+
+/* nn.PixelShuffle(s) on NCHW f32 (model_blocks.py:204,217): a pure index permutation, bit-exact.
+ *   x: [B][C*s*s][H][W] -> y: [B][C][H*s][W*s] */
+int bnerv_pixel_shuffle(const float* x, int B, int C, int H, int W, int s, float* y, void* stream);
+
+/* Sizes (in elements) of the buffers the caller must provide. */
+size_t bnerv_c8_numel(int B, int C, int H, int W);                 /* __half elements            */
+size_t bnerv_packed_weight_numel(int Cout, int Cin, int k, int s); /* __half elements            */
+size_t bnerv_packed_bias_numel(int Cout, int s);                   /* float elements (= Np)      */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNERV_B200_H_ */

@@ -1,0 +1,47 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "boosting-nerv_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    """-> (state_dict of torch tensors, dict of the other arrays as torch tensors)."""
+    z = np.load(os.path.join(GOLDEN, name))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    rest = {k: torch.from_numpy(z[k]) for k in z.files if not k.startswith("sd/")}
+    return sd, rest
+
+
+def load_block_golden():
+    z = np.load(os.path.join(GOLDEN, "blocks.npz"))
+    cases = {}
+    for k in z.files:
+        name, rest = k.split("/", 1)
+        cases.setdefault(name, {})[rest] = z[k]
+    return cases
+
+
+def max_rel(a, b):
+    """max |a-b| / max|b| — the 'relative fp32' metric used for the 1e-3 gate."""
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-12)).item()

@@ -1,0 +1,78 @@
+"""CPU: pin oracle/nerv_oracle.py against vectors minted from the unmodified reference (tests/golden)."""
+import torch
+import pytest
+
+from conftest import load_golden, load_block_golden, max_rel
+from oracle import nerv_oracle as orc
+from bnerv_b200.config import tiny_args
+
+TOL = 2e-6   # f32 op-order noise between the functional restatement and the reference's module graph
+
+
+def _cfg(model):
+    return orc.cfg_from_args(tiny_args(model))
+
+
+def test_nerv_boost_matches_reference():
+    sd, g = load_golden("nerv_tiny.npz")
+    img, outs = orc.nerv_boost_forward(sd, _cfg("NeRV_Boost"), g["t"])
+    assert img.shape == g["img"].shape
+    assert max_rel(img, g["img"]) < TOL
+    for i, o in enumerate(outs):
+        assert max_rel(o, g[f"out{i}"]) < TOL, i
+
+
+def test_enerv_boost_matches_reference():
+    sd, g = load_golden("enerv_tiny.npz")
+    img, outs = orc.enerv_boost_forward(sd, _cfg("ENeRV_Boost"), g["t"])
+    assert max_rel(img, g["img"]) < TOL
+    assert len(outs) == 5 and tuple(outs[0].shape) == (2, 32, 1, 1)      # out_list[0] is t_manipulate
+    for i, o in enumerate(outs):
+        assert max_rel(o, g[f"out{i}"]) < 5e-6, i
+
+
+def test_hnerv_boost_decoder_matches_reference():
+    sd, g = load_golden("hnerv_tiny.npz")
+    img, outs = orc.hnerv_boost_decode(sd, _cfg("HNeRV_Boost"), g["emb"], g["t"])
+    assert g["t"].dtype == torch.float64
+    assert max_rel(img, g["img"]) < TOL
+    assert torch.equal(outs[0], g["emb"])                                  # embed_list[0] is img_embed
+    for i, o in enumerate(outs):
+        assert max_rel(o, g[f"out{i}"]) < TOL, i
+
+
+def test_f64_oracle_close_to_f32_reference():
+    sd, g = load_golden("hnerv_tiny.npz")
+    img64, _ = orc.hnerv_boost_decode(sd, _cfg("HNeRV_Boost"), g["emb"], g["t"], dtype=torch.float64)
+    assert img64.dtype == torch.float64
+    assert max_rel(img64.float(), g["img"]) < 5e-6
+
+
+@pytest.mark.parametrize("name", ["s5_k3", "s2_k3", "s1_k3", "s3_k3", "s5_k1", "s2_wide"])
+def test_single_block_matches_reference(name):
+    c = load_block_golden()[name]
+    sd = {"blk." + k[3:]: torch.from_numpy(v) for k, v in c.items() if k.startswith("sd/")}
+    s = int(c["meta"][3])
+    x, e = torch.from_numpy(c["x"]), torch.from_numpy(c["e"])
+    y = orc.nerv_block(sd, "blk", x, e, s)
+    assert max_rel(y, torch.from_numpy(c["y"])) < TOL
+    x0 = torch.sin(orc.up_conv(sd, "blk.conv", x, s))
+    assert max_rel(x0, torch.from_numpy(c["x0"])) < TOL
+
+
+def test_position_encoding_both_dtype_paths():
+    c = load_block_golden()["pe"]
+    idx = torch.from_numpy(c["idx"])
+    assert torch.equal(orc.position_encoding(idx[:, None]).float().flatten(1), torch.from_numpy(c["f64_then_f32"]).flatten(1))
+    assert torch.equal(orc.position_encoding(idx[:, None].float()).flatten(1), torch.from_numpy(c["f32"]).flatten(1))
+    # the two paths genuinely differ (PE is chaotic in the dtype of t)
+    assert not torch.allclose(torch.from_numpy(c["f64_then_f32"]), torch.from_numpy(c["f32"]), atol=1e-3)
+
+
+def test_pixel_shuffle_golden_is_the_documented_permutation():
+    c = load_block_golden()["ps5"]
+    x, y = torch.from_numpy(c["x"]), torch.from_numpy(c["y"])
+    B, Cs, H, W = x.shape
+    s, C = 5, Cs // 25
+    ref = x.view(B, C, s, s, H, W).permute(0, 1, 4, 2, 5, 3).reshape(B, C, H * s, W * s)   # out[c,hs+i,ws+j]=in[c*s*s+i*s+j,h,w]
+    assert torch.equal(ref, y)
