@@ -131,6 +131,11 @@ class NeRV_Boost(_BoostBase):
         self.head_layer = CustomConv2d(ngf, 3, 1, 1, bias=True, args=args)
         self.out_bias, self.outf = args.out_bias, args.outf
 
+    def decode(self, input):
+        """Asynchronous decode on the native path: image only, no host sync, no timing."""
+        self._use_engine(input)
+        return self.engine().run_nerv(self.pe_t(input[:, None].float()), False)[0]
+
     def forward(self, input, input_embed=None, norm_idx=None):
         t0 = time.time()
         pe = self.pe_t(input[:, None].float())
@@ -205,6 +210,12 @@ class ENeRV_Boost(_BoostBase):
         emb = emb.reshape(b, self.fc_h, self.fc_w, emb.shape[-1]).permute(0, 3, 1, 2)
         return self.toconv(emb), t_manip
 
+    def decode(self, input):
+        """Asynchronous decode on the native path: image only, no host sync, no timing."""
+        self._use_engine(input)
+        emb, t_manip = self._stem(input)
+        return self.engine().run_cascade(emb.contiguous(), t_manip.flatten(1), False)[0]
+
     def forward(self, input, input_embed=None, norm_idx=False):
         use_engine = self._use_engine(input)
         t0 = time.time()
@@ -267,6 +278,11 @@ class HNeRV_Boost(_BoostBase):
         if entropy_model is not None:
             self.bitrate_e_dict.update(entropy_model.cal_bitrate(code, quant, self.training))
         return code, quant, img_embed
+
+    def decode(self, img_embed, norm_idx):
+        """Asynchronous decode on the native path: image only, no host sync, no timing."""
+        self._use_engine(img_embed)
+        return self.engine().run_hnerv(img_embed, self.pe_embed_t(norm_idx[:, None]).float(), False)[0]
 
     def forward_decoder(self, img_embed, norm_idx):
         use_engine = self._use_engine(img_embed)

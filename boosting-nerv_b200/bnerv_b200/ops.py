@@ -81,15 +81,31 @@ class PackedConv:
               lib.bnerv_pack_conv_weight(ptr(w), ptr(b), self.cout, self.cin, self.k, self.s, ptr(self.w), ptr(self.b), _stream()))
 
 
+# When set to a list, every conv_fused launch appends (algorithmic_flops, start_event, end_event) — used by
+# bench.py to time the dominant kernel inside the timed region on the launching stream.
+TIMING = None
+
+
+def conv_flops(B, cin, cout, k, s, H, W):
+    """Algorithmic FLOPs of one conv launch: 2*Cout*Cin*k*k*Hout*Wout with unpadded channels."""
+    return 2.0 * B * (cout * s * s) * cin * k * k * H * W
+
+
 def conv_fused(x_c8, pc, cin, H, W, act="none", resid=None, g1p=None, beta=None, out_pre=None, out_aff=None,
                out_nchw=None):
     """Launch the tcgen05 fused conv.  Output tensors are caller-provided (see bnerv_conv_fused)."""
     _need_cuda(x_c8)
     B = x_c8.shape[0]
     assert cin == pc.cin
+    if TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check("bnerv_conv_fused",
           lib.bnerv_conv_fused(ptr(x_c8), B, cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, pc.k, pc.s, ACT_CODES[act],
                                ptr(resid), ptr(g1p), ptr(beta), ptr(out_pre), ptr(out_aff), ptr(out_nchw), _stream()))
+    if TIMING is not None:
+        e1.record()
+        TIMING.append((conv_flops(B, cin, pc.cout, pc.k, pc.s, H, W), e0, e1, (cin, pc.cout, pc.k, pc.s, H, W, act)))
 
 
 def conv_fused_f32(x, weight, bias, s=1, act="none", resid=None, g1p=None, beta=None, want_pre=True):

@@ -89,6 +89,66 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// packed f32x2 epilogue math (sm_100 FFMA2/FADD2/FMUL2): two channels per instruction on the FMA pipe.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+
+__device__ __forceinline__ float mufu_sin(float x) { float r; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+__device__ __forceinline__ float2 sin2(float2 x) {
+    // k = round(x / 2pi) by the 1.5*2^23 trick (|x| < 2^22 * 2pi), r = x - k*2pi in two pieces, MUFU.SIN
+    const float magic = 12582912.0f;
+    float2 t = fma2(x, f2(0.15915494309189535f), f2(magic));
+    float2 k = add2(t, f2(-magic));
+    float2 r = fma2(k, f2(-6.2831854820251465f), x);
+    r = fma2(k, f2(1.7484555314695172e-07f), r);
+    return make_float2(mufu_sin(r.x), mufu_sin(r.y));
+}
+
+__device__ __forceinline__ float2 gelu2(float2 x) {
+    // 0.5 x (1 + erf(x/sqrt2)), erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7); coefficients negated so
+    // that erf(|z|) = 1 + pn(t) * exp(-z^2) comes out of one FFMA2.
+    float2 z  = mul2(x, f2(0.70710678118654752f));
+    float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+    float2 d  = fma2(az, f2(0.3275911f), f2(1.0f));
+    float2 t  = make_float2(mufu_rcp(d.x), mufu_rcp(d.y));
+    float2 pn = fma2(t, f2(-1.061405429f), f2(1.453152027f));
+    pn = fma2(pn, t, f2(-1.421413741f));
+    pn = fma2(pn, t, f2(0.284496736f));
+    pn = fma2(pn, t, f2(-0.254829592f));
+    pn = mul2(pn, t);
+    float2 q = mul2(mul2(z, z), f2(-1.4426950408889634f));
+    float2 e = make_float2(mufu_ex2(q.x), mufu_ex2(q.y));
+    float2 r = fma2(pn, e, f2(1.0f));                              // erf(|z|)
+    r = make_float2(copysignf(r.x, z.x), copysignf(r.y, z.y));
+    float2 h = mul2(x, f2(0.5f));
+    return fma2(h, r, h);
+}
+
+__device__ __forceinline__ float2 tanh01_2(float2 x) { return make_float2(tanh01(x.x), tanh01(x.y)); }
+
+template <int ACT>
+__device__ __forceinline__ float2 act2(float2 x) {
+    if (ACT == BNERV_ACT_SIN) return sin2(x);
+    if (ACT == BNERV_ACT_GELU) return gelu2(x);
+    if (ACT == BNERV_ACT_RELU) return make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f));
+    if (ACT == BNERV_ACT_TANH01) return tanh01_2(x);
+    return x;
+}
+
+// f32x2 -> f16x2 with saturation to +-65504 in one instruction (F2FP.SATFINITE.F16.F32.PACK_AB)
+__device__ __forceinline__ uint32_t pack_h2_satfinite(float2 v) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v.y), "f"(v.x));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier, TMA, tcgen05
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -33,7 +33,7 @@ constexpr int A_GROUP_B   = HALO_H * HALO_W * 16; // bytes of one 8-channel grou
 constexpr int A_STAGE_B   = 2 * A_GROUP_B;        // one K step = 16 channels = 2 groups (10368, 128-aligned)
 constexpr int ACC_COLS    = 128;                  // TMEM columns reserved per accumulator
 constexpr int TMEM_COLS   = 512;
-constexpr int N_EPI_WARPS = 4 * MT;
+constexpr int N_EPI_WARPS = 8 * MT;            // per UMMA tile: 4 lane quarters x 2 column parities
 constexpr int N_THREADS   = 64 + 32 * N_EPI_WARPS;
 constexpr int MAX_STAGES  = 8;
 constexpr int SMEM_LIMIT  = 227 * 1024;
@@ -49,6 +49,7 @@ struct ConvTcArgs {
     int cout, cout_p;       // real / padded output channels
     int s;                  // PixelShuffle factor
     int act;
+    int flags;              // F_* epilogue features (used by the generic instantiation)
     int tiles_x, tiles_y;
     int total_tiles;
     int stages;
@@ -78,11 +79,74 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcArgs& a, int tile) 
     return t;
 }
 
+// epilogue feature flags (compile-time in the specialised instantiations, run-time in the generic one)
+constexpr int F_RESID = 1, F_AFF = 2, F_PRE = 4, F_NCHW = 8, F_SHUF = 16;
+
+template <int ACT>
+__device__ __forceinline__ float2 act2_rt(float2 x, int act) {
+    if (ACT >= 0) return act2<ACT>(x);
+    switch (act) {
+        case BNERV_ACT_SIN:    return sin2(x);
+        case BNERV_ACT_GELU:   return gelu2(x);
+        case BNERV_ACT_RELU:   return act2<BNERV_ACT_RELU>(x);
+        case BNERV_ACT_TANH01: return tanh01_2(x);
+        default:               return x;
+    }
+}
+
+// One 8-channel group of one pixel: bias + activation (+ residual) (+ affine) and the stores.
+template <int ACT, int FLAGS>
+__device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, const uint32_t* v, int nn, int cc, int b,
+                                               size_t off, bool valid, const uint4& rr, int ho, int wo, int Ho, int Wo) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + nn));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + nn + 4));
+    float2 x[4];
+    x[0] = add2(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(b0.x, b0.y));
+    x[1] = add2(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(b0.z, b0.w));
+    x[2] = add2(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(b1.x, b1.y));
+    x[3] = add2(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(b1.z, b1.w));
+#pragma unroll
+    for (int p = 0; p < 4; ++p) x[p] = act2_rt<ACT>(x[p], a.act);
+    if (flags & F_RESID) {
+        x[0] = add2(x[0], unpack_h2(rr.x)); x[1] = add2(x[1], unpack_h2(rr.y));
+        x[2] = add2(x[2], unpack_h2(rr.z)); x[3] = add2(x[3], unpack_h2(rr.w));
+    }
+    if (!valid) return;
+    if (flags & F_PRE) {
+        uint4 o;
+        o.x = pack_h2_satfinite(x[0]); o.y = pack_h2_satfinite(x[1]);
+        o.z = pack_h2_satfinite(x[2]); o.w = pack_h2_satfinite(x[3]);
+        *reinterpret_cast<uint4*>(a.out_pre + off) = o;
+    }
+    if (flags & F_NCHW) {
+        const float xs[8] = {x[0].x, x[0].y, x[1].x, x[1].y, x[2].x, x[2].y, x[3].x, x[3].y};
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (cc + k < a.cout) a.out_nchw[(static_cast<size_t>(b * a.cout + cc + k) * Ho + ho) * Wo + wo] = xs[k];
+    }
+    if (flags & F_AFF) {
+        const float* gp = a.g1p + static_cast<size_t>(b) * a.cout_p + cc;
+        const float* bp = a.beta + static_cast<size_t>(b) * a.cout_p + cc;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + 4));
+        const float4 e0 = __ldg(reinterpret_cast<const float4*>(bp));
+        const float4 e1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+        uint4 o;
+        o.x = pack_h2_satfinite(fma2(x[0], make_float2(g0.x, g0.y), make_float2(e0.x, e0.y)));
+        o.y = pack_h2_satfinite(fma2(x[1], make_float2(g0.z, g0.w), make_float2(e0.z, e0.w)));
+        o.z = pack_h2_satfinite(fma2(x[2], make_float2(g1.x, g1.y), make_float2(e1.x, e1.y)));
+        o.w = pack_h2_satfinite(fma2(x[3], make_float2(g1.z, g1.w), make_float2(e1.z, e1.w)));
+        *reinterpret_cast<uint4*>(a.out_aff + off) = o;
+    }
+}
+
+template <int ACT, int FLAGS>
 __global__ void __launch_bounds__(N_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int flags = (FLAGS >= 0) ? FLAGS : a.flags;
 
     const int stage_bytes = A_STAGE_B + a.b_stage_bytes;
     uint8_t* bar_base     = smem + static_cast<size_t>(a.stages) * stage_bytes;
@@ -155,11 +219,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sb = sa + A_STAGE_B;
                     for (int tp = 0; tp < a.taps; ++tp) {
                         const int tap = tp + tap_lo;
-                        const int r = tap / 3, s = tap - 3 * r;
+                        const int r = tap / 3, sx = tap - 3 * r;
                         const uint64_t bdesc = umma_desc_kmajor_noswz(sb + tp * b_tap_b, b_lbo, 128u);
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
-                            const uint32_t a_addr = sa + (r * HALO_W + s + mt * 8) * 16;
+                            const uint32_t a_addr = sa + (r * HALO_W + sx + mt * 8) * 16;
                             const uint64_t adesc  = umma_desc_kmajor_noswz(a_addr, A_GROUP_B, HALO_W * 16);
                             umma_f16(tmem_base + (abuf * MT + mt) * ACC_COLS, adesc, bdesc, idesc,
                                      (kc > 0 || tp > 0) ? 1u : 0u);
@@ -175,114 +239,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
     } else {
-        // ===================== epilogue =====================
-        const int e  = warp - 2;
-        const int mt = e >> 2;
-        const int q  = warp & 3;                     // TMEM lane quarter this warp may access
-        const int m  = q * 32 + lane;                // row of the UMMA tile == pixel
+        // ===================== epilogue: 16 warps =====================
+        // warp -> (TMEM lane quarter q = warp%4 [hardware rule], UMMA tile mt, column parity half):
+        // a warp owns the 16-column groups g16 = half, half+2, half+4, half+6 of its tile.
+        const int e    = warp - 2;
+        const int q    = warp & 3;
+        const int mt   = (e >> 2) >> 1;
+        const int half = (e >> 2) & 1;
+        const int m    = q * 32 + lane;                // row of the UMMA tile == pixel
         int abuf = 0;
         uint32_t aphase = 0;
         const int s  = a.s;
         const int Ho = a.H * s, Wo = a.W * s;
         const int cout_groups = a.cout_p >> 3;
-        const bool has_aff = (a.g1p != nullptr);
+        const size_t plane = static_cast<size_t>(Ho) * Wo * 8;      // halves per 8-channel plane
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile(a, tile);
             const int h = t.h0 + (m >> 3);
             const int w = t.w0 + mt * 8 + (m & 7);
             const bool valid = (h < a.H) && (w < a.W);
-            // packed-row bookkeeping of the first group handled by this CTA
-            int sub = t.n0 / a.cout_p;               // PixelShuffle sub-position index i*s+j
-            int cc  = t.n0 - sub * a.cout_p;         // channel within the sub-position block
+            const size_t base_b = static_cast<size_t>(t.b) * cout_groups * plane;
+
+            // per 16-column group owned by this warp: packed row, channel, output pixel
+            int  nn16[4], cc16[4], ho16[4], wo16[4];
+            bool act16[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int g16 = half + 2 * j;
+                nn16[j]  = t.n0 + g16 * 16;
+                act16[j] = (g16 * 16 < a.n_acc) && (nn16[j] < a.n_total);
+                int sub = 0, cc = nn16[j];
+                if (flags & F_SHUF) { sub = nn16[j] / a.cout_p; cc = nn16[j] - sub * a.cout_p; }
+                const int i = sub / s, jj = sub - i * s;
+                cc16[j] = cc;
+                ho16[j] = h * s + i;
+                wo16[j] = w * s + jj;
+            }
 
             // Residual prefetch: issued before waiting for the accumulator so the HBM latency hides
             // behind the MMAs of this tile.
-            uint4 rres[ACC_COLS / 8];
-            if (a.resid != nullptr) {
-                int sub2 = sub, cc2 = cc;
+            uint4 rres[4][2];
+            if (flags & F_RESID) {
 #pragma unroll
-                for (int g = 0; g < ACC_COLS / 8; ++g) {
-                    rres[g] = make_uint4(0, 0, 0, 0);
-                    if (g * 8 < a.n_acc && t.n0 + g * 8 < a.n_total) {
-                        const int i = sub2 / s, j = sub2 - i * s;
-                        if (valid) {
-                            const size_t off = ((static_cast<size_t>(t.b * cout_groups + (cc2 >> 3)) * Ho + (h * s + i)) * Wo + (w * s + j)) * 8;
-                            rres[g] = __ldg(reinterpret_cast<const uint4*>(a.resid + off));
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        rres[j][hh] = make_uint4(0, 0, 0, 0);
+                        if (act16[j] && valid) {
+                            const size_t off = base_b + static_cast<size_t>((cc16[j] >> 3) + hh) * plane +
+                                               (static_cast<size_t>(ho16[j]) * Wo + wo16[j]) * 8;
+                            rres[j][hh] = __ldg(reinterpret_cast<const uint4*>(a.resid + off));
                         }
-                        cc2 += 8;
-                        if (cc2 >= a.cout_p) { cc2 = 0; ++sub2; }
                     }
-                }
             }
 
             mbar_wait(smem_u32(&tfull_bar[abuf]), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (abuf * MT + mt) * ACC_COLS;
 
+            uint32_t v[2][16];
+            if (act16[0]) tmem_ld16(taddr + half * 16, v[0]);
 #pragma unroll
-            for (int g16 = 0; g16 < ACC_COLS / 16; ++g16) {
-                if (g16 * 16 < a.n_acc && t.n0 + g16 * 16 < a.n_total) {     // CTA-uniform
-                    uint32_t v[16];
-                    tmem_ld16(taddr + g16 * 16, v);
+            for (int j = 0; j < 4; ++j) {
+                if (act16[j]) {                                           // CTA-uniform
                     tmem_ld_wait();
+                    if (j + 1 < 4 && act16[(j + 1) & 3]) tmem_ld16(taddr + (half + 2 * (j + 1)) * 16, v[(j + 1) & 1]);
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        const int g  = g16 * 2 + hh;
-                        const int nn = t.n0 + g * 8;                          // packed row of element 0
-                        const int i = sub / s, j = sub - i * s;
-                        const int ho = h * s + i, wo = w * s + j;
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + nn));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + nn + 4));
-                        float x[8];
-                        x[0] = __uint_as_float(v[hh * 8 + 0]) + b0.x;
-                        x[1] = __uint_as_float(v[hh * 8 + 1]) + b0.y;
-                        x[2] = __uint_as_float(v[hh * 8 + 2]) + b0.z;
-                        x[3] = __uint_as_float(v[hh * 8 + 3]) + b0.w;
-                        x[4] = __uint_as_float(v[hh * 8 + 4]) + b1.x;
-                        x[5] = __uint_as_float(v[hh * 8 + 5]) + b1.y;
-                        x[6] = __uint_as_float(v[hh * 8 + 6]) + b1.z;
-                        x[7] = __uint_as_float(v[hh * 8 + 7]) + b1.w;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) x[k] = apply_act(x[k], a.act);
-                        if (a.resid != nullptr) {
-                            const float2 r0 = unpack_h2(rres[g].x), r1 = unpack_h2(rres[g].y);
-                            const float2 r2 = unpack_h2(rres[g].z), r3 = unpack_h2(rres[g].w);
-                            x[0] += r0.x; x[1] += r0.y; x[2] += r1.x; x[3] += r1.y;
-                            x[4] += r2.x; x[5] += r2.y; x[6] += r3.x; x[7] += r3.y;
-                        }
-                        if (valid) {
-                            const size_t off = ((static_cast<size_t>(t.b * cout_groups + (cc >> 3)) * Ho + ho) * Wo + wo) * 8;
-                            if (a.out_pre != nullptr) {
-                                uint4 o;
-                                o.x = pack_h2_sat(x[0], x[1]); o.y = pack_h2_sat(x[2], x[3]);
-                                o.z = pack_h2_sat(x[4], x[5]); o.w = pack_h2_sat(x[6], x[7]);
-                                *reinterpret_cast<uint4*>(a.out_pre + off) = o;
-                            }
-                            if (a.out_nchw != nullptr) {
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) {
-                                    const int ch = cc + k;
-                                    if (ch < a.cout)
-                                        a.out_nchw[(static_cast<size_t>(t.b * a.cout + ch) * Ho + ho) * Wo + wo] = x[k];
-                                }
-                            }
-                            if (has_aff) {
-                                const float* gp = a.g1p + static_cast<size_t>(t.b) * a.cout_p + cc;
-                                const float* bp = a.beta + static_cast<size_t>(t.b) * a.cout_p + cc;
-                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
-                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + 4));
-                                const float4 e0 = __ldg(reinterpret_cast<const float4*>(bp));
-                                const float4 e1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
-                                uint4 o;
-                                o.x = pack_h2_sat(fmaf(x[0], g0.x, e0.x), fmaf(x[1], g0.y, e0.y));
-                                o.y = pack_h2_sat(fmaf(x[2], g0.z, e0.z), fmaf(x[3], g0.w, e0.w));
-                                o.z = pack_h2_sat(fmaf(x[4], g1.x, e1.x), fmaf(x[5], g1.y, e1.y));
-                                o.w = pack_h2_sat(fmaf(x[6], g1.z, e1.z), fmaf(x[7], g1.w, e1.w));
-                                *reinterpret_cast<uint4*>(a.out_aff + off) = o;
-                            }
-                        }
-                        cc += 8;
-                        if (cc >= a.cout_p) { cc = 0; ++sub; }
+                        const size_t off = base_b + static_cast<size_t>((cc16[j] >> 3) + hh) * plane +
+                                           (static_cast<size_t>(ho16[j]) * Wo + wo16[j]) * 8;
+                        epilogue_chunk<ACT, FLAGS>(a, flags, &v[j & 1][hh * 8], nn16[j] + hh * 8, cc16[j] + hh * 8, t.b, off,
+                                                   valid, rres[j][hh], ho16[j], wo16[j], Ho, Wo);
                     }
                 }
             }
@@ -396,6 +423,7 @@ extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, con
     a.out_pre = static_cast<__half*>(out_pre);
     a.out_aff = static_cast<__half*>(out_aff);
     a.out_nchw = out_nchw;
+    a.flags = (resid ? F_RESID : 0) | (g1p ? F_AFF : 0) | (out_pre ? F_PRE : 0) | (out_nchw ? F_NCHW : 0) | (s > 1 ? F_SHUF : 0);
 
     CUtensorMap tmA, tmB;
     // activations as u64: dims {2W, H, B*cin_groups}; strides {W*16, H*W*16} bytes
@@ -414,13 +442,27 @@ extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, con
         if (g_num_sms <= 0) g_num_sms = 148;
     }
     const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + bar_bytes;
-    static size_t smem_set = 0;
-    if (smem_bytes > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e != cudaSuccess) return set_error(static_cast<int>(e), "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
-        smem_set = SMEM_LIMIT;
-    }
     const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
-    conv_tc_kernel<<<grid, N_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, a);
+    // specialised epilogues for the five launch shapes of the decoder cascade, generic otherwise
+    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const ConvTcArgs);
+    KernelFn fn = conv_tc_kernel<-1, -1>;
+    int slot = 0;
+    const int fl = a.flags;
+#define BNERV_PICK(ID, ACT_, FL_)                                              \
+    if (act == (ACT_) && fl == (FL_)) { fn = conv_tc_kernel<(ACT_), (FL_)>; slot = (ID); }
+    BNERV_PICK(1, BNERV_ACT_SIN, F_AFF | F_PRE)                 // up-conv 1x1 / s=1 (+sin, x0 and u)
+    BNERV_PICK(2, BNERV_ACT_SIN, F_AFF | F_PRE | F_SHUF)        // up-conv + PixelShuffle
+    BNERV_PICK(3, BNERV_ACT_GELU, F_AFF)                        // conv0 + GELU + TAT affine
+    BNERV_PICK(4, BNERV_ACT_NONE, F_RESID | F_PRE)              // conv1 + residual
+    BNERV_PICK(5, BNERV_ACT_NONE, F_PRE | F_SHUF)               // E-NeRV stage-0 up-conv
+    BNERV_PICK(6, BNERV_ACT_TANH01, F_NCHW)                     // head conv -> image
+#undef BNERV_PICK
+    static bool smem_set[8] = {false, false, false, false, false, false, false, false};
+    if (!smem_set[slot]) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) return set_error(static_cast<int>(e), "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+        smem_set[slot] = true;
+    }
+    fn<<<grid, N_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, a);
     return check_launch("conv_tc_kernel");
 }

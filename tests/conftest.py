@@ -10,6 +10,9 @@ for p in (ROOT, os.path.join(ROOT, "boosting-nerv_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# references computed with torch on the GPU must be true f32 (cuDNN/cuBLAS default to TF32 for convs)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def pytest_configure(config):
