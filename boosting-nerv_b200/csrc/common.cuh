@@ -177,14 +177,42 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return ok;
 }
+// try_wait with a suspend-time hint: the thread is parked by the hardware until the phase completes or the
+// hint (ns) expires, instead of polling every ~25 cycles and stealing issue slots from the working warps.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok;
+}
 // Bounded wait: a pipeline bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a
 // hung GPU.  ~2 s at 2 GHz.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
+}
+
+// One lane of a converged warp (elect.sync): the issuing lane for TMA / tcgen05 instructions.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// named barrier over a subset of the CTA's warps (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
@@ -237,11 +265,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   core matrix = 8 rows x 16 bytes stored as 128 contiguous bytes;
 //   LBO = byte distance between core matrices adjacent in K, SBO = between 8-row groups in M/N.
 // (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor; version field = 1 on sm_100.)
-__device__ __forceinline__ uint64_t umma_desc_kmajor_noswz(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4)
-         | (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16)
+__device__ __host__ __forceinline__ uint64_t umma_desc_hi_noswz(uint32_t lbo, uint32_t sbo) {
+    return (static_cast<uint64_t>((lbo >> 4) & 0x3FFFu) << 16)
          | (static_cast<uint64_t>((sbo >> 4) & 0x3FFFu) << 32)
          | (1ull << 46);
+}
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswz(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | umma_desc_hi_noswz(lbo, sbo);
 }
 // instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n (cute UMMA::InstrDescriptor)
 __device__ __host__ __forceinline__ uint32_t umma_idesc_f16_m128(int n) {
