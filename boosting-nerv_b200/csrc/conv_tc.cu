@@ -37,6 +37,9 @@ constexpr int N_EPI_WARPS = 8 * MT;            // per UMMA tile: 4 lane quarters
 constexpr int N_THREADS   = 64 + 32 * N_EPI_WARPS;
 constexpr int MAX_STAGES  = 8;
 constexpr int SMEM_LIMIT  = 227 * 1024;
+constexpr int BAR_BYTES   = (2 * MAX_STAGES + 4) * 8 + 16;   // mbarriers + TMEM base slot (16-byte multiple)
+constexpr int CST_N       = 128;                  // per-tile epilogue constants: [2 buffers][bias|g1p|beta][CST_N] f32
+constexpr int CST_BYTES   = 2 * 3 * CST_N * 4;
 
 struct ConvTcArgs {
     int B, H, W;            // conv-resolution geometry (input == pre-shuffle output)
@@ -95,11 +98,14 @@ __device__ __forceinline__ float2 act2_rt(float2 x, int act) {
 }
 
 // One 8-channel group of one pixel: bias + activation (+ residual) (+ affine) and the stores.
+// cb points at this tile's constants in shared memory: [0..127] bias, [128..255] g1p, [256..383] beta, indexed by
+// the packed row relative to the tile (col = g16*16 + hh*8); all lanes read the same address (broadcast).
 template <int ACT, int FLAGS>
-__device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, const uint32_t* v, int nn, int cc, int b,
-                                               size_t off, bool valid, const uint4& rr, int ho, int wo, int Ho, int Wo) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + nn));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + nn + 4));
+__device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, const uint32_t* v, const float* cb, int col,
+                                               int cc, int b, size_t off, bool valid, const uint4& rr, int ho, int wo,
+                                               int Ho, int Wo) {
+    const float4 b0 = *reinterpret_cast<const float4*>(cb + col);
+    const float4 b1 = *reinterpret_cast<const float4*>(cb + col + 4);
     float2 x[4];
     x[0] = add2(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(b0.x, b0.y));
     x[1] = add2(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(b0.z, b0.w));
@@ -125,12 +131,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, c
             if (cc + k < a.cout) a.out_nchw[(static_cast<size_t>(b * a.cout + cc + k) * Ho + ho) * Wo + wo] = xs[k];
     }
     if (flags & F_AFF) {
-        const float* gp = a.g1p + static_cast<size_t>(b) * a.cout_p + cc;
-        const float* bp = a.beta + static_cast<size_t>(b) * a.cout_p + cc;
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + 4));
-        const float4 e0 = __ldg(reinterpret_cast<const float4*>(bp));
-        const float4 e1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+        const float4 g0 = *reinterpret_cast<const float4*>(cb + CST_N + col);
+        const float4 g1 = *reinterpret_cast<const float4*>(cb + CST_N + col + 4);
+        const float4 e0 = *reinterpret_cast<const float4*>(cb + 2 * CST_N + col);
+        const float4 e1 = *reinterpret_cast<const float4*>(cb + 2 * CST_N + col + 4);
         uint4 o;
         o.x = pack_h2_satfinite(fma2(x[0], make_float2(g0.x, g0.y), make_float2(e0.x, e0.y)));
         o.y = pack_h2_satfinite(fma2(x[1], make_float2(g0.z, g0.w), make_float2(e0.z, e0.w)));
@@ -140,11 +144,87 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, c
     }
 }
 
+struct Pipe {
+    uint32_t smem_base;      // shared-window address of the stage ring
+    uint32_t full, empty;    // shared-window addresses of full_bar[0] / empty_bar[0]
+    uint32_t tfull, tempty;  // ... of tfull_bar[0] / tempty_bar[0]
+    uint32_t tmem_base;
+    int stage_bytes;
+};
+
+// ===================== TMA producer (warp 0, converged; one elected lane issues) =====================
+__device__ __forceinline__ void producer_role(const ConvTcArgs& a, const Pipe& p, const CUtensorMap* tmA, const CUtensorMap* tmB) {
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = A_STAGE_B + a.b_stage_bytes;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(a, tile);
+        for (int kc = 0; kc < a.ksteps; ++kc) {
+            mbar_wait(p.empty + stage * 8, phase ^ 1);
+            if (elect_one()) {
+                const uint32_t fb = p.full + stage * 8;
+                const uint32_t sa = p.smem_base + stage * p.stage_bytes;
+                mbar_expect_tx(fb, tx_bytes);
+                // activations viewed as u64 elements: 2 per pixel-group -> x coordinate = 2*w
+                tma_load_3d(sa, tmA, fb, 2 * (t.w0 - 1), t.h0 - 1, t.b * a.cin_groups + 2 * kc);
+                tma_load_3d(sa + A_STAGE_B, tmB, fb, 2 * t.n0, 2 * kc, 0);
+            }
+            __syncwarp();
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+    }
+}
+
+// ===================== MMA issuer (warp 1, converged; one elected lane issues) =====================
+// Everything the issue needs is warp-uniform and the taps are unrolled with constant descriptor offsets, so one
+// K step (TAPS x MT UMMAs) is a straight run of UTCHMMA separated by a few uniform adds.
+template <int TAPS>
+__device__ __forceinline__ void mma_role(const ConvTcArgs& a, const Pipe& p) {
+    int stage = 0;
+    uint32_t phase = 0;
+    int abuf = 0;
+    uint32_t aphase = 0;
+    const uint32_t idesc   = umma_idesc_f16_m128(a.n_acc);
+    const uint32_t b_tap16 = 2u * a.n_acc;                      // one tap's [2 groups][n_acc][16 B] slab, in 16-byte units
+    const uint64_t a_hi    = umma_desc_hi_noswz(A_GROUP_B, HALO_W * 16);
+    const uint64_t b_hi    = umma_desc_hi_noswz(a.n_acc * 16u, 128u);
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        mbar_wait(p.tempty + abuf * 8, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = p.tmem_base + abuf * (MT * ACC_COLS);
+        for (int kc = 0; kc < a.ksteps; ++kc) {
+            mbar_wait(p.full + stage * 8, phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sa16 = (p.smem_base + stage * p.stage_bytes) >> 4;
+                const uint32_t sb16 = sa16 + (A_STAGE_B >> 4);
+#pragma unroll
+                for (int tp = 0; tp < TAPS; ++tp) {
+                    const int tap = (TAPS == 1) ? 4 : tp;       // 1x1 conv: the single tap reads the halo tile's centre
+                    const int r = tap / 3, sx = tap % 3;
+                    const uint64_t bdesc = b_hi | static_cast<uint64_t>(sb16 + tp * b_tap16);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint64_t adesc = a_hi | static_cast<uint64_t>(sa16 + (r * HALO_W + sx + mt * 8));
+                        umma_f16(d0 + mt * ACC_COLS, adesc, bdesc, idesc, (tp > 0) ? 1u : (kc > 0 ? 1u : 0u));
+                    }
+                }
+                umma_commit(p.empty + stage * 8);
+                if (kc == a.ksteps - 1) umma_commit(p.tfull + abuf * 8);
+            }
+            __syncwarp();
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        abuf ^= 1;
+        if (abuf == 0) aphase ^= 1;
+    }
+}
+
 template <int ACT, int FLAGS>
 __global__ void __launch_bounds__(N_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const int flags = (FLAGS >= 0) ? FLAGS : a.flags;
 
@@ -155,6 +235,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar   = empty_bar + MAX_STAGES;   // [2]
     uint64_t* tempty_bar  = tfull_bar + 2;            // [2]
     uint32_t* tmem_slot   = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float*    cst         = reinterpret_cast<float*>(bar_base + BAR_BYTES);   // [2][3][CST_N]
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.stages; ++i) {
@@ -173,71 +254,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t smem_base = smem_u32(smem);
+
+    Pipe p;
+    p.smem_base = smem_u32(smem);
+    p.full = smem_u32(full_bar);     p.empty = smem_u32(empty_bar);
+    p.tfull = smem_u32(tfull_bar);   p.tempty = smem_u32(tempty_bar);
+    p.tmem_base = *tmem_slot;
+    p.stage_bytes = stage_bytes;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t tx_bytes = A_STAGE_B + a.b_stage_bytes;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(a, tile);
-                for (int kc = 0; kc < a.ksteps; ++kc) {
-                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-                    const uint32_t fb = smem_u32(&full_bar[stage]);
-                    const uint32_t sa = smem_base + stage * stage_bytes;
-                    mbar_expect_tx(fb, tx_bytes);
-                    // activations viewed as u64 elements: 2 per pixel-group -> x coordinate = 2*w
-                    tma_load_3d(sa, &tmA, fb, 2 * (t.w0 - 1), t.h0 - 1, t.b * a.cin_groups + 2 * kc);
-                    tma_load_3d(sa + A_STAGE_B, &tmB, fb, 2 * t.n0, 2 * kc, 0);
-                    if (++stage == a.stages) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-        __syncwarp();
+        producer_role(a, p, &tmA, &tmB);
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int abuf = 0;
-            uint32_t aphase = 0;
-            const uint32_t idesc     = umma_idesc_f16_m128(a.n_acc);
-            const uint32_t b_tap_b   = 2u * a.n_acc * 16u;      // bytes of one tap's [2 groups][n_acc][16B]
-            const uint32_t b_lbo     = a.n_acc * 16u;
-            // 1x1 conv: the single tap reads the centre of the halo tile
-            const int tap_lo = (a.taps == 1) ? 4 : 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                mbar_wait(smem_u32(&tempty_bar[abuf]), aphase ^ 1);
-                tc_fence_after();
-                for (int kc = 0; kc < a.ksteps; ++kc) {
-                    mbar_wait(smem_u32(&full_bar[stage]), phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_base + stage * stage_bytes;
-                    const uint32_t sb = sa + A_STAGE_B;
-                    for (int tp = 0; tp < a.taps; ++tp) {
-                        const int tap = tp + tap_lo;
-                        const int r = tap / 3, sx = tap - 3 * r;
-                        const uint64_t bdesc = umma_desc_kmajor_noswz(sb + tp * b_tap_b, b_lbo, 128u);
-#pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) {
-                            const uint32_t a_addr = sa + (r * HALO_W + sx + mt * 8) * 16;
-                            const uint64_t adesc  = umma_desc_kmajor_noswz(a_addr, A_GROUP_B, HALO_W * 16);
-                            umma_f16(tmem_base + (abuf * MT + mt) * ACC_COLS, adesc, bdesc, idesc,
-                                     (kc > 0 || tp > 0) ? 1u : 0u);
-                        }
-                    }
-                    umma_commit(smem_u32(&empty_bar[stage]));
-                    if (kc == a.ksteps - 1) umma_commit(smem_u32(&tfull_bar[abuf]));
-                    if (++stage == a.stages) { stage = 0; phase ^= 1; }
-                }
-                abuf ^= 1;
-                if (abuf == 0) aphase ^= 1;
-            }
-        }
-        __syncwarp();
+        if (a.taps == 9) mma_role<9>(a, p); else mma_role<1>(a, p);
     } else {
         // ===================== epilogue: 16 warps =====================
         // warp -> (TMEM lane quarter q = warp%4 [hardware rule], UMMA tile mt, column parity half):
@@ -247,6 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int mt   = (e >> 2) >> 1;
         const int half = (e >> 2) & 1;
         const int m    = q * 32 + lane;                // row of the UMMA tile == pixel
+        const int et   = threadIdx.x - 64;             // 0 .. 32*N_EPI_WARPS-1
         int abuf = 0;
         uint32_t aphase = 0;
         const int s  = a.s;
@@ -259,6 +288,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int w = t.w0 + mt * 8 + (m & 7);
             const bool valid = (h < a.H) && (w < a.W);
             const size_t base_b = static_cast<size_t>(t.b) * cout_groups * plane;
+
+            // Stage this tile's per-row constants (bias, TAT scale+1, TAT shift) in shared memory: one global load
+            // per constant, issued before the accumulator wait; the chunks then read them as LDS broadcasts.
+            float* cb = cst + abuf * (3 * CST_N);
+            if (et < a.n_acc) {
+                const int nn = t.n0 + et;
+                float bv = 0.0f, gv = 0.0f, ev = 0.0f;
+                if (nn < a.n_total) {
+                    bv = __ldg(a.bias + nn);
+                    if (flags & F_AFF) {
+                        const int cc = (flags & F_SHUF) ? nn % a.cout_p : nn;
+                        gv = __ldg(a.g1p + static_cast<size_t>(t.b) * a.cout_p + cc);
+                        ev = __ldg(a.beta + static_cast<size_t>(t.b) * a.cout_p + cc);
+                    }
+                }
+                cb[et] = bv; cb[CST_N + et] = gv; cb[2 * CST_N + et] = ev;
+            }
 
             // per 16-column group owned by this warp: packed row, channel, output pixel
             int  nn16[4], cc16[4], ho16[4], wo16[4];
@@ -293,9 +339,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
             }
 
-            mbar_wait(smem_u32(&tfull_bar[abuf]), aphase);
+            // constants visible to all epilogue warps; also orders this tile's writes to cb after every warp's
+            // reads of the same buffer two tiles ago
+            named_bar_sync(1, 32 * N_EPI_WARPS);
+            mbar_wait(p.tfull + abuf * 8, aphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (abuf * MT + mt) * ACC_COLS;
+            const uint32_t taddr = p.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (abuf * MT + mt) * ACC_COLS;
 
             uint32_t v[2][16];
             if (act16[0]) tmem_ld16(taddr + half * 16, v[0]);
@@ -308,15 +357,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int hh = 0; hh < 2; ++hh) {
                         const size_t off = base_b + static_cast<size_t>((cc16[j] >> 3) + hh) * plane +
                                            (static_cast<size_t>(ho16[j]) * Wo + wo16[j]) * 8;
-                        epilogue_chunk<ACT, FLAGS>(a, flags, &v[j & 1][hh * 8], nn16[j] + hh * 8, cc16[j] + hh * 8, t.b, off,
-                                                   valid, rres[j][hh], ho16[j], wo16[j], Ho, Wo);
+                        epilogue_chunk<ACT, FLAGS>(a, flags, &v[j & 1][hh * 8], cb, (half + 2 * j) * 16 + hh * 8,
+                                                   cc16[j] + hh * 8, t.b, off, valid, rres[j][hh], ho16[j], wo16[j], Ho, Wo);
                     }
                 }
             }
             // all TMEM reads of this warp for this buffer are complete -> hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[abuf]));
+            if (lane == 0) mbar_arrive(p.tempty + abuf * 8);
             abuf ^= 1;
             if (abuf == 0) aphase ^= 1;
         }
@@ -326,7 +375,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        tmem_dealloc(p.tmem_base, TMEM_COLS);
     }
 }
 
@@ -413,7 +462,7 @@ extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, con
     a.total_tiles   = static_cast<int>(total);
     a.b_stage_bytes = a.taps * 2 * a.n_acc * 16;
     const int stage_bytes = A_STAGE_B + a.b_stage_bytes;
-    const int bar_bytes   = (2 * MAX_STAGES + 4) * 8 + 16;
+    const int bar_bytes   = BAR_BYTES + CST_BYTES;
     int stages = (SMEM_LIMIT - bar_bytes - 1024) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: stage of %d bytes does not fit twice", stage_bytes);
