@@ -16,6 +16,26 @@ void count_launch();
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Packed conv-output row n' -> (output channel c of the shuffled map, PixelShuffle sub-position i, j); the
+// reference conv channel is c*s*s + i*s + j (model_blocks.py:204,217).  Every 8 consecutive rows share (i, j).
+//   s == 2 : n' = ((i*Cout_p/8 + c/8)*2 + j)*8 + c%8  -- the two horizontal neighbours of one pixel's 8 channels are
+//            adjacent rows of ONE 16-column accumulator group, so a thread stores 32 contiguous bytes (a full
+//            sector) instead of two half sectors written by different n-tile passes (2x DRAM writes + fill reads).
+//   else   : n' = (i*s + j)*Cout_p + c
+__host__ __device__ __forceinline__ void packed_row_to_cij(int n, int s, int cout_p, int& c, int& i, int& j) {
+    if (s == 2) {
+        const int u = n >> 4, r = n & 15, g8 = cout_p >> 3;
+        j = r >> 3;
+        i = u / g8;
+        c = (u - i * g8) * 8 + (r & 7);
+    } else {
+        const int sub = n / cout_p;
+        c = n - sub * cout_p;
+        i = sub / s;
+        j = sub - i * s;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // epilogue math.  All in f32; accuracy targets are << the 1e-3 parity budget.
 // ---------------------------------------------------------------------------------------------
@@ -276,6 +296,60 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_noswz(uint32_t saddr, uint3
 // instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n (cute UMMA::InstrDescriptor)
 __device__ __host__ __forceinline__ uint32_t umma_idesc_f16_m128(int n) {
     return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) primitives
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x()    { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// Remote arrive with the default (CTA-scope release) semantics: the consumer only needs the TMEM reads ordered,
+// which tcgen05.fence::before_thread_sync provides; a .release.cluster arrive would make every epilogue warp wait
+// for its outstanding global stores (MEMBAR.ALL.CTA + ERRBAR, 22 % of epilogue samples in profiles/r01_v4a).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair: data lands in the issuing CTA's shared memory, the transaction
+// bytes are credited to `bar_cluster` (a shared::cluster address, normally the pair leader's barrier).
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const void* tmap, uint32_t bar_cluster, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {   // one whole warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 split over the pair (128 rows each, A from each CTA's own shared
+// memory) and B's N rows split half/half over the two CTAs' shared memory.  Issued by the leader CTA only.
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all previously issued MMAs completed) on the barrier at the same offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __host__ __forceinline__ uint32_t umma_idesc_f16(int m, int n) {
+    return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 }  // namespace bnerv

@@ -1,45 +1,70 @@
-// Fused implicit-GEMM conv for sm_100a: TMA-staged halo tiles -> tcgen05.mma (f16 x f16 -> f32 in TMEM)
-// -> in-register epilogue (bias, sin/GELU, residual, TAT affine, PixelShuffle addressing) -> 16-byte
-// vector stores.  Replaces CustomConv2d.forward + PixelShuffle + Sin/GELU + SFTLayer affine + residual
+// Fused implicit-GEMM conv for sm_100a: weight-stationary CTA pairs.
+//   TMA-staged halo tiles -> tcgen05.mma.cta_group::2 (f16 x f16 -> f32 in TMEM, M = 256 over two SMs)
+//   -> in-register epilogue (bias, sin/GELU, residual, TAT affine, PixelShuffle addressing) -> 16-byte stores.
+// Replaces CustomConv2d.forward + PixelShuffle + Sin/GELU + SFTLayer affine + residual
 // (lib/quant_ops.py:39-41, model_blocks.py:37,86-89,105,204,217) with one launch.
 //
 // GEMM view (per image):  D[pixels, n'] = sum_{tap, c} X[pixel + tap, c] * Wp[tap][c][n']
-//   M: a CTA works on a 16-row x 16-col pixel super-tile = MT(2) UMMA tiles of 16 rows x 8 cols (M=128)
-//   N: N_ACC <= 128 packed output rows per CTA (n' = PixelShuffle-major, see bnerv_b200.h)
-//   K: 9 taps x Cin_p channels, consumed 16 channels (one UMMA K step) per pipeline stage.
+//   M: each CTA of a pair owns a 16-row x 8*MT-col pixel super-tile = MT UMMA row blocks of 128 pixels; one UMMA
+//      (M = 256) covers row block mt of BOTH CTAs.
+//   N: n_acc <= 256/MT packed output rows (n' = PixelShuffle-major, see bnerv_b200.h) per pass ("n-tile").
+//   K: 9 taps x Cin_p channels, 16 channels (one UMMA K step) per pipeline stage.
+//
+// Why pairs + resident weights (profiles/r01_v3_*): with one CTA per tile every UMMA reads A (4 KB) and B
+// (N*32 B) from shared memory -> ~134 B/clk at N = 112, above the ~128 B/clk an SM delivers, and the weight
+// slab is re-streamed from L2 for every tile.  In a pair each SM reads its own A and only HALF of B, and each
+// CTA keeps its half of the n-tile's weights ([K steps][taps][2 groups][n_acc/2][16 B]) resident in shared
+// memory for the whole pass, so only activations stream (10 KB per K step).
 //
 // Shared-memory operand layout is the UMMA "no-swizzle, K-major" canonical form: a core matrix is
 // 8 rows x 16 B = 128 contiguous bytes.  The activation layout in HBM ([Cp/8][H][W][8] f16) makes one
-// TMA box {18 px, 18 rows, 2 channel groups} land as [group][row][px][16 B]: 8 neighbouring pixels of
+// TMA box {HALO_W px, 18 rows, 2 channel groups} land as [group][row][px][16 B]: 8 neighbouring pixels of
 // one image row ARE a core matrix, so the A operand of tap (r,s) is simply the same halo tile read
-// at start address + (r*18 + s)*16 B with SBO = one halo row (288 B).  The halo tile is fetched once
+// at start address + (r*HALO_W + s)*16 B with SBO = one halo row.  The halo tile is fetched once
 // and reused by all 9 taps (no im2col materialisation, no 9x re-fetch).
 //
-// Warp roles (320 threads): warp 0 = TMA producer (1 lane), warp 1 = TMEM owner + MMA issuer (1 lane),
-// warps 2..9 = epilogue (two groups of 4 warps, one group per UMMA tile; warp%4 selects its TMEM lane
-// quarter).  Two TMEM accumulator buffers (2 x 2 x 128 columns = all 512) let the epilogue of tile i
-// overlap the MMAs of tile i+1.  Persistent grid: one CTA per SM, static round-robin tile order.
+// Warp roles (576 threads per CTA): warp 0 = TMA producer, warp 1 = TMEM owner + (leader CTA only) MMA issuer,
+// warps 2..17 = epilogue (TMEM lane quarter = warp%4).  Two TMEM accumulator buffers (2 x 256 columns) let the
+// epilogue of tile i overlap the MMAs of tile i+1.  Persistent grid: 74 pairs, static round-robin tile order.
 #include <cuda.h>
 #include "common.cuh"
 
 namespace bnerv {
 
-constexpr int MT          = 2;                    // UMMA tiles (128 px each) per CTA super-tile
 constexpr int TILE_H      = 16;                   // pixel rows per super-tile
-constexpr int TILE_W      = 8 * MT;               // pixel cols per super-tile
-constexpr int HALO_W      = TILE_W + 2;           // 18
-constexpr int HALO_H      = TILE_H + 2;           // 18
-constexpr int A_GROUP_B   = HALO_H * HALO_W * 16; // bytes of one 8-channel group of the halo tile (5184)
-constexpr int A_STAGE_B   = 2 * A_GROUP_B;        // one K step = 16 channels = 2 groups (10368, 128-aligned)
-constexpr int ACC_COLS    = 128;                  // TMEM columns reserved per accumulator
+constexpr int HALO_H      = TILE_H + 2;
 constexpr int TMEM_COLS   = 512;
-constexpr int N_EPI_WARPS = 8 * MT;            // per UMMA tile: 4 lane quarters x 2 column parities
+constexpr int BUF_COLS    = 256;                  // TMEM columns per accumulator buffer
+constexpr int N_EPI_WARPS = 16;
 constexpr int N_THREADS   = 64 + 32 * N_EPI_WARPS;
-constexpr int MAX_STAGES  = 8;
+constexpr int MAX_STAGES  = 12;
+constexpr int MIN_STAGES  = 3;
 constexpr int SMEM_LIMIT  = 227 * 1024;
-constexpr int BAR_BYTES   = (2 * MAX_STAGES + 4) * 8 + 16;   // mbarriers + TMEM base slot (16-byte multiple)
-constexpr int CST_N       = 128;                  // per-tile epilogue constants: [2 buffers][bias|g1p|beta][CST_N] f32
-constexpr int CST_BYTES   = 2 * 3 * CST_N * 4;
+constexpr int N_BARS      = 2 * MAX_STAGES + 6;   // full[], empty[], tfull[2], tempty[2], wfull, wempty
+constexpr int BAR_BYTES   = N_BARS * 8 + 16;      // + TMEM base slot
+constexpr int CST_N       = 256;                  // per-tile epilogue constants, see Cst
+constexpr int MAX_GROUPS  = CST_N / 16;
+
+template <int MT_>
+struct Geo {
+    static constexpr int MT         = MT_;
+    static constexpr int TILE_W     = 8 * MT;
+    static constexpr int HALO_W     = TILE_W + 2;
+    static constexpr int A_GROUP_B  = HALO_H * HALO_W * 16;  // bytes of one 8-channel group of the halo tile
+    static constexpr int A_STAGE_B  = 2 * A_GROUP_B;         // one K step = 16 channels = 2 groups (128-byte multiple)
+    static constexpr int ACC_STRIDE = BUF_COLS / MT;         // TMEM columns between the MT accumulators of a buffer
+    static constexpr int CS         = 4 / MT;                // epilogue warps sharing one (lane quarter, row block)
+};
+
+struct ChunkInfo {          // 8 consecutive packed rows of the current n-tile = 8 channels of one output position
+    long long goff;         // output offset (halves) relative to the pixel's (i=j=0) position in channel group 0
+    int cc;                 // first output channel
+    int ij;                 // PixelShuffle sub-position: i | (j << 16)
+};
+struct Cst {                // staged per tile by the epilogue warps, read back as LDS broadcasts
+    float bias[CST_N], g1p[CST_N], beta[CST_N];
+    ChunkInfo chk[2 * MAX_GROUPS];
+};
 
 struct ConvTcArgs {
     int B, H, W;            // conv-resolution geometry (input == pre-shuffle output)
@@ -47,16 +72,21 @@ struct ConvTcArgs {
     int ksteps;             // Cin_p / 16
     int taps;               // 1 or 9
     int n_total;            // s*s*Cout_p
-    int n_acc;              // packed rows per CTA (multiple of 16, <= 128)
+    int n_acc;              // packed rows per n-tile (multiple of 16, <= 256/MT)
+    int n_half;             // n_acc / 2 : rows of B each CTA of the pair keeps
     int n_tiles;            // ceil(n_total / n_acc)
     int cout, cout_p;       // real / padded output channels
     int s;                  // PixelShuffle factor
     int act;
     int flags;              // F_* epilogue features (used by the generic instantiation)
-    int tiles_x, tiles_y;
-    int total_tiles;
+    int tiles_x, tiles_y;   // super-tiles per image
+    int pairs_x;            // ceil(tiles_x / 2)
+    int pair_tiles;         // B * tiles_y * pairs_x : work items per n-tile
+    int work_total;         // n_tiles * pair_tiles, n-tile major; pair p owns the contiguous range [p, p+1) * total / n_pairs
+    int n_pairs;            // CTA pairs in the grid
     int stages;
-    int b_stage_bytes;      // taps * 2 * n_acc * 16
+    int b_kstep_bytes;      // taps * 2 * n_half * 16 : one K step of the resident weight half
+    int b_bytes;            // ksteps * b_kstep_bytes
     const float* bias;      // [n_total]
     const float* g1p;       // [B][cout_p] or null
     const float* beta;      // [B][cout_p] or null
@@ -66,20 +96,29 @@ struct ConvTcArgs {
     float* out_nchw;        // NCHW f32 or null
 };
 
-struct TileCoord { int n0, b, h0, w0; };
+struct TileCoord { int b, h0, w0; };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvTcArgs& a, int tile) {
+template <int MT>
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcArgs& a, int pt, int rank) {
     TileCoord t;
-    int nt   = tile % a.n_tiles;
-    int rest = tile / a.n_tiles;
-    int tx   = rest % a.tiles_x;
-    rest /= a.tiles_x;
-    int ty = rest % a.tiles_y;
-    t.b    = rest / a.tiles_y;
-    t.n0   = nt * a.n_acc;
-    t.h0   = ty * TILE_H;
-    t.w0   = tx * TILE_W;
+    const int px = pt % a.pairs_x;
+    int rest = pt / a.pairs_x;
+    const int ty = rest % a.tiles_y;
+    t.b  = rest / a.tiles_y;
+    t.h0 = ty * TILE_H;
+    t.w0 = (2 * px + rank) * Geo<MT>::TILE_W;      // may lie entirely outside the image (odd tiles_x): TMA zero-fills
     return t;
+}
+
+// Work split: the (n-tile major) item list is cut into one contiguous range per pair, so a pair switches its resident
+// weights at most (range / pair_tiles + 1) times and pairs ~n_pairs/n_tiles apart walk the same pixel tiles at about
+// the same time (the activation tile is then served from L2 to all of them).
+struct WorkRange { int begin, end; };
+__device__ __forceinline__ WorkRange work_range(const ConvTcArgs& a, uint32_t pair) {
+    WorkRange r;
+    r.begin = static_cast<int>(static_cast<long long>(a.work_total) * pair / a.n_pairs);
+    r.end   = static_cast<int>(static_cast<long long>(a.work_total) * (pair + 1) / a.n_pairs);
+    return r;
 }
 
 // epilogue feature flags (compile-time in the specialised instantiations, run-time in the generic one)
@@ -98,14 +137,13 @@ __device__ __forceinline__ float2 act2_rt(float2 x, int act) {
 }
 
 // One 8-channel group of one pixel: bias + activation (+ residual) (+ affine) and the stores.
-// cb points at this tile's constants in shared memory: [0..127] bias, [128..255] g1p, [256..383] beta, indexed by
-// the packed row relative to the tile (col = g16*16 + hh*8); all lanes read the same address (broadcast).
+// `col` is the packed row relative to the n-tile; all lanes read the same constants (LDS broadcast).
 template <int ACT, int FLAGS>
-__device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, const uint32_t* v, const float* cb, int col,
+__device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, const uint32_t* v, const Cst* cb, int col,
                                                int cc, int b, size_t off, bool valid, const uint4& rr, int ho, int wo,
                                                int Ho, int Wo) {
-    const float4 b0 = *reinterpret_cast<const float4*>(cb + col);
-    const float4 b1 = *reinterpret_cast<const float4*>(cb + col + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(cb->bias + col);
+    const float4 b1 = *reinterpret_cast<const float4*>(cb->bias + col + 4);
     float2 x[4];
     x[0] = add2(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(b0.x, b0.y));
     x[1] = add2(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(b0.z, b0.w));
@@ -131,10 +169,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, c
             if (cc + k < a.cout) a.out_nchw[(static_cast<size_t>(b * a.cout + cc + k) * Ho + ho) * Wo + wo] = xs[k];
     }
     if (flags & F_AFF) {
-        const float4 g0 = *reinterpret_cast<const float4*>(cb + CST_N + col);
-        const float4 g1 = *reinterpret_cast<const float4*>(cb + CST_N + col + 4);
-        const float4 e0 = *reinterpret_cast<const float4*>(cb + 2 * CST_N + col);
-        const float4 e1 = *reinterpret_cast<const float4*>(cb + 2 * CST_N + col + 4);
+        const float4 g0 = *reinterpret_cast<const float4*>(cb->g1p + col);
+        const float4 g1 = *reinterpret_cast<const float4*>(cb->g1p + col + 4);
+        const float4 e0 = *reinterpret_cast<const float4*>(cb->beta + col);
+        const float4 e1 = *reinterpret_cast<const float4*>(cb->beta + col + 4);
         uint4 o;
         o.x = pack_h2_satfinite(fma2(x[0], make_float2(g0.x, g0.y), make_float2(e0.x, e0.y)));
         o.y = pack_h2_satfinite(fma2(x[1], make_float2(g0.z, g0.w), make_float2(e0.z, e0.w)));
@@ -145,97 +183,141 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, c
 }
 
 struct Pipe {
-    uint32_t smem_base;      // shared-window address of the stage ring
-    uint32_t full, empty;    // shared-window addresses of full_bar[0] / empty_bar[0]
+    uint32_t w_base;         // shared-window address of the resident weight half
+    uint32_t a_base;         // ... of the activation stage ring
+    uint32_t full, empty;    // ... of full_bar[0] / empty_bar[0]
     uint32_t tfull, tempty;  // ... of tfull_bar[0] / tempty_bar[0]
+    uint32_t wfull, wempty;
     uint32_t tmem_base;
-    int stage_bytes;
+    uint32_t rank;           // CTA rank in the pair (0 = leader)
+    uint32_t pair;           // pair index in the grid
 };
 
-// ===================== TMA producer (warp 0, converged; one elected lane issues) =====================
+// ===================== TMA producer (warp 0 of both CTAs, converged; one elected lane issues) =====================
+// Every load of either CTA credits its bytes to the LEADER's barrier (the leader's MMA thread is the only consumer);
+// the leader alone arms the barrier with the pair's total byte count.
+template <int MT>
 __device__ __forceinline__ void producer_role(const ConvTcArgs& a, const Pipe& p, const CUtensorMap* tmA, const CUtensorMap* tmB) {
+    using G = Geo<MT>;
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = A_STAGE_B + a.b_stage_bytes;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(a, tile);
-        for (int kc = 0; kc < a.ksteps; ++kc) {
-            mbar_wait(p.empty + stage * 8, phase ^ 1);
+    const uint32_t full_leader  = map_to_cta(p.full, 0);
+    const uint32_t wfull_leader = map_to_cta(p.wfull, 0);
+    const WorkRange wr = work_range(a, p.pair);
+    int wc = 0;                                   // weight loads issued so far
+    for (int it = wr.begin; it < wr.end; ++it) {
+        const int nt = it / a.pair_tiles, pt = it - nt * a.pair_tiles;
+        if (it == wr.begin || pt == 0) {
+            // the previous n-tile's MMAs (which read the resident weights of both CTAs) must have completed
+            if (wc > 0) mbar_wait(p.wempty, (wc - 1) & 1);
             if (elect_one()) {
-                const uint32_t fb = p.full + stage * 8;
-                const uint32_t sa = p.smem_base + stage * p.stage_bytes;
-                mbar_expect_tx(fb, tx_bytes);
-                // activations viewed as u64 elements: 2 per pixel-group -> x coordinate = 2*w
-                tma_load_3d(sa, tmA, fb, 2 * (t.w0 - 1), t.h0 - 1, t.b * a.cin_groups + 2 * kc);
-                tma_load_3d(sa + A_STAGE_B, tmB, fb, 2 * t.n0, 2 * kc, 0);
+                if (p.rank == 0) mbar_expect_tx(p.wfull, 2u * a.b_bytes);
+                const int row0 = nt * a.n_acc + p.rank * a.n_half;
+                for (int kc = 0; kc < a.ksteps; ++kc)
+                    tma_load_3d_pair(p.w_base + kc * a.b_kstep_bytes, tmB, wfull_leader, 2 * row0, 2 * kc, 0);
             }
             __syncwarp();
-            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            ++wc;
+        }
+        {
+            const TileCoord t = decode_tile<MT>(a, pt, p.rank);
+            for (int kc = 0; kc < a.ksteps; ++kc) {
+                mbar_wait(p.empty + stage * 8, phase ^ 1);
+                if (elect_one()) {
+                    if (p.rank == 0) mbar_expect_tx(p.full + stage * 8, 2u * G::A_STAGE_B);
+                    // activations viewed as u64 elements: 2 per pixel-group -> x coordinate = 2*w
+                    tma_load_3d_pair(p.a_base + stage * G::A_STAGE_B, tmA, full_leader + stage * 8,
+                                     2 * (t.w0 - 1), t.h0 - 1, t.b * a.cin_groups + 2 * kc);
+                }
+                __syncwarp();
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
         }
     }
 }
 
-// ===================== MMA issuer (warp 1, converged; one elected lane issues) =====================
+// ===================== MMA issuer (warp 1 of the leader CTA, converged; one elected lane issues) =====================
 // Everything the issue needs is warp-uniform and the taps are unrolled with constant descriptor offsets, so one
-// K step (TAPS x MT UMMAs) is a straight run of UTCHMMA separated by a few uniform adds.
-template <int TAPS>
+// K step (TAPS x MT UMMAs of M = 256) is a straight run of UTCHMMA separated by a few uniform adds.
+template <int MT, int TAPS>
 __device__ __forceinline__ void mma_role(const ConvTcArgs& a, const Pipe& p) {
+    using G = Geo<MT>;
     int stage = 0;
     uint32_t phase = 0;
     int abuf = 0;
     uint32_t aphase = 0;
-    const uint32_t idesc   = umma_idesc_f16_m128(a.n_acc);
-    const uint32_t b_tap16 = 2u * a.n_acc;                      // one tap's [2 groups][n_acc][16 B] slab, in 16-byte units
-    const uint64_t a_hi    = umma_desc_hi_noswz(A_GROUP_B, HALO_W * 16);
-    const uint64_t b_hi    = umma_desc_hi_noswz(a.n_acc * 16u, 128u);
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        mbar_wait(p.tempty + abuf * 8, aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d0 = p.tmem_base + abuf * (MT * ACC_COLS);
-        for (int kc = 0; kc < a.ksteps; ++kc) {
-            mbar_wait(p.full + stage * 8, phase);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t sa16 = (p.smem_base + stage * p.stage_bytes) >> 4;
-                const uint32_t sb16 = sa16 + (A_STAGE_B >> 4);
-#pragma unroll
-                for (int tp = 0; tp < TAPS; ++tp) {
-                    const int tap = (TAPS == 1) ? 4 : tp;       // 1x1 conv: the single tap reads the halo tile's centre
-                    const int r = tap / 3, sx = tap % 3;
-                    const uint64_t bdesc = b_hi | static_cast<uint64_t>(sb16 + tp * b_tap16);
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const uint64_t adesc = a_hi | static_cast<uint64_t>(sa16 + (r * HALO_W + sx + mt * 8));
-                        umma_f16(d0 + mt * ACC_COLS, adesc, bdesc, idesc, (tp > 0) ? 1u : (kc > 0 ? 1u : 0u));
-                    }
-                }
-                umma_commit(p.empty + stage * 8);
-                if (kc == a.ksteps - 1) umma_commit(p.tfull + abuf * 8);
+    const uint32_t idesc   = umma_idesc_f16(256, a.n_acc);
+    const uint32_t b_tap16 = 2u * a.n_half;                     // one tap's [2 groups][n_half][16 B] slab, in 16-byte units
+    const uint32_t b_ks16  = static_cast<uint32_t>(a.b_kstep_bytes) >> 4;
+    const uint64_t a_hi    = umma_desc_hi_noswz(G::A_GROUP_B, G::HALO_W * 16);
+    const uint64_t b_hi    = umma_desc_hi_noswz(a.n_half * 16u, 128u);
+    const uint32_t wb16    = (p.w_base & 0x3FFFFu) >> 4;
+    const uint32_t ab16    = (p.a_base & 0x3FFFFu) >> 4;
+    const WorkRange wr = work_range(a, p.pair);
+    int wc = 0;                                   // weight sets consumed so far
+    for (int it = wr.begin; it < wr.end; ++it) {
+        const int pt = it % a.pair_tiles;
+        if (it == wr.begin || pt == 0) {
+            if (wc > 0) {                         // every MMA that reads the old weights has been issued: release them
+                if (elect_one()) umma_commit_pair(p.wempty);
+                __syncwarp();
             }
-            __syncwarp();
-            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            mbar_wait(p.wfull, wc & 1);
+            tc_fence_after();
+            ++wc;
         }
-        abuf ^= 1;
-        if (abuf == 0) aphase ^= 1;
+        {
+            mbar_wait(p.tempty + abuf * 8, aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d0 = p.tmem_base + abuf * BUF_COLS;
+            for (int kc = 0; kc < a.ksteps; ++kc) {
+                mbar_wait(p.full + stage * 8, phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa16 = ab16 + stage * (G::A_STAGE_B >> 4);
+                    const uint32_t sb16 = wb16 + kc * b_ks16;
+#pragma unroll
+                    for (int tp = 0; tp < TAPS; ++tp) {
+                        const int tap = (TAPS == 1) ? 4 : tp;   // 1x1 conv: the single tap reads the halo tile's centre
+                        const int r = tap / 3, sx = tap % 3;
+                        const uint64_t bdesc = b_hi | static_cast<uint64_t>(sb16 + tp * b_tap16);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint64_t adesc = a_hi | static_cast<uint64_t>(sa16 + (r * G::HALO_W + sx + mt * 8));
+                            umma_f16_pair(d0 + mt * G::ACC_STRIDE, adesc, bdesc, idesc, (tp > 0) ? 1u : (kc > 0 ? 1u : 0u));
+                        }
+                    }
+                    umma_commit_pair(p.empty + stage * 8);
+                    if (kc == a.ksteps - 1) umma_commit_pair(p.tfull + abuf * 8);
+                }
+                __syncwarp();
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+            abuf ^= 1;
+            if (abuf == 0) aphase ^= 1;
+        }
     }
 }
 
-template <int ACT, int FLAGS>
+template <int MT, int ACT, int FLAGS>
 __global__ void __launch_bounds__(N_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcArgs a) {
+    using G = Geo<MT>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const int flags = (FLAGS >= 0) ? FLAGS : a.flags;
 
-    const int stage_bytes = A_STAGE_B + a.b_stage_bytes;
-    uint8_t* bar_base     = smem + static_cast<size_t>(a.stages) * stage_bytes;
+    uint8_t* a_ring       = smem + a.b_bytes;
+    uint8_t* bar_base     = a_ring + static_cast<size_t>(a.stages) * G::A_STAGE_B;
     uint64_t* full_bar    = reinterpret_cast<uint64_t*>(bar_base);
     uint64_t* empty_bar   = full_bar + MAX_STAGES;
     uint64_t* tfull_bar   = empty_bar + MAX_STAGES;   // [2]
     uint64_t* tempty_bar  = tfull_bar + 2;            // [2]
-    uint32_t* tmem_slot   = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float*    cst         = reinterpret_cast<float*>(bar_base + BAR_BYTES);   // [2][3][CST_N]
+    uint64_t* wfull_bar   = tempty_bar + 2;
+    uint64_t* wempty_bar  = wfull_bar + 1;
+    uint32_t* tmem_slot   = reinterpret_cast<uint32_t*>(wempty_bar + 1);
+    Cst*      cst         = reinterpret_cast<Cst*>(bar_base + BAR_BYTES);     // [2]
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.stages; ++i) {
@@ -244,138 +326,158 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&tfull_bar[i]), 1);
-            mbar_init(smem_u32(&tempty_bar[i]), N_EPI_WARPS);
+            mbar_init(smem_u32(&tempty_bar[i]), 2 * N_EPI_WARPS);      // the epilogue warps of BOTH CTAs (leader's copy is used)
         }
+        mbar_init(smem_u32(wfull_bar), 1);
+        mbar_init(smem_u32(wempty_bar), 1);
         fence_mbar_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (warp == 1) tmem_alloc_pair(smem_u32(tmem_slot), TMEM_COLS);
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();            // barriers of both CTAs initialised before any remote arrive / TMA credit
     tc_fence_after();
 
     Pipe p;
-    p.smem_base = smem_u32(smem);
+    p.w_base = smem_u32(smem);
+    p.a_base = smem_u32(a_ring);
     p.full = smem_u32(full_bar);     p.empty = smem_u32(empty_bar);
     p.tfull = smem_u32(tfull_bar);   p.tempty = smem_u32(tempty_bar);
+    p.wfull = smem_u32(wfull_bar);   p.wempty = smem_u32(wempty_bar);
     p.tmem_base = *tmem_slot;
-    p.stage_bytes = stage_bytes;
+    p.rank = cluster_ctarank();
+    p.pair = cluster_id_x();
 
     if (warp == 0) {
-        producer_role(a, p, &tmA, &tmB);
+        producer_role<MT>(a, p, &tmA, &tmB);
     } else if (warp == 1) {
-        if (a.taps == 9) mma_role<9>(a, p); else mma_role<1>(a, p);
+        if (p.rank == 0) {
+            if (a.taps == 9) mma_role<MT, 9>(a, p); else mma_role<MT, 1>(a, p);
+        }
     } else {
-        // ===================== epilogue: 16 warps =====================
-        // warp -> (TMEM lane quarter q = warp%4 [hardware rule], UMMA tile mt, column parity half):
-        // a warp owns the 16-column groups g16 = half, half+2, half+4, half+6 of its tile.
+        // ===================== epilogue: 16 warps per CTA =====================
+        // warp -> (TMEM lane quarter q = warp%4 [hardware rule], row block mt, column slot cs of CS):
+        // a warp owns the 16-column groups g16 = cs, cs+CS, cs+2CS, cs+3CS of its row block.
         const int e    = warp - 2;
         const int q    = warp & 3;
-        const int mt   = (e >> 2) >> 1;
-        const int half = (e >> 2) & 1;
-        const int m    = q * 32 + lane;                // row of the UMMA tile == pixel
-        const int et   = threadIdx.x - 64;             // 0 .. 32*N_EPI_WARPS-1
+        const int sub  = e >> 2;                        // 0..3
+        const int mt   = (MT == 2) ? (sub >> 1) : 0;
+        const int cs   = (MT == 2) ? (sub & 1) : sub;
+        const int m    = q * 32 + lane;                 // row of the UMMA row block == pixel
+        const int et   = threadIdx.x - 64;              // 0 .. 32*N_EPI_WARPS-1
         int abuf = 0;
         uint32_t aphase = 0;
         const int s  = a.s;
         const int Ho = a.H * s, Wo = a.W * s;
         const int cout_groups = a.cout_p >> 3;
         const size_t plane = static_cast<size_t>(Ho) * Wo * 8;      // halves per 8-channel plane
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-            const TileCoord t = decode_tile(a, tile);
-            const int h = t.h0 + (m >> 3);
-            const int w = t.w0 + mt * 8 + (m & 7);
-            const bool valid = (h < a.H) && (w < a.W);
-            const size_t base_b = static_cast<size_t>(t.b) * cout_groups * plane;
+        const uint32_t tempty_leader = map_to_cta(p.tempty, 0);
+        const WorkRange wr = work_range(a, p.pair);
+        for (int it = wr.begin; it < wr.end; ++it) {
+            const int nt = it / a.pair_tiles, pt = it - nt * a.pair_tiles;
+            const int n0 = nt * a.n_acc;
+            {
+                const TileCoord t = decode_tile<MT>(a, pt, p.rank);
+                const int h = t.h0 + (m >> 3);
+                const int w = t.w0 + mt * 8 + (m & 7);
+                const bool valid = (h < a.H) && (w < a.W);
+                const size_t base_b = static_cast<size_t>(t.b) * cout_groups * plane;
+                const size_t pix = (static_cast<size_t>(h) * s * Wo + static_cast<size_t>(w) * s) * 8;
 
-            // Stage this tile's per-row constants (bias, TAT scale+1, TAT shift) in shared memory: one global load
-            // per constant, issued before the accumulator wait; the chunks then read them as LDS broadcasts.
-            float* cb = cst + abuf * (3 * CST_N);
-            if (et < a.n_acc) {
-                const int nn = t.n0 + et;
-                float bv = 0.0f, gv = 0.0f, ev = 0.0f;
-                if (nn < a.n_total) {
-                    bv = __ldg(a.bias + nn);
-                    if (flags & F_AFF) {
-                        const int cc = (flags & F_SHUF) ? nn % a.cout_p : nn;
-                        gv = __ldg(a.g1p + static_cast<size_t>(t.b) * a.cout_p + cc);
-                        ev = __ldg(a.beta + static_cast<size_t>(t.b) * a.cout_p + cc);
-                    }
-                }
-                cb[et] = bv; cb[CST_N + et] = gv; cb[2 * CST_N + et] = ev;
-            }
-
-            // per 16-column group owned by this warp: packed row, channel, output pixel
-            int  nn16[4], cc16[4], ho16[4], wo16[4];
-            bool act16[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int g16 = half + 2 * j;
-                nn16[j]  = t.n0 + g16 * 16;
-                act16[j] = (g16 * 16 < a.n_acc) && (nn16[j] < a.n_total);
-                int sub = 0, cc = nn16[j];
-                if (flags & F_SHUF) { sub = nn16[j] / a.cout_p; cc = nn16[j] - sub * a.cout_p; }
-                const int i = sub / s, jj = sub - i * s;
-                cc16[j] = cc;
-                ho16[j] = h * s + i;
-                wo16[j] = w * s + jj;
-            }
-
-            // Residual prefetch: issued before waiting for the accumulator so the HBM latency hides
-            // behind the MMAs of this tile.
-            uint4 rres[4][2];
-            if (flags & F_RESID) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        rres[j][hh] = make_uint4(0, 0, 0, 0);
-                        if (act16[j] && valid) {
-                            const size_t off = base_b + static_cast<size_t>((cc16[j] >> 3) + hh) * plane +
-                                               (static_cast<size_t>(ho16[j]) * Wo + wo16[j]) * 8;
-                            rres[j][hh] = __ldg(reinterpret_cast<const uint4*>(a.resid + off));
+                // Stage this tile's per-row constants (bias, TAT scale+1, TAT shift) and per-16-column-group
+                // addressing in shared memory: one global load per constant, issued before the accumulator wait.
+                Cst* cb = cst + abuf;
+                if (et < a.n_acc) {
+                    const int nn = n0 + et;
+                    float bv = 0.0f, gv = 0.0f, ev = 0.0f;
+                    if (nn < a.n_total) {
+                        bv = __ldg(a.bias + nn);
+                        if (flags & F_AFF) {
+                            int cc = nn, i, j;
+                            if (flags & F_SHUF) packed_row_to_cij(nn, s, a.cout_p, cc, i, j);
+                            gv = __ldg(a.g1p + static_cast<size_t>(t.b) * a.cout_p + cc);
+                            ev = __ldg(a.beta + static_cast<size_t>(t.b) * a.cout_p + cc);
                         }
                     }
-            }
+                    cb->bias[et] = bv; cb->g1p[et] = gv; cb->beta[et] = ev;
+                } else if (et >= 256 && et < 256 + 2 * MAX_GROUPS) {
+                    const int ch = et - 256;                    // chunk = 8 packed rows
+                    const int nn = n0 + ch * 8;
+                    int cc = nn, i = 0, j = 0;
+                    if (flags & F_SHUF) packed_row_to_cij(nn, s, a.cout_p, cc, i, j);
+                    ChunkInfo ci;
+                    ci.goff = static_cast<long long>(cc >> 3) * static_cast<long long>(plane) + (static_cast<long long>(i) * Wo + j) * 8;
+                    ci.cc = cc;
+                    ci.ij = i | (j << 16);
+                    cb->chk[ch] = ci;
+                }
 
-            // constants visible to all epilogue warps; also orders this tile's writes to cb after every warp's
-            // reads of the same buffer two tiles ago
-            named_bar_sync(1, 32 * N_EPI_WARPS);
-            mbar_wait(p.tfull + abuf * 8, aphase);
-            tc_fence_after();
-            const uint32_t taddr = p.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (abuf * MT + mt) * ACC_COLS;
+                // constants visible to all epilogue warps; also orders this tile's writes to cb after every warp's
+                // reads of the same buffer two tiles ago
+                named_bar_sync(1, 32 * N_EPI_WARPS);
 
-            uint32_t v[2][16];
-            if (act16[0]) tmem_ld16(taddr + half * 16, v[0]);
+                bool act16[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (act16[j]) {                                           // CTA-uniform
-                    tmem_ld_wait();
-                    if (j + 1 < 4 && act16[(j + 1) & 3]) tmem_ld16(taddr + (half + 2 * (j + 1)) * 16, v[(j + 1) & 1]);
+                for (int j = 0; j < 4; ++j) {
+                    const int g16 = cs + G::CS * j;
+                    act16[j] = (g16 * 16 < a.n_acc) && (n0 + g16 * 16 < a.n_total);
+                }
+
+                // Residual prefetch: issued before waiting for the accumulator so the HBM latency hides
+                // behind the MMAs of this tile.
+                uint4 rres[4][2];
+                if (flags & F_RESID) {
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const size_t off = base_b + static_cast<size_t>((cc16[j] >> 3) + hh) * plane +
-                                           (static_cast<size_t>(ho16[j]) * Wo + wo16[j]) * 8;
-                        epilogue_chunk<ACT, FLAGS>(a, flags, &v[j & 1][hh * 8], cb, (half + 2 * j) * 16 + hh * 8,
-                                                   cc16[j] + hh * 8, t.b, off, valid, rres[j][hh], ho16[j], wo16[j], Ho, Wo);
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            rres[j][hh] = make_uint4(0, 0, 0, 0);
+                            if (act16[j] && valid) {
+                                const size_t off = base_b + pix + static_cast<size_t>(cb->chk[2 * (cs + G::CS * j) + hh].goff);
+                                rres[j][hh] = __ldg(reinterpret_cast<const uint4*>(a.resid + off));
+                            }
+                        }
+                }
+
+                mbar_wait(p.tfull + abuf * 8, aphase);
+                tc_fence_after();
+                const uint32_t taddr = p.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + abuf * BUF_COLS + mt * G::ACC_STRIDE;
+
+                uint32_t v[2][16];
+                if (act16[0]) tmem_ld16(taddr + cs * 16, v[0]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (act16[j]) {                                           // CTA-uniform
+                        const int g16 = cs + G::CS * j;
+                        tmem_ld_wait();
+                        if (j + 1 < 4 && act16[(j + 1) & 3]) tmem_ld16(taddr + (cs + G::CS * (j + 1)) * 16, v[(j + 1) & 1]);
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const ChunkInfo ci = cb->chk[2 * g16 + hh];
+                            const int ho = h * s + (ci.ij & 0xffff), wo = w * s + (ci.ij >> 16);
+                            const size_t off = base_b + pix + static_cast<size_t>(ci.goff);
+                            epilogue_chunk<ACT, FLAGS>(a, flags, &v[j & 1][hh * 8], cb, g16 * 16 + hh * 8, ci.cc,
+                                                       t.b, off, valid, rres[j][hh], ho, wo, Ho, Wo);
+                        }
                     }
                 }
+                // all TMEM reads of this warp for this buffer are complete -> hand it back to the leader's MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader + abuf * 8);
+                abuf ^= 1;
+                if (abuf == 0) aphase ^= 1;
             }
-            // all TMEM reads of this warp for this buffer are complete -> hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p.tempty + abuf * 8);
-            abuf ^= 1;
-            if (abuf == 0) aphase ^= 1;
         }
     }
 
+    // both CTAs done (the leader's MMAs write the peer's TMEM; the peer's loads credit the leader's barriers)
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(p.tmem_base, TMEM_COLS);
+        tmem_dealloc_pair(p.tmem_base, TMEM_COLS);
     }
 }
 
@@ -417,11 +519,69 @@ static int make_map_u64_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64
 
 static int g_num_sms = 0;
 
-int choose_n_acc(int n_total) {
-    // fewest N tiles with N_ACC <= 128, then the smallest multiple of 16 that covers them evenly
-    int tiles = (n_total + 127) / 128;
-    int per   = (n_total + tiles - 1) / tiles;
-    return round_up(per, 16);
+static int a_stage_bytes(int mt) { return mt == 2 ? Geo<2>::A_STAGE_B : Geo<1>::A_STAGE_B; }
+static int fixed_smem_bytes() { return BAR_BYTES + 2 * static_cast<int>(sizeof(Cst)); }
+
+// Rows per n-tile.  The pair keeps taps*Kp*n_acc*2 bytes of weights resident (half per CTA) next to at least
+// MIN_STAGES activation stages.  Among the sizes that fit, minimise (padded N) x (shared-memory operand-bandwidth
+// penalty of a narrow N: one UMMA reads 32*(128 + n/2) B per SM in 128*n/256 cycles); ties go to the larger tile.
+int choose_n_acc(int n_total, int ksteps, int taps) {
+    int best = 0;
+    double best_cost = 0.0;
+    for (int n = 16; n <= 256; n += 16) {
+        const int mt = n <= 128 ? 2 : 1;
+        const long long b_half = 1LL * ksteps * taps * 2 * (n / 2) * 16;
+        if (b_half + 1LL * MIN_STAGES * a_stage_bytes(mt) + fixed_smem_bytes() > SMEM_LIMIT) break;
+        const int tiles = (n_total + n - 1) / n;
+        const double bw = 8192.0 * (1.0 / n + 1.0 / 256.0) / 110.0;
+        const double cost = static_cast<double>(tiles) * n * (bw > 1.0 ? bw : 1.0);
+        if (best == 0 || cost <= best_cost) { best = n; best_cost = cost; }
+        if (n >= n_total) break;
+    }
+    return best;
+}
+
+template <int MT>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& a, int act, size_t smem_bytes,
+                       cudaStream_t stream) {
+    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const ConvTcArgs);
+    // specialised epilogues for the launch shapes of the decoder cascade, generic otherwise
+    KernelFn fn = conv_tc_kernel<MT, -1, -1>;
+    int slot = 0;
+    const int fl = a.flags;
+#define BNERV_PICK(ID, ACT_, FL_)                                              \
+    if (act == (ACT_) && fl == (FL_)) { fn = conv_tc_kernel<MT, (ACT_), (FL_)>; slot = (ID); }
+    BNERV_PICK(1, BNERV_ACT_SIN, F_AFF | F_PRE)                 // up-conv 1x1 / s=1 (+sin, x0 and u)
+    BNERV_PICK(2, BNERV_ACT_SIN, F_AFF | F_PRE | F_SHUF)        // up-conv + PixelShuffle
+    BNERV_PICK(3, BNERV_ACT_GELU, F_AFF)                        // conv0 + GELU + TAT affine
+    BNERV_PICK(4, BNERV_ACT_NONE, F_RESID | F_PRE)              // conv1 + residual
+    BNERV_PICK(5, BNERV_ACT_NONE, F_PRE | F_SHUF)               // E-NeRV stage-0 up-conv
+    BNERV_PICK(6, BNERV_ACT_TANH01, F_NCHW)                     // head conv -> image
+#undef BNERV_PICK
+    static bool smem_set[8] = {false, false, false, false, false, false, false, false};
+    if (!smem_set[slot]) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) return set_error(static_cast<int>(e), "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+        smem_set[slot] = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * a.n_pairs);
+    cfg.blockDim = dim3(N_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, tmA, tmB, a);
+    if (e != cudaSuccess) {
+        count_launch();
+        return set_error(static_cast<int>(e), "conv_tc_kernel launch: %s", cudaGetErrorString(e));
+    }
+    return check_launch("conv_tc_kernel");
 }
 
 }  // namespace bnerv
@@ -439,6 +599,7 @@ extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, con
     if ((g1p != nullptr) != (out_aff != nullptr)) return set_error(BNERV_E_BADARG, "conv_fused: out_aff requires g1p/beta and vice versa");
     if (!out_pre && !out_aff && !out_nchw) return set_error(BNERV_E_BADARG, "conv_fused: no output");
     if (act < BNERV_ACT_NONE || act > BNERV_ACT_TANH01) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: act %d", act);
+    if (s > 0xffff) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: PixelShuffle factor %d", s);
     const uintptr_t align_or = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) |
                                reinterpret_cast<uintptr_t>(bias_packed) | reinterpret_cast<uintptr_t>(resid) |
                                reinterpret_cast<uintptr_t>(g1p) | reinterpret_cast<uintptr_t>(beta) |
@@ -452,20 +613,28 @@ extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, con
     a.ksteps     = cin_p / 16;
     a.taps       = k * k;
     a.n_total    = s * s * cout_p;
-    a.n_acc      = choose_n_acc(a.n_total);
+    a.n_acc      = choose_n_acc(a.n_total, a.ksteps, a.taps);
+    if (a.n_acc == 0)
+        return set_error(BNERV_E_UNSUPPORTED, "conv_fused: Cin = %d too wide for shared-memory-resident weights (k = %d)", Cin, k);
+    a.n_half     = a.n_acc / 2;
     a.n_tiles    = (a.n_total + a.n_acc - 1) / a.n_acc;
     a.cout = Cout; a.cout_p = cout_p; a.s = s; a.act = act;
-    a.tiles_x = (W + TILE_W - 1) / TILE_W;
+    const int mt = a.n_acc <= 128 ? 2 : 1;
+    const int tile_w = 8 * mt;
+    a.tiles_x = (W + tile_w - 1) / tile_w;
     a.tiles_y = (H + TILE_H - 1) / TILE_H;
-    const long long total = 1LL * a.n_tiles * B * a.tiles_x * a.tiles_y;
-    if (total > 0x7fffffffLL) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: too many tiles");
-    a.total_tiles   = static_cast<int>(total);
-    a.b_stage_bytes = a.taps * 2 * a.n_acc * 16;
-    const int stage_bytes = A_STAGE_B + a.b_stage_bytes;
-    const int bar_bytes   = BAR_BYTES + CST_BYTES;
-    int stages = (SMEM_LIMIT - bar_bytes - 1024) / stage_bytes;
+    a.pairs_x = (a.tiles_x + 1) / 2;
+    const long long pair_tiles = 1LL * B * a.tiles_y * a.pairs_x;
+    if (pair_tiles > 0x3fffffffLL) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: too many tiles");
+    a.pair_tiles    = static_cast<int>(pair_tiles);
+    if (pair_tiles * a.n_tiles > 0x3fffffffLL) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: too many tiles");
+    a.work_total    = a.pair_tiles * a.n_tiles;
+    a.b_kstep_bytes = a.taps * 2 * a.n_half * 16;
+    a.b_bytes       = a.ksteps * a.b_kstep_bytes;
+    const int a_stage = a_stage_bytes(mt);
+    int stages = (SMEM_LIMIT - fixed_smem_bytes() - a.b_bytes) / a_stage;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
-    if (stages < 2) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: stage of %d bytes does not fit twice", stage_bytes);
+    if (stages < MIN_STAGES) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: %d activation stages do not fit", MIN_STAGES);
     a.stages = stages;
     a.bias = bias_packed; a.g1p = g1p; a.beta = beta;
     a.resid = static_cast<const __half*>(resid);
@@ -474,44 +643,26 @@ extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, con
     a.out_nchw = out_nchw;
     a.flags = (resid ? F_RESID : 0) | (g1p ? F_AFF : 0) | (out_pre ? F_PRE : 0) | (out_nchw ? F_NCHW : 0) | (s > 1 ? F_SHUF : 0);
 
-    CUtensorMap tmA, tmB;
-    // activations as u64: dims {2W, H, B*cin_groups}; strides {W*16, H*W*16} bytes
-    int rc = make_map_u64_3d(&tmA, x, 2ull * W, H, 1ull * B * a.cin_groups, 16ull * W, 16ull * W * H,
-                             2 * HALO_W, HALO_H, 2);
-    if (rc) return rc;
-    // packed weights as u64: dims {2*Np, Kp/8, taps}; strides {Np*16, Np*16*Kp/8}
-    rc = make_map_u64_3d(&tmB, w_packed, 2ull * a.n_total, a.cin_groups, a.taps, 16ull * a.n_total,
-                         16ull * a.n_total * a.cin_groups, 2 * a.n_acc, 2, a.taps);
-    if (rc) return rc;
-
     if (g_num_sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (g_num_sms <= 0) g_num_sms = 148;
     }
-    const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + bar_bytes;
-    const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
-    // specialised epilogues for the five launch shapes of the decoder cascade, generic otherwise
-    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const ConvTcArgs);
-    KernelFn fn = conv_tc_kernel<-1, -1>;
-    int slot = 0;
-    const int fl = a.flags;
-#define BNERV_PICK(ID, ACT_, FL_)                                              \
-    if (act == (ACT_) && fl == (FL_)) { fn = conv_tc_kernel<(ACT_), (FL_)>; slot = (ID); }
-    BNERV_PICK(1, BNERV_ACT_SIN, F_AFF | F_PRE)                 // up-conv 1x1 / s=1 (+sin, x0 and u)
-    BNERV_PICK(2, BNERV_ACT_SIN, F_AFF | F_PRE | F_SHUF)        // up-conv + PixelShuffle
-    BNERV_PICK(3, BNERV_ACT_GELU, F_AFF)                        // conv0 + GELU + TAT affine
-    BNERV_PICK(4, BNERV_ACT_NONE, F_RESID | F_PRE)              // conv1 + residual
-    BNERV_PICK(5, BNERV_ACT_NONE, F_PRE | F_SHUF)               // E-NeRV stage-0 up-conv
-    BNERV_PICK(6, BNERV_ACT_TANH01, F_NCHW)                     // head conv -> image
-#undef BNERV_PICK
-    static bool smem_set[8] = {false, false, false, false, false, false, false, false};
-    if (!smem_set[slot]) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e != cudaSuccess) return set_error(static_cast<int>(e), "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
-        smem_set[slot] = true;
-    }
-    fn<<<grid, N_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, a);
-    return check_launch("conv_tc_kernel");
+    const int max_pairs = g_num_sms / 2;
+    a.n_pairs = a.work_total < max_pairs ? a.work_total : max_pairs;
+
+    CUtensorMap tmA, tmB;
+    // activations as u64: dims {2W, H, B*cin_groups}; strides {W*16, H*W*16} bytes
+    int rc = make_map_u64_3d(&tmA, x, 2ull * W, H, 1ull * B * a.cin_groups, 16ull * W, 16ull * W * H,
+                             2 * (tile_w + 2), HALO_H, 2);
+    if (rc) return rc;
+    // packed weights as u64: dims {2*Np, Kp/8, taps}; strides {Np*16, Np*16*Kp/8}; one box = one K step of one CTA's half
+    rc = make_map_u64_3d(&tmB, w_packed, 2ull * a.n_total, a.cin_groups, a.taps, 16ull * a.n_total,
+                         16ull * a.n_total * a.cin_groups, 2 * a.n_half, 2, a.taps);
+    if (rc) return rc;
+
+    const size_t smem_bytes = static_cast<size_t>(a.b_bytes) + static_cast<size_t>(stages) * a_stage + fixed_smem_bytes();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return mt == 2 ? launch_conv<2>(tmA, tmB, a, act, smem_bytes, st) : launch_conv<1>(tmA, tmB, a, act, smem_bytes, st);
 }

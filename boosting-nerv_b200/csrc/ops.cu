@@ -20,11 +20,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
         r /= np;
         const int kg  = r % (cin_p >> 3);
         const int tap = r / (cin_p >> 3);
-        const int sub = n / cout_p, c = n - sub * cout_p;
+        int c, i, j;
+        packed_row_to_cij(n, s, cout_p, c, i, j);
         const int ci = kg * 8 + kk;
         float v = 0.0f;
         if (c < Cout && ci < Cin) {
-            const int o = c * s * s + sub;        // reference output channel feeding (c, i, j), sub = i*s+j
+            const int o = c * s * s + i * s + j;  // reference output channel feeding (c, i, j)
             v = w[(static_cast<size_t>(o) * Cin + ci) * k * k + tap];
         }
         wp[idx] = __float2half_rn(v);
@@ -34,8 +35,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
 __global__ void pack_bias_kernel(const float* __restrict__ bias, int Cout, int s, int cout_p, float* __restrict__ bp) {
     const int np = s * s * cout_p;
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < np; n += gridDim.x * blockDim.x) {
-        const int sub = n / cout_p, c = n - sub * cout_p;
-        bp[n] = (bias != nullptr && c < Cout) ? bias[c * s * s + sub] : 0.0f;
+        int c, i, j;
+        packed_row_to_cij(n, s, cout_p, c, i, j);
+        bp[n] = (bias != nullptr && c < Cout) ? bias[c * s * s + i * s + j] : 0.0f;
     }
 }
 
