@@ -123,6 +123,7 @@ __device__ __forceinline__ WorkRange work_range(const ConvTcArgs& a, uint32_t pa
 
 // epilogue feature flags (compile-time in the specialised instantiations, run-time in the generic one)
 constexpr int F_RESID = 1, F_AFF = 2, F_PRE = 4, F_NCHW = 8, F_SHUF = 16;
+constexpr int F_WIDE = 32;   // s == 2 row packing: the two chunks of a group are 32 contiguous output bytes
 
 template <int ACT>
 __device__ __forceinline__ float2 act2_rt(float2 x, int act) {
@@ -136,49 +137,87 @@ __device__ __forceinline__ float2 act2_rt(float2 x, int act) {
     }
 }
 
-// One 8-channel group of one pixel: bias + activation (+ residual) (+ affine) and the stores.
-// `col` is the packed row relative to the n-tile; all lanes read the same constants (LDS broadcast).
+// 256-bit store (STG.E.ENL2.256): both horizontal PixelShuffle neighbours of a pixel's 8 channels in one request.
+__device__ __forceinline__ void st_global_32B(__half* p, const uint4& lo, const uint4& hi) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+}
+
+__device__ __forceinline__ uint4 pack8(const float2* x) {
+    uint4 o;
+    o.x = pack_h2_satfinite(x[0]); o.y = pack_h2_satfinite(x[1]);
+    o.z = pack_h2_satfinite(x[2]); o.w = pack_h2_satfinite(x[3]);
+    return o;
+}
+
+// Epilogue of one 16-column accumulator group of one pixel = two chunks of 8 channels (chunk hh = columns hh*8..+7):
+// bias + activation (+ residual) (+ TAT affine) and the stores.  Constants are LDS broadcasts from the tile's Cst;
+// the bias is fetched by the caller BEFORE the accumulator wait, scale/shift are requested right after the bias add
+// so their latency hides behind the activation math.
+struct GroupAddr { size_t off[2]; int cc[2], ho[2], wo[2]; };
+
 template <int ACT, int FLAGS>
-__device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, const uint32_t* v, const Cst* cb, int col,
-                                               int cc, int b, size_t off, bool valid, const uint4& rr, int ho, int wo,
-                                               int Ho, int Wo) {
-    const float4 b0 = *reinterpret_cast<const float4*>(cb->bias + col);
-    const float4 b1 = *reinterpret_cast<const float4*>(cb->bias + col + 4);
-    float2 x[4];
-    x[0] = add2(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(b0.x, b0.y));
-    x[1] = add2(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(b0.z, b0.w));
-    x[2] = add2(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(b1.x, b1.y));
-    x[3] = add2(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(b1.z, b1.w));
+__device__ __forceinline__ void epilogue_group(const ConvTcArgs& a, int flags, const uint32_t* v, const float4* bs,
+                                               const Cst* cb, int col, int b, const GroupAddr& ga, bool valid,
+                                               const uint4* rr, int Ho, int Wo) {
+    float2 x[8];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) x[p] = act2_rt<ACT>(x[p], a.act);
+    for (int p = 0; p < 4; ++p) {
+        x[2 * p]     = add2(make_float2(__uint_as_float(v[4 * p]),     __uint_as_float(v[4 * p + 1])), make_float2(bs[p].x, bs[p].y));
+        x[2 * p + 1] = add2(make_float2(__uint_as_float(v[4 * p + 2]), __uint_as_float(v[4 * p + 3])), make_float2(bs[p].z, bs[p].w));
+    }
+    float4 gg[4], ee[4];
+    if (flags & F_AFF) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            gg[p] = *reinterpret_cast<const float4*>(cb->g1p + col + 4 * p);
+            ee[p] = *reinterpret_cast<const float4*>(cb->beta + col + 4 * p);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 8; ++p) x[p] = act2_rt<ACT>(x[p], a.act);
     if (flags & F_RESID) {
-        x[0] = add2(x[0], unpack_h2(rr.x)); x[1] = add2(x[1], unpack_h2(rr.y));
-        x[2] = add2(x[2], unpack_h2(rr.z)); x[3] = add2(x[3], unpack_h2(rr.w));
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            x[4 * hh + 0] = add2(x[4 * hh + 0], unpack_h2(rr[hh].x)); x[4 * hh + 1] = add2(x[4 * hh + 1], unpack_h2(rr[hh].y));
+            x[4 * hh + 2] = add2(x[4 * hh + 2], unpack_h2(rr[hh].z)); x[4 * hh + 3] = add2(x[4 * hh + 3], unpack_h2(rr[hh].w));
+        }
     }
     if (!valid) return;
     if (flags & F_PRE) {
-        uint4 o;
-        o.x = pack_h2_satfinite(x[0]); o.y = pack_h2_satfinite(x[1]);
-        o.z = pack_h2_satfinite(x[2]); o.w = pack_h2_satfinite(x[3]);
-        *reinterpret_cast<uint4*>(a.out_pre + off) = o;
+        const uint4 o0 = pack8(x), o1 = pack8(x + 4);
+        if (flags & F_WIDE) {
+            st_global_32B(a.out_pre + ga.off[0], o0, o1);
+        } else {
+            *reinterpret_cast<uint4*>(a.out_pre + ga.off[0]) = o0;
+            *reinterpret_cast<uint4*>(a.out_pre + ga.off[1]) = o1;
+        }
     }
     if (flags & F_NCHW) {
-        const float xs[8] = {x[0].x, x[0].y, x[1].x, x[1].y, x[2].x, x[2].y, x[3].x, x[3].y};
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (cc + k < a.cout) a.out_nchw[(static_cast<size_t>(b * a.cout + cc + k) * Ho + ho) * Wo + wo] = xs[k];
+        for (int hh = 0; hh < 2; ++hh) {
+            const float xs[8] = {x[4 * hh].x, x[4 * hh].y, x[4 * hh + 1].x, x[4 * hh + 1].y,
+                                 x[4 * hh + 2].x, x[4 * hh + 2].y, x[4 * hh + 3].x, x[4 * hh + 3].y};
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (ga.cc[hh] + k < a.cout)
+                    a.out_nchw[(static_cast<size_t>(b * a.cout + ga.cc[hh] + k) * Ho + ga.ho[hh]) * Wo + ga.wo[hh]] = xs[k];
+        }
     }
     if (flags & F_AFF) {
-        const float4 g0 = *reinterpret_cast<const float4*>(cb->g1p + col);
-        const float4 g1 = *reinterpret_cast<const float4*>(cb->g1p + col + 4);
-        const float4 e0 = *reinterpret_cast<const float4*>(cb->beta + col);
-        const float4 e1 = *reinterpret_cast<const float4*>(cb->beta + col + 4);
-        uint4 o;
-        o.x = pack_h2_satfinite(fma2(x[0], make_float2(g0.x, g0.y), make_float2(e0.x, e0.y)));
-        o.y = pack_h2_satfinite(fma2(x[1], make_float2(g0.z, g0.w), make_float2(e0.z, e0.w)));
-        o.z = pack_h2_satfinite(fma2(x[2], make_float2(g1.x, g1.y), make_float2(e1.x, e1.y)));
-        o.w = pack_h2_satfinite(fma2(x[3], make_float2(g1.z, g1.w), make_float2(e1.z, e1.w)));
-        *reinterpret_cast<uint4*>(a.out_aff + off) = o;
+        float2 y[8];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            y[2 * p]     = fma2(x[2 * p],     make_float2(gg[p].x, gg[p].y), make_float2(ee[p].x, ee[p].y));
+            y[2 * p + 1] = fma2(x[2 * p + 1], make_float2(gg[p].z, gg[p].w), make_float2(ee[p].z, ee[p].w));
+        }
+        const uint4 o0 = pack8(y), o1 = pack8(y + 4);
+        if (flags & F_WIDE) {
+            st_global_32B(a.out_aff + ga.off[0], o0, o1);
+        } else {
+            *reinterpret_cast<uint4*>(a.out_aff + ga.off[0]) = o0;
+            *reinterpret_cast<uint4*>(a.out_aff + ga.off[1]) = o1;
+        }
     }
 }
 
@@ -424,20 +463,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     act16[j] = (g16 * 16 < a.n_acc) && (n0 + g16 * 16 < a.n_total);
                 }
 
+                // output addressing of one of this thread's groups: arithmetic for plain convs, the staged table for
+                // PixelShuffle (recomputed where needed instead of kept live across the accumulator wait)
+                auto group_addr = [&](int g16) {
+                    GroupAddr ga;
+                    if (flags & F_SHUF) {
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const ChunkInfo ci = cb->chk[2 * g16 + ((flags & F_WIDE) ? 0 : hh)];
+                            ga.off[hh] = base_b + pix + static_cast<size_t>(ci.goff) + ((flags & F_WIDE) ? 8 * hh : 0);
+                            ga.cc[hh] = ci.cc;
+                            ga.ho[hh] = h * s + (ci.ij & 0xffff);
+                            ga.wo[hh] = w * s + (ci.ij >> 16) + ((flags & F_WIDE) ? hh : 0);
+                        }
+                    } else {
+                        const int cc = n0 + g16 * 16;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            ga.off[hh] = base_b + pix + static_cast<size_t>((cc >> 3) + hh) * plane;
+                            ga.cc[hh] = cc + 8 * hh;
+                            ga.ho[hh] = h;
+                            ga.wo[hh] = w;
+                        }
+                    }
+                    return ga;
+                };
+
                 // Residual prefetch: issued before waiting for the accumulator so the HBM latency hides
                 // behind the MMAs of this tile.
                 uint4 rres[4][2];
                 if (flags & F_RESID) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < 4; ++j) {
+                        const GroupAddr ga = group_addr(cs + G::CS * j);
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
                             rres[j][hh] = make_uint4(0, 0, 0, 0);
-                            if (act16[j] && valid) {
-                                const size_t off = base_b + pix + static_cast<size_t>(cb->chk[2 * (cs + G::CS * j) + hh].goff);
-                                rres[j][hh] = __ldg(reinterpret_cast<const uint4*>(a.resid + off));
-                            }
+                            if (act16[j] && valid) rres[j][hh] = __ldg(reinterpret_cast<const uint4*>(a.resid + ga.off[hh]));
                         }
+                    }
                 }
 
                 mbar_wait(p.tfull + abuf * 8, aphase);
@@ -449,17 +513,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (act16[j]) {                                           // CTA-uniform
-                        const int g16 = cs + G::CS * j;
+                        const int col = (cs + G::CS * j) * 16;
+                        float4 bs[4];
+#pragma unroll
+                        for (int p4 = 0; p4 < 4; ++p4) bs[p4] = *reinterpret_cast<const float4*>(cb->bias + col + 4 * p4);
                         tmem_ld_wait();
                         if (j + 1 < 4 && act16[(j + 1) & 3]) tmem_ld16(taddr + (cs + G::CS * (j + 1)) * 16, v[(j + 1) & 1]);
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const ChunkInfo ci = cb->chk[2 * g16 + hh];
-                            const int ho = h * s + (ci.ij & 0xffff), wo = w * s + (ci.ij >> 16);
-                            const size_t off = base_b + pix + static_cast<size_t>(ci.goff);
-                            epilogue_chunk<ACT, FLAGS>(a, flags, &v[j & 1][hh * 8], cb, g16 * 16 + hh * 8, ci.cc,
-                                                       t.b, off, valid, rres[j][hh], ho, wo, Ho, Wo);
-                        }
+                        const GroupAddr ga = group_addr(cs + G::CS * j);
+                        epilogue_group<ACT, FLAGS>(a, flags, v[j & 1], bs, cb, col, t.b, ga, valid, rres[j], Ho, Wo);
                     }
                 }
                 // all TMEM reads of this warp for this buffer are complete -> hand it back to the leader's MMA warp
@@ -552,7 +613,8 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
 #define BNERV_PICK(ID, ACT_, FL_)                                              \
     if (act == (ACT_) && fl == (FL_)) { fn = conv_tc_kernel<MT, (ACT_), (FL_)>; slot = (ID); }
     BNERV_PICK(1, BNERV_ACT_SIN, F_AFF | F_PRE)                 // up-conv 1x1 / s=1 (+sin, x0 and u)
-    BNERV_PICK(2, BNERV_ACT_SIN, F_AFF | F_PRE | F_SHUF)        // up-conv + PixelShuffle
+    BNERV_PICK(2, BNERV_ACT_SIN, F_AFF | F_PRE | F_SHUF)        // up-conv + PixelShuffle (s = 3, 5)
+    BNERV_PICK(7, BNERV_ACT_SIN, F_AFF | F_PRE | F_SHUF | F_WIDE)   // up-conv + PixelShuffle(2), 32-byte stores
     BNERV_PICK(3, BNERV_ACT_GELU, F_AFF)                        // conv0 + GELU + TAT affine
     BNERV_PICK(4, BNERV_ACT_NONE, F_RESID | F_PRE)              // conv1 + residual
     BNERV_PICK(5, BNERV_ACT_NONE, F_PRE | F_SHUF)               // E-NeRV stage-0 up-conv
@@ -641,7 +703,7 @@ extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, con
     a.out_pre = static_cast<__half*>(out_pre);
     a.out_aff = static_cast<__half*>(out_aff);
     a.out_nchw = out_nchw;
-    a.flags = (resid ? F_RESID : 0) | (g1p ? F_AFF : 0) | (out_pre ? F_PRE : 0) | (out_nchw ? F_NCHW : 0) | (s > 1 ? F_SHUF : 0);
+    a.flags = (resid ? F_RESID : 0) | (g1p ? F_AFF : 0) | (out_pre ? F_PRE : 0) | (out_nchw ? F_NCHW : 0) | (s > 1 ? F_SHUF : 0) | (s == 2 ? F_WIDE : 0);
 
     if (g_num_sms == 0) {
         int dev = 0;
