@@ -8,6 +8,10 @@ activation workspaces, and runs the block cascade with three fused-conv launches
 plus ONE launch that evaluates every SFT layer's (scale, shift) MLP for the frame(s), and the head conv
 (+tanh*0.5+0.5) that writes the NCHW f32 image.  (model_blocks.py:34-46, 74-105; model_*.py forward.)
 
+The whole per-frame sequence (position encoding, stem MLPs, SFT table, cascade, head) is captured ONCE per input
+shape into a CUDA graph and replayed: ~40 launches per frame with no host work in between, the fused convs chained
+by programmatic dependent launch.  ``engine.use_graph = False`` runs the same sequence eagerly.
+
 Weights are re-packed only when the effective tensor (``dequant_w ?? weight``) changed — detected through
 tensor identity + in-place version counters, so optimiser steps and ``cal_params`` invalidate the cache.
 """
@@ -106,9 +110,23 @@ def _sft_tensors(sft):
     return out
 
 
+class _Captured:
+    """One captured decode: static input buffers, the graph, and its (static) outputs."""
+    __slots__ = ("graph", "inputs", "outputs")
+
+
 class DecoderEngine:
+    use_graph = True
+
     def __init__(self, model):
         self.model = model
+        self.kind = {"HNeRV_Boost": "hnerv", "NeRV_Boost": "nerv", "ENeRV_Boost": "enerv"}.get(type(model).__name__)
+        self._graphs = {}      # (input shapes/dtypes, keep) -> _Captured
+        self._wkey = None
+        enc = getattr(model, "encoder", None)
+        skip = set() if enc is None else {id(m) for m in enc.modules()}     # the encoder is not on the decode path
+        self._wmods = [(m.__dict__, m._parameters) for m in model.modules()
+                       if isinstance(m, (nn.Conv2d, nn.Linear)) and id(m) not in skip]
         name = type(model).__name__
         if name == "HNeRV_Boost":
             blocks, self.t_mlp = list(model.decoder), model.stem_t
@@ -171,24 +189,86 @@ class DecoderEngine:
         return ws
 
     # -- entry points ------------------------------------------------------------------------------
-    def run_hnerv(self, img_embed, pe, keep=False):
-        """HNeRV_Boost.forward_decoder body (model_hnerv.py:264-277)."""
-        t_embed = self._mlp(self.t_mlp, pe.flatten(1).float())
-        return self.run_cascade(img_embed.float().contiguous(), t_embed, keep)
+    def weights_key(self):
+        """Identity + in-place version of every effective weight/bias the decode reads (torch stems included)."""
+        key = []
+        for d, prm in self._wmods:              # effective_weight() without nn.Module.__getattr__ (runs on every forward)
+            w = d.get("dequant_w")
+            if w is None:
+                w = prm["weight"]
+            b = d.get("dequant_b")
+            if b is None:
+                b = prm.get("bias")
+            key.append(id(w))
+            key.append(w._version)
+            if b is not None:
+                key.append(id(b))
+                key.append(b._version)
+        return tuple(key)
 
-    def run_nerv(self, pe, keep=False):
-        """NeRV_Boost.forward body after the position encoding (model_nerv.py:48-57)."""
+    def invalidate(self):
+        """Drop captured graphs (call after replacing weights when decoding through ``decode(check_weights=False)``)."""
+        self._graphs.clear()
+        self._wkey = None
+
+    def _body(self, inputs, keep):
+        """The full per-frame sequence for this model family; pure stream work.  Returns (img, outs, extra)."""
         m = self.model
-        v = pe.flatten(1).float()
-        x = self._mlp(m.stem, v).view(v.size(0), m.fc_dim, m.fc_h, m.fc_w)
-        t_embed = self._mlp(m.stem_t, v)
-        return self.run_cascade(x, t_embed, keep)
+        if self.kind == "hnerv":                # HNeRV_Boost.forward_decoder (model_hnerv.py:264-277); f64 PE -> f32 (:267)
+            img_embed, norm_idx = inputs
+            pe = m.pe_embed_t(norm_idx[:, None]).float()
+            t_embed = self._mlp(self.t_mlp, pe.flatten(1).float())
+            img, outs = self.run_cascade(img_embed.float().contiguous(), t_embed, keep)
+            return img, outs, None
+        if self.kind == "nerv":                 # NeRV_Boost.forward (model_nerv.py:47-57)
+            (t,) = inputs
+            v = m.pe_t(t[:, None].float()).flatten(1).float()
+            x = self._mlp(m.stem, v).view(v.size(0), m.fc_dim, m.fc_h, m.fc_w)
+            t_embed = self._mlp(m.stem_t, v)
+            img, outs = self.run_cascade(x, t_embed, keep)
+            return img, outs, None
+        (t,) = inputs                           # ENeRV_Boost.forward (model_enerv.py:281-313); transformer stem stays in torch
+        emb, t_manip = m._stem(t)
+        img, outs = self.run_cascade(emb.contiguous(), t_manip.flatten(1), keep)
+        return img, outs, t_manip
+
+    def decode(self, inputs, keep=False, check_weights=True):
+        """inputs: (img_embed, norm_idx) for HNeRV_Boost, (t,) otherwise.  Returns (img, outs, extra).
+        With graphs enabled the returned tensors are the graph's static outputs: they are overwritten by the next
+        decode of the same shape (callers that keep them must clone)."""
+        inputs = tuple(inputs)
+        if not inputs[0].is_cuda:
+            raise RuntimeError("bnerv_b200 engine needs CUDA tensors (no CPU path)")
+        if not self.use_graph:
+            return self._body(inputs, keep)
+        if check_weights:
+            wk = self.weights_key()
+            if wk != self._wkey:
+                self._graphs.clear()
+                self._wkey = wk
+        gkey = (tuple((tuple(t.shape), t.dtype) for t in inputs), keep)
+        cap = self._graphs.get(gkey)
+        if cap is None:
+            cap = self._capture(inputs, keep)
+            self._graphs[gkey] = cap
+        for dst, src in zip(cap.inputs, inputs):
+            dst.copy_(src, non_blocking=True)
+        cap.graph.replay()
+        return cap.outputs
+
+    def _capture(self, inputs, keep):
+        cap = _Captured()
+        cap.inputs = [t.detach().clone() for t in inputs]
+        self._body(cap.inputs, keep)            # eager warm-up: packs weights, builds workspaces / SFT tables, sets attributes
+        torch.cuda.synchronize()
+        cap.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cap.graph):
+            cap.outputs = self._body(cap.inputs, keep)
+        return cap
 
     def run_cascade(self, x, t_embed, keep=False):
         """x: [B, C, h, w] f32 NCHW stem output; t_embed: [B, ch_t] f32.  Returns (img, [block outputs]).
         keep: True = every block output as NCHW f32, "first" = only block 0's, False = none."""
-        if not x.is_cuda:
-            raise RuntimeError("bnerv_b200 engine needs CUDA tensors (no CPU path)")
         B, C, h, w = x.shape
         dev = x.device
         ws = self._workspace(B, h, w, dev)

@@ -94,6 +94,11 @@ class _BoostBase(nn.Module):
     def engine(self):
         return _engine_for(self)
 
+    def _own(self, t):
+        """forward() hands out tensors the caller owns (reference semantics); the engine's graph outputs are static
+        buffers that the next decode overwrites."""
+        return t.clone() if self.engine().use_graph else t
+
 
 def _decoder_widths(args, expansion):
     """Channel schedule of NeRV/E-NeRV stages (model_nerv.py:26-38): yields (stage, j, ngf, new_ngf, stride)."""
@@ -132,16 +137,17 @@ class NeRV_Boost(_BoostBase):
         self.out_bias, self.outf = args.out_bias, args.outf
 
     def decode(self, input):
-        """Asynchronous decode on the native path: image only, no host sync, no timing."""
+        """Asynchronous decode on the native path: image only, no host sync, no timing, weights assumed frozen
+        (``model.engine().invalidate()`` after changing them).  The returned image is overwritten by the next decode."""
         self._use_engine(input)
-        return self.engine().run_nerv(self.pe_t(input[:, None].float()), False)[0]
+        return self.engine().decode((input,), False, check_weights=False)[0]
 
     def forward(self, input, input_embed=None, norm_idx=None):
         t0 = time.time()
-        pe = self.pe_t(input[:, None].float())
         if self._use_engine(input):
-            img, outs = self.engine().run_nerv(pe, True if self.keep_intermediates else "first")
-            return img, outs, self._finish(t0)
+            img, outs, _ = self.engine().decode((input,), True if self.keep_intermediates else "first")
+            return self._own(img), [self._own(o) for o in outs], self._finish(t0)
+        pe = self.pe_t(input[:, None].float())
         x = self.stem(pe).view(pe.size(0), self.fc_dim, self.fc_h, self.fc_w)
         cond = self.stem_t(pe)
         outs = []
@@ -192,9 +198,15 @@ class ENeRV_Boost(_BoostBase):
         self.t_layers, self.norm_layers = None, None
 
     def _xy_grid(self, device):
-        ys = torch.arange(self.fc_h) / self.fc_h
-        xs = torch.arange(self.fc_w) / self.fc_w
-        return torch.stack(torch.meshgrid(ys, xs, indexing="ij"), dim=0).flatten(1, 2).to(device)
+        """The normalised (y, x) grid of model_enerv.py:281-282.  It is frame-invariant, so it is built once per
+        device (same values, same dtype) instead of on the host for every call - which also keeps the decode
+        capturable into a CUDA graph (no pageable H2D copy on the stream)."""
+        cache = self.__dict__.setdefault("_xy_cache", {})
+        if device not in cache:
+            ys = torch.arange(self.fc_h) / self.fc_h
+            xs = torch.arange(self.fc_w) / self.fc_w
+            cache[device] = torch.stack(torch.meshgrid(ys, xs, indexing="ij"), dim=0).flatten(1, 2).to(device)
+        return cache[device]
 
     def _stem(self, input):
         """Everything ahead of the conv cascade (model_enerv.py:281-303): returns (emb NCHW, t_manipulate)."""
@@ -211,18 +223,17 @@ class ENeRV_Boost(_BoostBase):
         return self.toconv(emb), t_manip
 
     def decode(self, input):
-        """Asynchronous decode on the native path: image only, no host sync, no timing."""
+        """Asynchronous decode on the native path (see NeRV_Boost.decode)."""
         self._use_engine(input)
-        emb, t_manip = self._stem(input)
-        return self.engine().run_cascade(emb.contiguous(), t_manip.flatten(1), False)[0]
+        return self.engine().decode((input,), False, check_weights=False)[0]
 
     def forward(self, input, input_embed=None, norm_idx=False):
         use_engine = self._use_engine(input)
         t0 = time.time()
-        emb, t_manip = self._stem(input)
         if use_engine:
-            img, outs = self.engine().run_cascade(emb.contiguous(), t_manip.flatten(1), self.keep_intermediates)
-            return img, [t_manip] + outs, self._finish(t0)
+            img, outs, t_manip = self.engine().decode((input,), self.keep_intermediates)
+            return self._own(img), [self._own(t_manip)] + [self._own(o) for o in outs], self._finish(t0)
+        emb, t_manip = self._stem(input)
         x, outs = emb, [t_manip]
         for layer in self.layers:
             x = layer((x, t_manip))
@@ -280,17 +291,17 @@ class HNeRV_Boost(_BoostBase):
         return code, quant, img_embed
 
     def decode(self, img_embed, norm_idx):
-        """Asynchronous decode on the native path: image only, no host sync, no timing."""
+        """Asynchronous decode on the native path (see NeRV_Boost.decode)."""
         self._use_engine(img_embed)
-        return self.engine().run_hnerv(img_embed, self.pe_embed_t(norm_idx[:, None]).float(), False)[0]
+        return self.engine().decode((img_embed, norm_idx), False, check_weights=False)[0]
 
     def forward_decoder(self, img_embed, norm_idx):
         use_engine = self._use_engine(img_embed)
         t0 = time.time()
-        pe = self.pe_embed_t(norm_idx[:, None]).float()          # f64 PE -> f32, model_hnerv.py:267
         if use_engine:
-            img, outs = self.engine().run_hnerv(img_embed, pe, self.keep_intermediates)
-            return img, [img_embed] + outs, self._finish(t0)
+            img, outs, _ = self.engine().decode((img_embed, norm_idx), self.keep_intermediates)
+            return self._own(img), [img_embed] + [self._own(o) for o in outs], self._finish(t0)
+        pe = self.pe_embed_t(norm_idx[:, None]).float()          # f64 PE -> f32, model_hnerv.py:267
         cond = self.stem_t(pe)
         x, outs = img_embed, [img_embed]
         for blk in self.decoder:

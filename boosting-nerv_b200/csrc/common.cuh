@@ -298,6 +298,11 @@ __device__ __host__ __forceinline__ uint32_t umma_idesc_f16_m128(int n) {
     return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
+// Programmatic dependent launch: wait until the preceding kernel in the stream has completed and its writes are
+// visible / allow the next kernel's CTAs to start their prologue as this kernel's CTAs retire.
+__device__ __forceinline__ void pdl_wait()              { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // CTA-pair (cta_group::2) primitives
 // ---------------------------------------------------------------------------------------------

@@ -27,6 +27,7 @@
 // warps 2..17 = epilogue (TMEM lane quarter = warp%4).  Two TMEM accumulator buffers (2 x 256 columns) let the
 // epilogue of tile i overlap the MMAs of tile i+1.  Persistent grid: 74 pairs, static round-robin tile order.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace bnerv {
@@ -244,6 +245,7 @@ __device__ __forceinline__ void producer_role(const ConvTcArgs& a, const Pipe& p
     const uint32_t wfull_leader = map_to_cta(p.wfull, 0);
     const WorkRange wr = work_range(a, p.pair);
     int wc = 0;                                   // weight loads issued so far
+    if (wr.begin >= wr.end) { pdl_wait(); pdl_launch_dependents(); }
     for (int it = wr.begin; it < wr.end; ++it) {
         const int nt = it / a.pair_tiles, pt = it - nt * a.pair_tiles;
         if (it == wr.begin || pt == 0) {
@@ -257,6 +259,13 @@ __device__ __forceinline__ void producer_role(const ConvTcArgs& a, const Pipe& p
             }
             __syncwarp();
             ++wc;
+            if (it == wr.begin) {
+                // The first weight set was requested above, overlapping the previous kernel's tail (programmatic
+                // dependent launch; packed weights are never written by a kernel that triggers early).  Activations
+                // are the previous kernel's output: wait for it to complete before the first halo-tile load.
+                pdl_wait();
+                pdl_launch_dependents();
+            }
         }
         {
             const TileCoord t = decode_tile<MT>(a, pt, p.rank);
@@ -413,6 +422,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const size_t plane = static_cast<size_t>(Ho) * Wo * 8;      // halves per 8-channel plane
         const uint32_t tempty_leader = map_to_cta(p.tempty, 0);
         const WorkRange wr = work_range(a, p.pair);
+        pdl_wait();            // residual / TAT tables come from earlier kernels; our stores must not overtake their readers
         for (int it = wr.begin; it < wr.end; ++it) {
             const int nt = it / a.pair_tiles, pt = it - nt * a.pair_tiles;
             const int n0 = nt * a.n_acc;
@@ -631,13 +641,16 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
     cfg.blockDim = dim3(N_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue + weight fetch overlap the previous kernel's tail
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("BNERV_NO_PDL") != nullptr;      // debugging switch
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = no_pdl ? 1 : 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, fn, tmA, tmB, a);
     if (e != cudaSuccess) {
         count_launch();

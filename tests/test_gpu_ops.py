@@ -140,6 +140,14 @@ CONV_CASES = [  # B, cin, cout, H, W, k, s, act, resid, affine
     (1, 86, 43, 20, 24, 3, 2, "sin", False, True),
     (1, 1, 1, 1, 1, 3, 1, "none", False, False),         # degenerate: single pixel, single channel
     (3, 12, 12, 1, 40, 3, 1, "sin", True, True),         # one-row image, batch 3
+    # CTA-pair / resident-weight structure (conv_tc.cu): n-tile passes, work ranges, both tile geometries
+    (1, 233, 233, 20, 30, 3, 1, "gelu", False, True),    # Kp=240: weights fit only as 3 n-tiles of 80 rows
+    (1, 135, 112, 24, 40, 3, 2, "sin", False, True),     # PixelShuffle(2) row packing over 4 n-tiles, 32-byte stores
+    (1, 64, 48, 12, 20, 3, 3, "sin", False, True),       # PixelShuffle(3): 432 rows, plain (i,j)-major packing
+    (1, 40, 100, 6, 8, 1, 5, "sin", False, True),        # 1x1 up-conv, 2800 rows: more n-tiles than pixel tiles
+    (1, 32, 200, 20, 24, 3, 1, "none", False, False),    # n_acc = 208 > 128: one row block per CTA (MT = 1)
+    (2, 48, 48, 40, 70, 3, 1, "none", True, False),      # batch 2, odd number of super-tiles per row, residual
+    (1, 16, 16, 16, 8, 3, 1, "none", False, False),      # a single super-tile: the pair's second CTA is all padding
 ]
 
 
@@ -214,3 +222,9 @@ def test_argument_errors_are_reported_not_launched(ops):
         ops.conv_fused(x, pc, 16, 4, 4, out_aff=torch.empty_like(x))
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.nchw_to_c8(torch.zeros(1, 1, 1, 1))
+    # a conv whose narrowest weight tile (16 rows x 9 taps x Kp) cannot stay resident in shared memory is refused
+    wide = ops.PackedConv(torch.zeros(16, 1400, 3, 3, device="cuda"), None, 1)
+    xw = torch.zeros(ops.c8_shape(1, 1400, 4, 4), dtype=torch.float16, device="cuda")
+    with pytest.raises(BnervError, match="too wide") as ei:
+        ops.conv_fused(xw, wide, 1400, 4, 4, out_pre=torch.empty(ops.c8_shape(1, 16, 4, 4), dtype=torch.float16, device="cuda"))
+    assert ei.value.code == -2

@@ -24,6 +24,17 @@ with torch.no_grad():
     for _ in range(3):
         run()
     torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(steps):
+        run()
+    g1.record()
+    torch.cuda.synchronize()
+    print(f"{cfg}: CUDA-graph replay {g0.elapsed_time(g1) / steps:.3f} ms/frame ({1e3 * steps / g0.elapsed_time(g1):.1f} frames/s)")
+    model.engine().use_graph = False          # per-launch events need eager launches
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
     ops.TIMING = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -34,7 +45,7 @@ with torch.no_grad():
 timing, ops.TIMING = ops.TIMING, None
 per = len(timing) // steps
 tot_ms = e0.elapsed_time(e1) / steps
-print(f"{cfg}: {tot_ms:.3f} ms/frame ({1e3 / tot_ms:.1f} frames/s), {per} fused-conv launches per frame")
+print(f"{cfg}: eager with per-launch events {tot_ms:.3f} ms/frame ({1e3 / tot_ms:.1f} frames/s), {per} fused-conv launches per frame")
 print(f"{'#':>3s} {'cin':>4s} {'cout':>4s} k s {'H':>5s} {'W':>5s} {'act':>6s} {'ms':>8s} {'share':>6s} {'TFLOP/s':>8s}")
 acc = 0.0
 for i in range(per):
