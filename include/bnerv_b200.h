@@ -18,9 +18,11 @@
  *              consecutive channels of one pixel, so a pixel row of one group is a dense run in HBM
  *              (TMA-friendly) and 8 neighbouring pixels of one group form one UMMA core matrix.
  *   packed conv weight : [taps][Kp/8][Np][8] __half (taps = k*k, Kp = round_up(Cin,16),
- *              Np = s*s*round_up(Cout,16)); row n' = (i*s + j)*Cout_p + c holds reference output
- *              channel c*s*s + i*s + j, i.e. PixelShuffle (model_blocks.py:204,217) is folded into
- *              the row order.  Rows/cols of padding are zero.
+ *              Np = s*s*round_up(Cout,16)); row n' holds reference output channel c*s*s + i*s + j,
+ *              i.e. PixelShuffle (model_blocks.py:204,217) is folded into the row order:
+ *              n' = (i*s + j)*Cout_p + c, except s == 2 where n' = ((i*Cout_p/8 + c/8)*2 + j)*8 + c%8
+ *              (both horizontal neighbours of a pixel in one 16-row group -> 32-byte stores).
+ *              The layout is private to bnerv_pack_conv_weight / bnerv_conv_fused.  Padding is zero.
  */
 #ifndef BNERV_B200_H_
 #define BNERV_B200_H_
@@ -76,7 +78,11 @@ int bnerv_pack_conv_weight(const float* w_oihw, const float* bias, int Cout, int
  *   out_pre  : C8 f16, receives x0 (may be NULL when out_aff is given)
  *   out_aff  : C8 f16, receives u  (NULL when g1p is NULL)
  *   out_nchw : f32 [B][Cout][H*s][W*s], receives x0 (after act) in the reference layout, or NULL
- * Computation: f16 operands, f32 accumulation (tcgen05.mma kind::f16, accumulators in TMEM).
+ * Computation: f16 operands, f32 accumulation (tcgen05.mma.cta_group::2 kind::f16, accumulators in TMEM);
+ * each CTA pair keeps its weight tile resident in shared memory, so Cin is limited to what fits there
+ * (k = 3: Cin <= ~1300; wider returns BNERV_E_UNSUPPORTED).  The launch uses programmatic dependent launch:
+ * w_packed / bias_packed must not be written by the kernel enqueued immediately before this call unless
+ * that kernel is one of this library's (none of which trigger early completion while writing them).
  * ---------------------------------------------------------------------------------------------- */
 int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W,
                      const void* w_packed, const float* bias_packed, int Cout, int k, int s,
