@@ -40,8 +40,8 @@ ALG_GFLOP = {"hnerv_l": 4429.9, "enerv_m": 443.3, "nerv_s": 19.33, "nerv_xs": 19
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=250)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="hnerv_l", help="preset name in bnerv_b200.config (default: the metric's workload)")
     ap.add_argument("--batch", type=int, default=1, help="frames per launch (reference scripts use -b 1)")
@@ -254,9 +254,19 @@ def run_b200(opt):
         launches = (_capi.launch_count() - n1) // K * K     # kernels of this library per K steps (same count replayed by the graph)
         timing, ops.TIMING = ops.TIMING, None
         eng.use_graph = True
-        conv_ms = sum(a.elapsed_time(b) for _, a, b, _ in timing)
-        conv_flops = sum(f for f, _, _, _ in timing)
-        top = max(timing, key=lambda r: r[1].elapsed_time(r[2])) if timing else None
+        # per launch shape: median over the K steps (a host hiccup between the two event records of one eager
+        # launch would otherwise show up as a multi-ms "launch"); a step's conv time = sum of the shape medians
+        by_shape = {}
+        for f, a, b, shp in timing:
+            by_shape.setdefault(shp, []).append((a.elapsed_time(b), f))
+        per_step = K if K > 0 else 1
+        shapes = []
+        for shp, rows in by_shape.items():
+            med = statistics.median(r[0] for r in rows)
+            shapes.append({"shape": shp, "ms": med, "flops": rows[0][1], "per_step": len(rows) / per_step})
+        conv_ms = sum(r["ms"] * r["per_step"] for r in shapes) * K
+        conv_flops = sum(r["flops"] * r["per_step"] for r in shapes) * K
+        top = max(shapes, key=lambda r: r["ms"] * r["per_step"]) if shapes else None
 
         # ---------------- end to end through the reference-facing API ----------------
         out_host = torch.empty((B, 3, img.shape[-2], img.shape[-1]), dtype=torch.float32).pin_memory()
@@ -328,8 +338,9 @@ def run_b200(opt):
                      "conv_ms_per_step": conv_ms / K,
                      "kernel_timing": "separate eager pass of the same K steps, CUDA events around each launch; the timed region replays a CUDA graph",
                      "traffic": traffic, "traffic_note": traffic_note, "algorithmic_bytes": alg_bytes,
-                     "top_launch": None if top is None else {"shape(cin,cout,k,s,H,W,act)": list(top[3]), "ms": top[1].elapsed_time(top[2]),
-                                                              "tflops": top[0] / top[1].elapsed_time(top[2]) / 1e9}},
+                     "top_launch": None if top is None else {"shape(cin,cout,k,s,H,W,act)": list(top["shape"]), "ms": top["ms"],
+                                                              "launches_per_step": top["per_step"],
+                                                              "tflops": top["flops"] / top["ms"] / 1e9}},
     }
     if world == 1 and not opt.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)

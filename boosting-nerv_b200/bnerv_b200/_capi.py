@@ -16,6 +16,10 @@ EXPORTS = [
     "bnerv_abi_version", "bnerv_last_error", "bnerv_launch_count", "bnerv_pack_conv_weight", "bnerv_conv_fused",
     "bnerv_conv_fused_f32", "bnerv_sft_affine", "bnerv_linear_act", "bnerv_nchw_to_c8", "bnerv_c8_to_nchw",
     "bnerv_pixel_shuffle", "bnerv_c8_numel", "bnerv_packed_weight_numel", "bnerv_packed_bias_numel",
+    # backward of the cascade (ABI version 2)
+    "bnerv_conv_fused_ex", "bnerv_head_bwd", "bnerv_pack_conv_weight_dgrad", "bnerv_conv_wgrad", "bnerv_wgrad_acc_numel",
+    "bnerv_wgrad_finalize", "bnerv_bias_finalize", "bnerv_channel_sum", "bnerv_resblock_mid_bwd", "bnerv_block_front_bwd",
+    "bnerv_unshuffle_c8",
 ]
 
 
@@ -44,6 +48,18 @@ def _load():
     lib.bnerv_launch_count.restype = ctypes.c_uint64
     lib.bnerv_pack_conv_weight.argtypes = [vp, vp, i, i, i, i, vp, vp, vp]
     lib.bnerv_conv_fused.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
+    lib.bnerv_conv_fused_ex.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.bnerv_head_bwd.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp]
+    lib.bnerv_pack_conv_weight_dgrad.argtypes = [vp, i, i, i, i, vp, vp]
+    lib.bnerv_conv_wgrad.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp]
+    lib.bnerv_wgrad_acc_numel.argtypes = [i, i, i]
+    lib.bnerv_wgrad_acc_numel.restype = ctypes.c_size_t
+    lib.bnerv_wgrad_finalize.argtypes = [vp, i, i, i, i, vp, i, vp, vp]
+    lib.bnerv_bias_finalize.argtypes = [vp, i, i, vp, i, vp, vp]
+    lib.bnerv_channel_sum.argtypes = [vp, i, i, i, i, i, vp, vp]
+    lib.bnerv_resblock_mid_bwd.argtypes = [vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
+    lib.bnerv_block_front_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
+    lib.bnerv_unshuffle_c8.argtypes = [vp, i, i, i, i, i, vp, vp]
     lib.bnerv_conv_fused_f32.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp, i, vp, vp, vp]
     lib.bnerv_sft_affine.argtypes = [vp, i, vp, i, i, vp]
     lib.bnerv_linear_act.argtypes = [vp, i, i, vp, vp, i, i, vp, vp]

@@ -92,17 +92,23 @@ def conv_flops(B, cin, cout, k, s, H, W):
 
 
 def conv_fused(x_c8, pc, cin, H, W, act="none", resid=None, g1p=None, beta=None, out_pre=None, out_aff=None,
-               out_nchw=None):
-    """Launch the tcgen05 fused conv.  Output tensors are caller-provided (see bnerv_conv_fused)."""
+               out_nchw=None, out_deriv=None):
+    """Launch the tcgen05 fused conv.  Output tensors are caller-provided (see bnerv_conv_fused[_ex])."""
     _need_cuda(x_c8)
     B = x_c8.shape[0]
     assert cin == pc.cin
     if TIMING is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check("bnerv_conv_fused",
-          lib.bnerv_conv_fused(ptr(x_c8), B, cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, pc.k, pc.s, ACT_CODES[act],
-                               ptr(resid), ptr(g1p), ptr(beta), ptr(out_pre), ptr(out_aff), ptr(out_nchw), _stream()))
+    if out_deriv is None:
+        check("bnerv_conv_fused",
+              lib.bnerv_conv_fused(ptr(x_c8), B, cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, pc.k, pc.s, ACT_CODES[act],
+                                   ptr(resid), ptr(g1p), ptr(beta), ptr(out_pre), ptr(out_aff), ptr(out_nchw), _stream()))
+    else:
+        check("bnerv_conv_fused_ex",
+              lib.bnerv_conv_fused_ex(ptr(x_c8), B, cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, pc.k, pc.s, ACT_CODES[act],
+                                      ptr(resid), ptr(g1p), ptr(beta), ptr(out_pre), ptr(out_aff), ptr(out_nchw),
+                                      ptr(out_deriv), _stream()))
     if TIMING is not None:
         e1.record()
         TIMING.append((conv_flops(B, cin, pc.cout, pc.k, pc.s, H, W), e0, e1, (cin, pc.cout, pc.k, pc.s, H, W, act)))
@@ -171,3 +177,112 @@ class SftTable:
         e = e.contiguous()
         assert e.shape == (self.B, self.ch_t)
         check("bnerv_sft_affine", lib.bnerv_sft_affine(ptr(self.desc), len(self.C), ptr(e), self.B, self.ch_t, _stream()))
+
+
+# ------------------------------------------------------------------------------------------------
+# backward of the cascade (include/bnerv_b200.h, "Backward of the cascade")
+# ------------------------------------------------------------------------------------------------
+class PackedDgrad:
+    """Packed weights of the conv that computes dL/dx from the un-shuffled dL/dy: a conv with Cin' = s*s*Cout_p,
+    Cout' = Cin, the same k, no shuffle, zero bias (weights transposed and tap-flipped)."""
+
+    def __init__(self, weight, s=1):
+        _need_cuda(weight)
+        co_s2, cin_fwd, k, _ = weight.shape
+        self.k, self.s = k, 1
+        self.s_fwd = s
+        self.cout_fwd = co_s2 // (s * s)
+        self.cin = s * s * round_up(self.cout_fwd, 16)      # K of the dgrad conv (already padded)
+        self.cout = cin_fwd                                 # N of the dgrad conv
+        dev = weight.device
+        self.w = torch.empty(lib.bnerv_packed_weight_numel(self.cout, self.cin, k, 1), dtype=torch.float16, device=dev)
+        self.b = torch.zeros(lib.bnerv_packed_bias_numel(self.cout, 1), dtype=torch.float32, device=dev)
+        self.repack(weight)
+
+    def repack(self, weight):
+        w = weight.detach().contiguous().float()
+        check("bnerv_pack_conv_weight_dgrad",
+              lib.bnerv_pack_conv_weight_dgrad(ptr(w), self.cout_fwd, self.cout, self.k, self.s_fwd, ptr(self.w), _stream()))
+
+
+def head_bwd(dimg, img, scale):
+    """dz (C8 f16) = S * dimg * d(tanh01)/dz; fills scale = [S, 1/S] (2-float CUDA tensor) on the device."""
+    _need_cuda(dimg, img, scale)
+    dimg, img = dimg.contiguous().float(), img.contiguous().float()
+    B, C, H, W = img.shape
+    dz = torch.empty(c8_shape(B, C, H, W), dtype=torch.float16, device=img.device)
+    scratch = torch.empty(1, dtype=torch.float32, device=img.device)
+    check("bnerv_head_bwd", lib.bnerv_head_bwd(ptr(dimg), ptr(img), B, C, H, W, ptr(scratch), ptr(scale), ptr(dz), _stream()))
+    return dz
+
+
+def conv_wgrad(x_c8, dy_c8, cin, k):
+    """acc [k*k][M_p][Cin_p] f32 = sum_pixels dy (x) shifted x (scaled by the loss scale)."""
+    _need_cuda(x_c8, dy_c8)
+    B, _, H, W, _ = x_c8.shape
+    m_p = dy_c8.shape[1] * 8
+    assert dy_c8.shape[0] == B and dy_c8.shape[2] == H and dy_c8.shape[3] == W
+    acc = torch.zeros(lib.bnerv_wgrad_acc_numel(m_p, cin, k), dtype=torch.float32, device=x_c8.device)
+    check("bnerv_conv_wgrad", lib.bnerv_conv_wgrad(ptr(x_c8), ptr(dy_c8), B, cin, H, W, m_p, k, ptr(acc), _stream()))
+    return acc
+
+
+def wgrad_finalize(acc, cout, cin, k, s, inv_scale, grad=None):
+    """-> grad OIHW f32 [cout*s*s, cin, k, k] (new tensor, or accumulated into `grad`)."""
+    accumulate = grad is not None
+    if grad is None:
+        grad = torch.empty((cout * s * s, cin, k, k), dtype=torch.float32, device=acc.device)
+    assert grad.is_contiguous() and grad.dtype == torch.float32
+    check("bnerv_wgrad_finalize", lib.bnerv_wgrad_finalize(ptr(acc), cout, cin, k, s, ptr(inv_scale), int(accumulate), ptr(grad), _stream()))
+    return grad
+
+
+def bias_finalize(acc, cout, s, inv_scale):
+    grad = torch.empty(cout * s * s, dtype=torch.float32, device=acc.device)
+    check("bnerv_bias_finalize", lib.bnerv_bias_finalize(ptr(acc), cout, s, ptr(inv_scale), 0, ptr(grad), _stream()))
+    return grad
+
+
+def channel_sum(x_c8, per_b=False):
+    _need_cuda(x_c8)
+    B, G, H, W, _ = x_c8.shape
+    out = torch.zeros((B, G * 8) if per_b else (G * 8,), dtype=torch.float32, device=x_c8.device)
+    check("bnerv_channel_sum", lib.bnerv_channel_sum(ptr(x_c8), B, G * 8, H, W, int(per_b), ptr(out), _stream()))
+    return out
+
+
+def resblock_mid_bwd(dw, v, dact, g1p, C):
+    """-> (dc0 C8, dG [B,Cp], dB [B,Cp], dbias0 [Cp]) all reductions scaled by the loss scale."""
+    B, G, H, W, _ = dw.shape
+    dev = dw.device
+    dc0 = torch.empty_like(dw)
+    dG = torch.zeros((B, G * 8), dtype=torch.float32, device=dev)
+    dB = torch.zeros((B, G * 8), dtype=torch.float32, device=dev)
+    db = torch.zeros(G * 8, dtype=torch.float32, device=dev)
+    check("bnerv_resblock_mid_bwd", lib.bnerv_resblock_mid_bwd(ptr(dw), ptr(v), ptr(dact), ptr(g1p), B, C, H, W, ptr(dc0),
+                                                               ptr(dG), ptr(dB), ptr(db), _stream()))
+    return dc0, dG, dB, db
+
+
+def block_front_bwd(du, dout, x0, dact, g0p, C):
+    """-> (dy C8 at the block's output resolution, dG, dB, dbias1)."""
+    B, G, H, W, _ = du.shape
+    dev = du.device
+    dy = torch.empty_like(du)
+    dG = torch.zeros((B, G * 8), dtype=torch.float32, device=dev)
+    dB = torch.zeros((B, G * 8), dtype=torch.float32, device=dev)
+    db = torch.zeros(G * 8, dtype=torch.float32, device=dev)
+    check("bnerv_block_front_bwd", lib.bnerv_block_front_bwd(ptr(du), ptr(dout), ptr(x0), ptr(dact), ptr(g0p), B, C, H, W,
+                                                             ptr(dy), ptr(dG), ptr(dB), ptr(db), _stream()))
+    return dy, dG, dB, db
+
+
+def unshuffle_c8(src, C, s):
+    """PixelShuffle(s) transposed: [B][Cp/8][H*s][W*s][8] -> [B][s*s*Cp/8][H][W][8]."""
+    if s == 1:
+        return src
+    B, G, Hs, Ws, _ = src.shape
+    H, W = Hs // s, Ws // s
+    dst = torch.empty((B, s * s * G, H, W, 8), dtype=torch.float16, device=src.device)
+    check("bnerv_unshuffle_c8", lib.bnerv_unshuffle_c8(ptr(src), B, C, H, W, s, ptr(dst), _stream()))
+    return dst

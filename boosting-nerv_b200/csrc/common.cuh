@@ -152,6 +152,52 @@ __device__ __forceinline__ float2 gelu2(float2 x) {
 
 __device__ __forceinline__ float2 tanh01_2(float2 x) { return make_float2(tanh01(x.x), tanh01(x.y)); }
 
+// Activation AND its derivative at the pre-activation (training forward: the derivative map is what the backward
+// pass multiplies by, so neither the pre-activation nor a second transcendental pass is needed later).
+__device__ __forceinline__ float mufu_cos(float x) { float r; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+__device__ __forceinline__ float2 sin2_d(float2 x, float2& d) {           // d = cos(x)
+    const float magic = 12582912.0f;
+    float2 t = fma2(x, f2(0.15915494309189535f), f2(magic));
+    float2 k = add2(t, f2(-magic));
+    float2 r = fma2(k, f2(-6.2831854820251465f), x);
+    r = fma2(k, f2(1.7484555314695172e-07f), r);
+    d = make_float2(mufu_cos(r.x), mufu_cos(r.y));
+    return make_float2(mufu_sin(r.x), mufu_sin(r.y));
+}
+
+__device__ __forceinline__ float2 gelu2_d(float2 x, float2& d) {          // d = Phi(x) + x * phi(x)
+    float2 z  = mul2(x, f2(0.70710678118654752f));
+    float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+    float2 dd = fma2(az, f2(0.3275911f), f2(1.0f));
+    float2 t  = make_float2(mufu_rcp(dd.x), mufu_rcp(dd.y));
+    float2 pn = fma2(t, f2(-1.061405429f), f2(1.453152027f));
+    pn = fma2(pn, t, f2(-1.421413741f));
+    pn = fma2(pn, t, f2(0.284496736f));
+    pn = fma2(pn, t, f2(-0.254829592f));
+    pn = mul2(pn, t);
+    float2 q = mul2(mul2(z, z), f2(-1.4426950408889634f));
+    float2 e = make_float2(mufu_ex2(q.x), mufu_ex2(q.y));                 // exp(-x^2/2)
+    float2 r = fma2(pn, e, f2(1.0f));
+    r = make_float2(copysignf(r.x, z.x), copysignf(r.y, z.y));            // erf(x/sqrt2)
+    float2 h = mul2(x, f2(0.5f));
+    float2 cdf = fma2(r, f2(0.5f), f2(0.5f));
+    d = fma2(mul2(x, e), f2(0.3989422804014327f), cdf);
+    return fma2(h, r, h);
+}
+
+// act: BNERV_ACT_* (run-time); returns act(x), d = act'(x)
+__device__ __forceinline__ float2 act2_with_deriv(float2 x, int act, float2& d) {
+    switch (act) {
+        case BNERV_ACT_SIN:  return sin2_d(x, d);
+        case BNERV_ACT_GELU: return gelu2_d(x, d);
+        case BNERV_ACT_RELU: d = make_float2(x.x > 0.0f ? 1.0f : 0.0f, x.y > 0.0f ? 1.0f : 0.0f);
+                             return make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f));
+        case BNERV_ACT_TANH01: { float2 o = tanh01_2(x); d = make_float2(2.0f * o.x * (1.0f - o.x), 2.0f * o.y * (1.0f - o.y)); return o; }
+        default: d = f2(1.0f); return x;
+    }
+}
+
 template <int ACT>
 __device__ __forceinline__ float2 act2(float2 x) {
     if (ACT == BNERV_ACT_SIN) return sin2(x);

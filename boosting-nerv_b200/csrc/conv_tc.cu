@@ -87,7 +87,9 @@ struct ConvTcArgs {
     int n_pairs;            // CTA pairs in the grid
     int stages;
     int b_kstep_bytes;      // taps * 2 * n_half * 16 : one K step of the resident weight half
-    int b_bytes;            // ksteps * b_kstep_bytes
+    int b_bytes;            // ksteps * b_kstep_bytes (0 in streaming mode)
+    int b_stream;           // 1: weights do not stay resident; every pipeline stage carries its K step of B next to A
+    int stage_bytes;        // A stage (+ one K step of the weight half in streaming mode)
     const float* bias;      // [n_total]
     const float* g1p;       // [B][cout_p] or null
     const float* beta;      // [B][cout_p] or null
@@ -95,6 +97,7 @@ struct ConvTcArgs {
     __half* out_pre;        // C8 or null
     __half* out_aff;        // C8 or null
     float* out_nchw;        // NCHW f32 or null
+    __half* out_deriv;      // C8 or null: act'(pre-activation) (training forward)
 };
 
 struct TileCoord { int b, h0, w0; };
@@ -125,6 +128,7 @@ __device__ __forceinline__ WorkRange work_range(const ConvTcArgs& a, uint32_t pa
 // epilogue feature flags (compile-time in the specialised instantiations, run-time in the generic one)
 constexpr int F_RESID = 1, F_AFF = 2, F_PRE = 4, F_NCHW = 8, F_SHUF = 16;
 constexpr int F_WIDE = 32;   // s == 2 row packing: the two chunks of a group are 32 contiguous output bytes
+constexpr int F_DERIV = 64;  // also write act'(pre-activation) (training forward)
 
 template <int ACT>
 __device__ __forceinline__ float2 act2_rt(float2 x, int act) {
@@ -175,8 +179,14 @@ __device__ __forceinline__ void epilogue_group(const ConvTcArgs& a, int flags, c
             ee[p] = *reinterpret_cast<const float4*>(cb->beta + col + 4 * p);
         }
     }
+    float2 dv[8];
+    if (flags & F_DERIV) {
 #pragma unroll
-    for (int p = 0; p < 8; ++p) x[p] = act2_rt<ACT>(x[p], a.act);
+        for (int p = 0; p < 8; ++p) x[p] = act2_with_deriv(x[p], (ACT >= 0) ? ACT : a.act, dv[p]);
+    } else {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) x[p] = act2_rt<ACT>(x[p], a.act);
+    }
     if (flags & F_RESID) {
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -185,6 +195,15 @@ __device__ __forceinline__ void epilogue_group(const ConvTcArgs& a, int flags, c
         }
     }
     if (!valid) return;
+    if (flags & F_DERIV) {
+        const uint4 o0 = pack8(dv), o1 = pack8(dv + 4);
+        if (flags & F_WIDE) {
+            st_global_32B(a.out_deriv + ga.off[0], o0, o1);
+        } else {
+            *reinterpret_cast<uint4*>(a.out_deriv + ga.off[0]) = o0;
+            *reinterpret_cast<uint4*>(a.out_deriv + ga.off[1]) = o1;
+        }
+    }
     if (flags & F_PRE) {
         const uint4 o0 = pack8(x), o1 = pack8(x + 4);
         if (flags & F_WIDE) {
@@ -248,7 +267,9 @@ __device__ __forceinline__ void producer_role(const ConvTcArgs& a, const Pipe& p
     if (wr.begin >= wr.end) { pdl_wait(); pdl_launch_dependents(); }
     for (int it = wr.begin; it < wr.end; ++it) {
         const int nt = it / a.pair_tiles, pt = it - nt * a.pair_tiles;
-        if (it == wr.begin || pt == 0) {
+        if (a.b_stream) {
+            if (it == wr.begin) { pdl_wait(); pdl_launch_dependents(); }
+        } else if (it == wr.begin || pt == 0) {
             // the previous n-tile's MMAs (which read the resident weights of both CTAs) must have completed
             if (wc > 0) mbar_wait(p.wempty, (wc - 1) & 1);
             if (elect_one()) {
@@ -272,10 +293,13 @@ __device__ __forceinline__ void producer_role(const ConvTcArgs& a, const Pipe& p
             for (int kc = 0; kc < a.ksteps; ++kc) {
                 mbar_wait(p.empty + stage * 8, phase ^ 1);
                 if (elect_one()) {
-                    if (p.rank == 0) mbar_expect_tx(p.full + stage * 8, 2u * G::A_STAGE_B);
+                    if (p.rank == 0) mbar_expect_tx(p.full + stage * 8, 2u * a.stage_bytes);
                     // activations viewed as u64 elements: 2 per pixel-group -> x coordinate = 2*w
-                    tma_load_3d_pair(p.a_base + stage * G::A_STAGE_B, tmA, full_leader + stage * 8,
+                    tma_load_3d_pair(p.a_base + stage * a.stage_bytes, tmA, full_leader + stage * 8,
                                      2 * (t.w0 - 1), t.h0 - 1, t.b * a.cin_groups + 2 * kc);
+                    if (a.b_stream)      // this K step of this CTA's half of the n-tile's weights rides in the same stage
+                        tma_load_3d_pair(p.a_base + stage * a.stage_bytes + G::A_STAGE_B, tmB, full_leader + stage * 8,
+                                         2 * (nt * a.n_acc + static_cast<int>(p.rank) * a.n_half), 2 * kc, 0);
                 }
                 __syncwarp();
                 if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -305,7 +329,7 @@ __device__ __forceinline__ void mma_role(const ConvTcArgs& a, const Pipe& p) {
     int wc = 0;                                   // weight sets consumed so far
     for (int it = wr.begin; it < wr.end; ++it) {
         const int pt = it % a.pair_tiles;
-        if (it == wr.begin || pt == 0) {
+        if (!a.b_stream && (it == wr.begin || pt == 0)) {
             if (wc > 0) {                         // every MMA that reads the old weights has been issued: release them
                 if (elect_one()) umma_commit_pair(p.wempty);
                 __syncwarp();
@@ -322,8 +346,8 @@ __device__ __forceinline__ void mma_role(const ConvTcArgs& a, const Pipe& p) {
                 mbar_wait(p.full + stage * 8, phase);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t sa16 = ab16 + stage * (G::A_STAGE_B >> 4);
-                    const uint32_t sb16 = wb16 + kc * b_ks16;
+                    const uint32_t sa16 = ab16 + stage * (static_cast<uint32_t>(a.stage_bytes) >> 4);
+                    const uint32_t sb16 = a.b_stream ? sa16 + (G::A_STAGE_B >> 4) : wb16 + kc * b_ks16;
 #pragma unroll
                     for (int tp = 0; tp < TAPS; ++tp) {
                         const int tap = (TAPS == 1) ? 4 : tp;   // 1x1 conv: the single tap reads the halo tile's centre
@@ -357,7 +381,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int flags = (FLAGS >= 0) ? FLAGS : a.flags;
 
     uint8_t* a_ring       = smem + a.b_bytes;
-    uint8_t* bar_base     = a_ring + static_cast<size_t>(a.stages) * G::A_STAGE_B;
+    uint8_t* bar_base     = a_ring + static_cast<size_t>(a.stages) * a.stage_bytes;
     uint64_t* full_bar    = reinterpret_cast<uint64_t*>(bar_base);
     uint64_t* empty_bar   = full_bar + MAX_STAGES;
     uint64_t* tfull_bar   = empty_bar + MAX_STAGES;   // [2]
@@ -573,6 +597,8 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
+PFN_encodeTiled get_encode_tiled() { return get_encode(); }     // shared with conv_wgrad.cu
+
 static int make_map_u64_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                            uint64_t stride1_b, uint64_t stride2_b, uint32_t b0, uint32_t b1, uint32_t b2) {
     PFN_encodeTiled enc = get_encode();
@@ -612,6 +638,24 @@ int choose_n_acc(int n_total, int ksteps, int taps) {
     return best;
 }
 
+// Streaming mode (weights too wide to stay resident next to a useful n-tile, e.g. the dgrad of a PixelShuffle
+// up-conv whose K is s*s*Cout): every stage carries A plus one K step of the weight half; at least 4 stages.
+int choose_n_acc_stream(int n_total, int taps) {
+    int best = 0;
+    double best_cost = 0.0;
+    for (int n = 16; n <= 256; n += 16) {
+        const int mt = n <= 128 ? 2 : 1;
+        const long long stage = a_stage_bytes(mt) + 1LL * taps * 2 * (n / 2) * 16;
+        if (4 * stage + fixed_smem_bytes() > SMEM_LIMIT) break;
+        const int tiles = (n_total + n - 1) / n;
+        const double bw = 8192.0 * (1.0 / n + 1.0 / 256.0) / 110.0;
+        const double cost = static_cast<double>(tiles) * n * (bw > 1.0 ? bw : 1.0);
+        if (best == 0 || cost <= best_cost) { best = n; best_cost = cost; }
+        if (n >= n_total) break;
+    }
+    return best;
+}
+
 template <int MT>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& a, int act, size_t smem_bytes,
                        cudaStream_t stream) {
@@ -629,8 +673,14 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
     BNERV_PICK(4, BNERV_ACT_NONE, F_RESID | F_PRE)              // conv1 + residual
     BNERV_PICK(5, BNERV_ACT_NONE, F_PRE | F_SHUF)               // E-NeRV stage-0 up-conv
     BNERV_PICK(6, BNERV_ACT_TANH01, F_NCHW)                     // head conv -> image
+    // training forward: the same launches also write act'(pre-activation)
+    BNERV_PICK(8,  BNERV_ACT_SIN, F_AFF | F_PRE | F_DERIV)
+    BNERV_PICK(9,  BNERV_ACT_SIN, F_AFF | F_PRE | F_SHUF | F_DERIV)
+    BNERV_PICK(10, BNERV_ACT_SIN, F_AFF | F_PRE | F_SHUF | F_WIDE | F_DERIV)
+    BNERV_PICK(11, BNERV_ACT_GELU, F_AFF | F_PRE | F_DERIV)
+    BNERV_PICK(12, BNERV_ACT_NONE, F_PRE)                       // dgrad
 #undef BNERV_PICK
-    static bool smem_set[8] = {false, false, false, false, false, false, false, false};
+    static bool smem_set[16] = {};
     if (!smem_set[slot]) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return set_error(static_cast<int>(e), "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
@@ -667,18 +717,28 @@ extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, con
                                 const float* bias_packed, int Cout, int k, int s, int act, const void* resid,
                                 const float* g1p, const float* beta, void* out_pre, void* out_aff, float* out_nchw,
                                 void* stream) {
+    return bnerv_conv_fused_ex(x, B, Cin, H, W, w_packed, bias_packed, Cout, k, s, act, resid, g1p, beta, out_pre, out_aff,
+                               out_nchw, nullptr, stream);
+}
+
+extern "C" int bnerv_conv_fused_ex(const void* x, int B, int Cin, int H, int W, const void* w_packed,
+                                   const float* bias_packed, int Cout, int k, int s, int act, const void* resid,
+                                   const float* g1p, const float* beta, void* out_pre, void* out_aff, float* out_nchw,
+                                   void* out_deriv, void* stream) {
     if (!x || !w_packed || !bias_packed) return set_error(BNERV_E_BADARG, "conv_fused: null operand");
     if (B <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || s <= 0) return set_error(BNERV_E_BADARG, "conv_fused: non-positive size");
     if (k != 1 && k != 3) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: kernel size %d (only 1 and 3)", k);
     if ((g1p == nullptr) != (beta == nullptr)) return set_error(BNERV_E_BADARG, "conv_fused: g1p and beta must both be given");
     if ((g1p != nullptr) != (out_aff != nullptr)) return set_error(BNERV_E_BADARG, "conv_fused: out_aff requires g1p/beta and vice versa");
     if (!out_pre && !out_aff && !out_nchw) return set_error(BNERV_E_BADARG, "conv_fused: no output");
+    if (out_deriv && resid) return set_error(BNERV_E_BADARG, "conv_fused: out_deriv is the derivative of the activation; not defined with a residual");
     if (act < BNERV_ACT_NONE || act > BNERV_ACT_TANH01) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: act %d", act);
     if (s > 0xffff) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: PixelShuffle factor %d", s);
     const uintptr_t align_or = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) |
                                reinterpret_cast<uintptr_t>(bias_packed) | reinterpret_cast<uintptr_t>(resid) |
                                reinterpret_cast<uintptr_t>(g1p) | reinterpret_cast<uintptr_t>(beta) |
-                               reinterpret_cast<uintptr_t>(out_pre) | reinterpret_cast<uintptr_t>(out_aff);
+                               reinterpret_cast<uintptr_t>(out_pre) | reinterpret_cast<uintptr_t>(out_aff) |
+                               reinterpret_cast<uintptr_t>(out_deriv);
     if (align_or & 15) return set_error(BNERV_E_BADARG, "conv_fused: pointers must be 16-byte aligned");
 
     const int cin_p = round_up(Cin, 16), cout_p = round_up(Cout, 16);
@@ -689,8 +749,10 @@ extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, con
     a.taps       = k * k;
     a.n_total    = s * s * cout_p;
     a.n_acc      = choose_n_acc(a.n_total, a.ksteps, a.taps);
-    if (a.n_acc == 0)
-        return set_error(BNERV_E_UNSUPPORTED, "conv_fused: Cin = %d too wide for shared-memory-resident weights (k = %d)", Cin, k);
+    static const bool force_stream = getenv("BNERV_FORCE_STREAM") != nullptr;      // testing switch
+    a.b_stream   = (force_stream || a.n_acc == 0 || (a.n_acc < 64 && a.n_acc < a.n_total)) ? 1 : 0;
+    if (a.b_stream) a.n_acc = choose_n_acc_stream(a.n_total, a.taps);
+    if (a.n_acc == 0) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: no tile configuration fits (Cin = %d, k = %d)", Cin, k);
     a.n_half     = a.n_acc / 2;
     a.n_tiles    = (a.n_total + a.n_acc - 1) / a.n_acc;
     a.cout = Cout; a.cout_p = cout_p; a.s = s; a.act = act;
@@ -705,8 +767,9 @@ extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, con
     if (pair_tiles * a.n_tiles > 0x3fffffffLL) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: too many tiles");
     a.work_total    = a.pair_tiles * a.n_tiles;
     a.b_kstep_bytes = a.taps * 2 * a.n_half * 16;
-    a.b_bytes       = a.ksteps * a.b_kstep_bytes;
-    const int a_stage = a_stage_bytes(mt);
+    a.b_bytes       = a.b_stream ? 0 : a.ksteps * a.b_kstep_bytes;
+    const int a_stage = a_stage_bytes(mt) + (a.b_stream ? a.b_kstep_bytes : 0);
+    a.stage_bytes   = a_stage;
     int stages = (SMEM_LIMIT - fixed_smem_bytes() - a.b_bytes) / a_stage;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < MIN_STAGES) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: %d activation stages do not fit", MIN_STAGES);
@@ -716,7 +779,8 @@ extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, con
     a.out_pre = static_cast<__half*>(out_pre);
     a.out_aff = static_cast<__half*>(out_aff);
     a.out_nchw = out_nchw;
-    a.flags = (resid ? F_RESID : 0) | (g1p ? F_AFF : 0) | (out_pre ? F_PRE : 0) | (out_nchw ? F_NCHW : 0) | (s > 1 ? F_SHUF : 0) | (s == 2 ? F_WIDE : 0);
+    a.out_deriv = static_cast<__half*>(out_deriv);
+    a.flags = (out_deriv ? F_DERIV : 0) | (resid ? F_RESID : 0) | (g1p ? F_AFF : 0) | (out_pre ? F_PRE : 0) | (out_nchw ? F_NCHW : 0) | (s > 1 ? F_SHUF : 0) | (s == 2 ? F_WIDE : 0);
 
     if (g_num_sms == 0) {
         int dev = 0;

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define BNERV_ABI_VERSION 1
+#define BNERV_ABI_VERSION 2
 
 /* error codes (negative) */
 #define BNERV_E_BADARG      (-1)   /* null pointer / non-positive size / misaligned pointer          */
@@ -89,6 +89,15 @@ int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W,
                      int act, const void* resid, const float* g1p, const float* beta,
                      void* out_pre, void* out_aff, float* out_nchw, void* stream);
 
+/* bnerv_conv_fused plus one more optional output for the TRAINING forward:
+ *   out_deriv : C8 f16 at the output resolution, receives act'(y) evaluated at the pre-activation (cos(y) for
+ *               SIN, Phi(y) + y*phi(y) for GELU, 1 for NONE) - the map the backward pass multiplies by, so neither the
+ *               pre-activation nor a second transcendental pass is needed later.  Must be NULL when resid is given. */
+int bnerv_conv_fused_ex(const void* x, int B, int Cin, int H, int W,
+                        const void* w_packed, const float* bias_packed, int Cout, int k, int s,
+                        int act, const void* resid, const float* g1p, const float* beta,
+                        void* out_pre, void* out_aff, float* out_nchw, void* out_deriv, void* stream);
+
 /* Same contract and operand layouts as bnerv_conv_fused, computed by an f32 CUDA-core kernel on the
  * reference's own layouts (NCHW f32 activations, OIHW f32 weights) — the exact-arithmetic path used
  * for tiny layers and as the on-device cross-check of the tensor-core kernel.
@@ -128,6 +137,62 @@ int bnerv_c8_to_nchw(const void* x_c8, int B, int C, int H, int W, float* y, voi
 /* nn.PixelShuffle(s) on NCHW f32 (model_blocks.py:204,217): a pure index permutation, bit-exact.
  *   x: [B][C*s*s][H][W] -> y: [B][C][H*s][W*s] */
 int bnerv_pixel_shuffle(const float* x, int B, int C, int H, int W, int s, float* y, void* stream);
+
+/* ================================================================================================
+ * Backward of the cascade: what torch.autograd computes for the reference's
+ * loss.backward() (train_nerv_all.py:342-348) through CustomConv2d / PixelShuffle / Sin / GELU / SFTLayer /
+ * OutImg, as native kernels on the same C8 f16 maps.
+ *
+ * Gradient maps are C8 f16 multiplied by ONE power-of-two loss scale S per backward pass, chosen on the device
+ * by bnerv_head_bwd (scale[0] = S, scale[1] = 1/S, no host synchronisation); every f32 reduction below is
+ * S * (true gradient) and is un-scaled by the *_finalize calls / by the caller with scale[1].
+ * "Un-shuffled" gradient map of a PixelShuffle(s) up-conv: C8 f16 [B][s*s*Cout_p/8][H][W][8] whose channel
+ * m = (i*s + j)*Cout_p + c is reference conv channel c*s*s + i*s + j (s = 1: the plain C8 map).
+ * ================================================================================================ */
+
+/* OutImg 'tanh' transposed (model_blocks.py:61): dz = S * dimg * 2*img*(1 - img), written as a C8 f16 map.
+ *   dimg, img : NCHW f32 [B][C][H][W] (img = the forward output); amax_scratch : 1 float of device scratch;
+ *   scale : 2 floats (device), receives {S, 1/S}; dz_c8 : C8 f16 [B][Cp/8][H][W][8]. */
+int bnerv_head_bwd(const float* dimg, const float* img, int B, int C, int H, int W, float* amax_scratch,
+                   float* scale, void* dz_c8, void* stream);
+
+/* dgrad: dx = conv_fused(x = un-shuffled dy, w = this packing, Cin' = s*s*Cout_p, Cout' = Cin, same k, s' = 1,
+ * act NONE, zero bias).  Packs W[o][ci][r][q] (OIHW f32) transposed and tap-flipped into the layout
+ * bnerv_conv_fused reads; w_packed holds bnerv_packed_weight_numel(Cin, s*s*Cout_p, k, 1) halves. */
+int bnerv_pack_conv_weight_dgrad(const float* w_oihw, int Cout, int Cin, int k, int s, void* w_packed, void* stream);
+
+/* wgrad: acc[tap][m][c] += sum_{b,h,w} dy[b,m,h,w] * x[b,c,h+r-pad,w+q-pad]   (tcgen05, K = pixels)
+ *   x  : C8 f16 [B][Cin_p/8][H][W][8], the conv's forward input;  dy : un-shuffled C8 f16 gradient with M_p channels;
+ *   acc: f32 [k*k][M_p][Cin_p], caller-zeroed, accumulated with vector reductions (bnerv_wgrad_acc_numel floats). */
+int bnerv_conv_wgrad(const void* x, const void* dy, int B, int Cin, int H, int W, int M_p, int k, float* acc,
+                     void* stream);
+size_t bnerv_wgrad_acc_numel(int M_p, int Cin, int k);
+/* acc (M_p = s*s*Cout_p) -> reference layout: grad_oihw[Cout*s*s][Cin][k][k] (=|+=) acc * (*inv_scale). */
+int bnerv_wgrad_finalize(const float* acc, int Cout, int Cin, int k, int s, const float* inv_scale, int accumulate,
+                         float* grad_oihw, void* stream);
+/* un-shuffled channel sums [s*s*Cout_p] -> grad[Cout*s*s] (=|+=) acc * (*inv_scale) in the reference order. */
+int bnerv_bias_finalize(const float* acc, int Cout, int s, const float* inv_scale, int accumulate, float* grad,
+                        void* stream);
+
+/* out[(per_b ? b : 0)][c] += sum_{h,w(,b)} x[b,c,h,w] over a C8 f16 map with Cp (multiple of 8) channels. */
+int bnerv_channel_sum(const void* x_c8, int B, int Cp, int H, int W, int per_b, float* out, void* stream);
+
+/* ResBlock_SFT middle transposed (model_blocks.py:86-87; forward v = gelu(c0), w = v*g1p + beta1):
+ *   dc0 = dw * g1p * dact;  dG[b][c] += sum dw*v;  dB[b][c] += sum dw;  dbias0[c] += sum dc0
+ *   dw, v, dact (= gelu'(c0) from bnerv_conv_fused_ex), dc0 : C8 f16 [B][Cp/8][H][W][8]; g1p, dG, dB : f32 [B][Cp];
+ *   dbias0 : f32 [Cp].  The three reductions accumulate (caller zeroes). */
+int bnerv_resblock_mid_bwd(const void* dw, const void* v, const void* dact, const float* g1p, int B, int C, int H,
+                           int W, void* dc0, float* dG, float* dB, float* dbias0, void* stream);
+
+/* NeRVBlock front transposed (model_blocks.py:37,85,89; forward x0 = act(y), u = x0*g0p + beta0, out = x0 + conv1(..)):
+ *   dy = (dout + du*g0p) * dact;  dG[b][c] += sum du*x0;  dB[b][c] += sum du;  dbias1[c] += sum dout
+ *   (dout is also dL/d conv1-output, hence conv1's bias gradient).  dy is at the block's output resolution;
+ *   bnerv_unshuffle_c8 turns it into the up-conv's gradient map when s > 1. */
+int bnerv_block_front_bwd(const void* du, const void* dout, const void* x0, const void* dact, const float* g0p,
+                          int B, int C, int H, int W, void* dy, float* dG, float* dB, float* dbias1, void* stream);
+
+/* PixelShuffle(s) transposed on C8 maps: src [B][Cp/8][H*s][W*s][8] -> dst [B][s*s*Cp/8][H][W][8] (un-shuffled order). */
+int bnerv_unshuffle_c8(const void* src, int B, int C, int H, int W, int s, void* dst, void* stream);
 
 /* Sizes (in elements) of the buffers the caller must provide. */
 size_t bnerv_c8_numel(int B, int C, int H, int W);                 /* __half elements            */
