@@ -12,6 +12,10 @@ Dispatch (``model.backend``):
           through the C-ABI; CPU tensors or a missing extension raise — there is no CPU fallback.
           With autograd enabled (training, outside the accelerated scope) the torch forward is used.
   'torch' always the plain torch forward (debugging / CPU wiring tests).
+Training (autograd enabled, CUDA tensors), ``model.train_backend``:
+  'b200'  (default) the conv cascade runs forward AND backward on the sm_100a kernels (``train.cascade_train``:
+          f16 operands, f32 accumulation, loss-scaled f16 gradient maps); the stems and SFT MLPs stay in torch autograd.
+  'torch' autograd through the plain torch forward (fp32 / cuDNN), the reference's own arithmetic.
 ``model.keep_intermediates`` (default False): fill the returned list with every block output converted
 to NCHW f32 like the reference does; callers only read element 0 (train_nerv_all.py:488,495), which is
 always provided.
@@ -40,6 +44,7 @@ def _engine_for(model):
 class _BoostBase(nn.Module):
     """Bookkeeping shared by the three families (quantiser plumbing of model_nerv.py:62-96)."""
     backend = "b200"
+    train_backend = "b200"
     keep_intermediates = False
 
     def _quant_layers(self):
@@ -84,6 +89,18 @@ class _BoostBase(nn.Module):
             raise RuntimeError("bnerv_b200: the decode path runs only on a CUDA (sm_100a) device; got a CPU tensor. "
                                "Set model.backend = 'torch' explicitly for the plain-torch debugging path.")
         return True
+
+    def _use_native_train(self, ref_tensor):
+        """Autograd is on (the caller checked _use_engine first): native fwd+bwd for CUDA tensors unless opted out."""
+        if self.backend == "torch" or self.train_backend == "torch":
+            return False
+        if self.train_backend != "b200":
+            raise ValueError(f"unknown train_backend {self.train_backend!r}")
+        return ref_tensor.is_cuda and torch.is_grad_enabled()
+
+    def _cascade_train(self, x, cond):
+        from .train import cascade_train
+        return cascade_train(self.engine(), x, cond)
 
     @staticmethod
     def _finish(t0):
@@ -150,6 +167,9 @@ class NeRV_Boost(_BoostBase):
         pe = self.pe_t(input[:, None].float())
         x = self.stem(pe).view(pe.size(0), self.fc_dim, self.fc_h, self.fc_w)
         cond = self.stem_t(pe)
+        if self._use_native_train(input):
+            img, first = self._cascade_train(x, cond)
+            return img, [first], self._finish(t0)
         outs = []
         for layer in self.layers:
             x = layer((x, cond))
@@ -234,6 +254,9 @@ class ENeRV_Boost(_BoostBase):
             img, outs, t_manip = self.engine().decode((input,), self.keep_intermediates)
             return self._own(img), [self._own(t_manip)] + [self._own(o) for o in outs], self._finish(t0)
         emb, t_manip = self._stem(input)
+        if self._use_native_train(input):
+            img, first = self._cascade_train(emb, t_manip)
+            return img, [t_manip, first], self._finish(t0)
         x, outs = emb, [t_manip]
         for layer in self.layers:
             x = layer((x, t_manip))
@@ -303,6 +326,9 @@ class HNeRV_Boost(_BoostBase):
             return self._own(img), [img_embed] + [self._own(o) for o in outs], self._finish(t0)
         pe = self.pe_embed_t(norm_idx[:, None]).float()          # f64 PE -> f32, model_hnerv.py:267
         cond = self.stem_t(pe)
+        if self._use_native_train(img_embed):
+            img, first = self._cascade_train(img_embed, cond)
+            return img, [img_embed, first], self._finish(t0)
         x, outs = img_embed, [img_embed]
         for blk in self.decoder:
             x = blk((x, cond))
