@@ -79,8 +79,8 @@ int bnerv_pack_conv_weight(const float* w_oihw, const float* bias, int Cout, int
  *   out_aff  : C8 f16, receives u  (NULL when g1p is NULL)
  *   out_nchw : f32 [B][Cout][H*s][W*s], receives x0 (after act) in the reference layout, or NULL
  * Computation: f16 operands, f32 accumulation (tcgen05.mma.cta_group::2 kind::f16, accumulators in TMEM);
- * each CTA pair keeps its weight tile resident in shared memory, so Cin is limited to what fits there
- * (k = 3: Cin <= ~1300; wider returns BNERV_E_UNSUPPORTED).  The launch uses programmatic dependent launch:
+ * each CTA pair keeps its weight tile resident in shared memory; when Cin is too wide for a useful tile to stay
+ * resident the weights stream through the stage ring with the activations instead.  The launch uses programmatic dependent launch:
  * w_packed / bias_packed must not be written by the kernel enqueued immediately before this call unless
  * that kernel is one of this library's (none of which trigger early completion while writing them).
  * ---------------------------------------------------------------------------------------------- */
