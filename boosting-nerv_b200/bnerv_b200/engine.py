@@ -43,10 +43,11 @@ class _ConvSlot:
         self.cin, self.cout = module.in_channels, module.out_channels // (s * s)
         self.key, self.pc = None, None
 
-    def packed(self):
+    def packed(self, force=False):
+        """force: re-pack unconditionally (inside a captured training graph the pack kernels ARE the per-step ingest)."""
         w, b = effective_weight(self.m)
         key = (_tensor_key(w), _tensor_key(b))
-        if key != self.key:
+        if key != self.key or force:
             if self.pc is None:
                 self.pc = ops.PackedConv(w, b, self.s)
             else:

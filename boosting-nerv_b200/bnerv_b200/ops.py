@@ -227,18 +227,19 @@ def conv_wgrad(x_c8, dy_c8, cin, k):
     return acc
 
 
-def wgrad_finalize(acc, cout, cin, k, s, inv_scale, grad=None):
-    """-> grad OIHW f32 [cout*s*s, cin, k, k] (new tensor, or accumulated into `grad`)."""
+def wgrad_finalize(acc, cout, cin, k, s, inv_scale, grad=None, out=None):
+    """-> grad OIHW f32 [cout*s*s, cin, k, k]: a new tensor, written into `out`, or accumulated into `grad`."""
     accumulate = grad is not None
     if grad is None:
-        grad = torch.empty((cout * s * s, cin, k, k), dtype=torch.float32, device=acc.device)
-    assert grad.is_contiguous() and grad.dtype == torch.float32
+        grad = out if out is not None else torch.empty((cout * s * s, cin, k, k), dtype=torch.float32, device=acc.device)
+    assert grad.is_contiguous() and grad.dtype == torch.float32 and grad.numel() == cout * s * s * cin * k * k
     check("bnerv_wgrad_finalize", lib.bnerv_wgrad_finalize(ptr(acc), cout, cin, k, s, ptr(inv_scale), int(accumulate), ptr(grad), _stream()))
     return grad
 
 
-def bias_finalize(acc, cout, s, inv_scale):
-    grad = torch.empty(cout * s * s, dtype=torch.float32, device=acc.device)
+def bias_finalize(acc, cout, s, inv_scale, out=None):
+    grad = out if out is not None else torch.empty(cout * s * s, dtype=torch.float32, device=acc.device)
+    assert grad.is_contiguous() and grad.dtype == torch.float32 and grad.numel() == cout * s * s
     check("bnerv_bias_finalize", lib.bnerv_bias_finalize(ptr(acc), cout, s, ptr(inv_scale), 0, ptr(grad), _stream()))
     return grad
 

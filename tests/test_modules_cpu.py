@@ -90,3 +90,31 @@ def test_out_of_scope_baselines_are_importable_but_refuse():
         model_blocks.ActivationLayer("nope")           # model_blocks.py:156
     with pytest.raises(NotImplementedError):
         model_blocks.NormLayer("ln", 4)                # model_blocks.py:169
+
+
+def test_batched_sft_tables_equal_per_layer_affine():
+    """train._Layout.sft_tables (all TAT MLPs of the cascade in a few batched ops) == SFTLayer.affine per layer
+    (model_blocks.py:101-104), and autograd reaches every SFT parameter through it."""
+    from bnerv_b200 import ENeRV_Boost, HNeRV_Boost, tiny_args
+    from bnerv_b200.engine import DecoderEngine
+    from bnerv_b200.train import _Layout
+    for cls, fam in ((HNeRV_Boost, "HNeRV_Boost"), (ENeRV_Boost, "ENeRV_Boost")):
+        torch.manual_seed(0)
+        a = tiny_args(fam)
+        m = cls(a) if fam == "HNeRV_Boost" else cls(3, a)
+        eng = DecoderEngine(m)
+        lay = _Layout(eng, 3)
+        cond = torch.randn(3, a.ch_t, 1, 1)
+        sc, sh = lay.sft_tables(cond)
+        i = 0
+        for blk in eng.blocks:
+            for layer in blk.sfts:
+                s_ref, h_ref = layer.affine(cond)
+                off, c = lay.sft_cols[i]
+                assert torch.allclose(sc[:, off:off + c], s_ref.flatten(1), atol=1e-6)
+                assert torch.allclose(sh[:, off:off + c], h_ref.flatten(1), atol=1e-6)
+                i += 1
+        (sc.sum() + sh.sum()).backward()
+        for blk in eng.blocks:
+            for layer in blk.sfts:
+                assert all(p.grad is not None for p in layer.parameters())
