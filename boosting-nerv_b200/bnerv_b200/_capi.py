@@ -19,7 +19,7 @@ EXPORTS = [
     # backward of the cascade (ABI version 2)
     "bnerv_conv_fused_ex", "bnerv_head_bwd", "bnerv_pack_conv_weight_dgrad", "bnerv_conv_wgrad", "bnerv_wgrad_acc_numel",
     "bnerv_wgrad_finalize", "bnerv_bias_finalize", "bnerv_channel_sum", "bnerv_resblock_mid_bwd", "bnerv_block_front_bwd",
-    "bnerv_unshuffle_c8",
+    "bnerv_unshuffle_c8", "bnerv_pack_conv_weight_q", "bnerv_frame_metrics", "bnerv_frame_metrics_scratch_doubles",
 ]
 
 
@@ -48,6 +48,10 @@ def _load():
     lib.bnerv_launch_count.restype = ctypes.c_uint64
     lib.bnerv_pack_conv_weight.argtypes = [vp, vp, i, i, i, i, vp, vp, vp]
     lib.bnerv_conv_fused.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
+    lib.bnerv_pack_conv_weight_q.argtypes = [vp, vp, i, vp, vp, i, i, i, i, i, i, vp, vp, vp]
+    lib.bnerv_frame_metrics.argtypes = [vp, vp, i, ctypes.c_size_t, vp, vp, vp]
+    lib.bnerv_frame_metrics_scratch_doubles.argtypes = [i]
+    lib.bnerv_frame_metrics_scratch_doubles.restype = ctypes.c_size_t
     lib.bnerv_conv_fused_ex.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.bnerv_head_bwd.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp]
     lib.bnerv_pack_conv_weight_dgrad.argtypes = [vp, i, i, i, i, vp, vp]

@@ -81,6 +81,25 @@ class PackedConv:
               lib.bnerv_pack_conv_weight(ptr(w), ptr(b), self.cout, self.cin, self.k, self.s, ptr(self.w), ptr(self.b), _stream()))
 
 
+    _CODE_DTYPES = {torch.int8: 1, torch.int16: 2, torch.int32: 4}
+
+    def repack_codes(self, w_codes, w_scale, b_codes=None, b_scale=None):
+        """Ingest integer codes + scale(s) directly (bnerv_pack_conv_weight_q): bit-identical to
+        repack(w_codes.float() * w_scale, b_codes.float() * b_scale), without materialising the dequantised tensors."""
+        _need_cuda(w_codes, w_scale, b_codes, b_scale)
+        nb = self._CODE_DTYPES.get(w_codes.dtype)
+        if nb is None or (b_codes is not None and b_codes.dtype != w_codes.dtype):
+            raise TypeError("codes must be int8 / int16 / int32 tensors of one dtype")
+        assert tuple(w_codes.shape) == (self.cout * self.s * self.s, self.cin, self.k, self.k)
+        w_codes, w_scale = w_codes.contiguous(), w_scale.detach().contiguous().float()
+        if b_codes is not None:
+            b_codes, b_scale = b_codes.contiguous(), b_scale.detach().contiguous().float()
+        check("bnerv_pack_conv_weight_q",
+              lib.bnerv_pack_conv_weight_q(ptr(w_codes), ptr(w_scale), int(w_scale.numel() > 1), ptr(b_codes), ptr(b_scale),
+                                           int(b_scale is not None and b_scale.numel() > 1), nb, self.cout, self.cin, self.k,
+                                           self.s, ptr(self.w), ptr(self.b), _stream()))
+
+
 # When set to a list, every conv_fused launch appends (algorithmic_flops, start_event, end_event) — used by
 # bench.py to time the dominant kernel inside the timed region on the launching stream.
 TIMING = None
@@ -287,3 +306,16 @@ def unshuffle_c8(src, C, s):
     dst = torch.empty((B, s * s * G, H, W, 8), dtype=torch.float16, device=src.device)
     check("bnerv_unshuffle_c8", lib.bnerv_unshuffle_c8(ptr(src), B, C, H, W, s, ptr(dst), _stream()))
     return dst
+
+
+def frame_metrics(img, gt):
+    """-> f32 [B, 3] on the device: (mse, mae, psnr) per frame (hnerv_utils.py:338-341, 400-403), no host sync."""
+    _need_cuda(img, gt)
+    assert img.shape == gt.shape and img.dtype == torch.float32 and gt.dtype == torch.float32
+    img, gt = img.contiguous(), gt.contiguous()
+    B = img.shape[0]
+    n = img.numel() // B
+    scratch = torch.empty(lib.bnerv_frame_metrics_scratch_doubles(B), dtype=torch.float64, device=img.device)
+    out = torch.empty((B, 3), dtype=torch.float32, device=img.device)
+    check("bnerv_frame_metrics", lib.bnerv_frame_metrics(ptr(img), ptr(gt), B, n, ptr(scratch), ptr(out), _stream()))
+    return out

@@ -249,6 +249,49 @@ __global__ void bias_finalize_kernel(const float* __restrict__ acc, int Cout, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// per-frame error sums for the metrics / pixel losses (hnerv_utils.py:338-341,400-403): deterministic two-stage
+// reduction (fixed block order, f64 partials), so PSNR does not depend on atomics ordering
+// ---------------------------------------------------------------------------------------------
+constexpr int FM_BLOCKS = 296;      // partial sums per frame (2 per SM)
+
+__global__ void frame_err_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, double* __restrict__ part) {
+    const float* pa = a + static_cast<size_t>(blockIdx.y) * n;
+    const float* pb = b + static_cast<size_t>(blockIdx.y) * n;
+    float sq = 0.0f, ab = 0.0f;
+    double dsq = 0.0, dab = 0.0;
+    int cnt = 0;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float d = pa[i] - pb[i];
+        sq = fmaf(d, d, sq);
+        ab += fabsf(d);
+        if (++cnt == 64) { dsq += sq; dab += ab; sq = ab = 0.0f; cnt = 0; }      // bound the f32 running sums
+    }
+    dsq += sq; dab += ab;
+    __shared__ double red[2][BW_THREADS];
+    red[0][threadIdx.x] = dsq; red[1][threadIdx.x] = dab;
+    __syncthreads();
+    for (int off = BW_THREADS / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) { red[0][threadIdx.x] += red[0][threadIdx.x + off]; red[1][threadIdx.x] += red[1][threadIdx.x + off]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        part[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 2 + 0] = red[0][0];
+        part[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 2 + 1] = red[1][0];
+    }
+}
+
+__global__ void frame_err_final_kernel(const double* __restrict__ part, int nblk, size_t n, float* __restrict__ out) {
+    const int b = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    double sq = 0.0, ab = 0.0;
+    for (int i = 0; i < nblk; ++i) { sq += part[(static_cast<size_t>(b) * nblk + i) * 2]; ab += part[(static_cast<size_t>(b) * nblk + i) * 2 + 1]; }
+    const double mse = sq / static_cast<double>(n), mae = ab / static_cast<double>(n);
+    out[b * 3 + 0] = static_cast<float>(mse);
+    out[b * 3 + 1] = static_cast<float>(mae);
+    out[b * 3 + 2] = -10.0f * log10f(static_cast<float>(mse) + 1e-9f);      // psnr_fn_single, hnerv_utils.py:400-403 (f32 like torch)
+}
+
 static int grid_1d(size_t total, int block) {
     size_t g = (total + block - 1) / block;
     const size_t cap = 148 * 16;
@@ -345,4 +388,18 @@ extern "C" int bnerv_bias_finalize(const float* acc, int Cout, int s, const floa
     bias_finalize_kernel<<<grid_1d(static_cast<size_t>(Cout) * s * s, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         acc, Cout, s, round_up(Cout, 16), inv_scale, accumulate, grad);
     return check_launch("bias_finalize_kernel");
+}
+
+extern "C" size_t bnerv_frame_metrics_scratch_doubles(int B) { return B > 0 ? static_cast<size_t>(B) * FM_BLOCKS * 2 : 0; }
+
+extern "C" int bnerv_frame_metrics(const float* img, const float* gt, int B, size_t n_per_frame, double* scratch, float* out,
+                                   void* stream) {
+    if (!img || !gt || !scratch || !out) return set_error(BNERV_E_BADARG, "frame_metrics: null pointer");
+    if (B <= 0 || n_per_frame == 0) return set_error(BNERV_E_BADARG, "frame_metrics: non-positive size");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    frame_err_partial_kernel<<<dim3(FM_BLOCKS, B), BW_THREADS, 0, st>>>(img, gt, n_per_frame, scratch);
+    int rc = check_launch("frame_err_partial_kernel");
+    if (rc) return rc;
+    frame_err_final_kernel<<<B, 32, 0, st>>>(scratch, FM_BLOCKS, n_per_frame, out);
+    return check_launch("frame_err_final_kernel");
 }

@@ -750,6 +750,8 @@ extern "C" int bnerv_conv_fused_ex(const void* x, int B, int Cin, int H, int W, 
     a.n_total    = s * s * cout_p;
     a.n_acc      = choose_n_acc(a.n_total, a.ksteps, a.taps);
     static const bool force_stream = getenv("BNERV_FORCE_STREAM") != nullptr;      // testing switch
+    // resident tiles narrower than 64 rows pay more in padded columns / narrow-N shared-memory bandwidth than the
+    // weights' L2 re-reads cost; between 64 and 96 rows the two modes measured within noise of each other in-model
     a.b_stream   = (force_stream || a.n_acc == 0 || (a.n_acc < 64 && a.n_acc < a.n_total)) ? 1 : 0;
     if (a.b_stream) a.n_acc = choose_n_acc_stream(a.n_total, a.taps);
     if (a.n_acc == 0) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: no tile configuration fits (Cin = %d, k = %d)", Cin, k);

@@ -32,6 +32,46 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int Cout, int Ci
     }
 }
 
+// Quantised ingest (lib/transform_ops.py:239-251 Scale_T.decode, lib/quant_ops.py:40): the effective weight is
+// dequant = round(w / scale) * scale; given the integer codes and the scale(s) the f32 product is formed here exactly
+// as torch forms it, so the packed f16 weights are bit-identical to packing the materialised dequant_w.
+template <typename CodeT>
+__global__ void pack_weight_q_kernel(const CodeT* __restrict__ q, const float* __restrict__ scale, int scale_per_channel,
+                                     int Cout, int Cin, int k, int s, int cout_p, int cin_p, __half* __restrict__ wp) {
+    const int np = s * s * cout_p;
+    const size_t total = static_cast<size_t>(k) * k * cin_p * np;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int kk = idx & 7;
+        size_t r = idx >> 3;
+        const int n = r % np;
+        r /= np;
+        const int kg  = r % (cin_p >> 3);
+        const int tap = r / (cin_p >> 3);
+        int c, i, j;
+        packed_row_to_cij(n, s, cout_p, c, i, j);
+        const int ci = kg * 8 + kk;
+        float v = 0.0f;
+        if (c < Cout && ci < Cin) {
+            const int o = c * s * s + i * s + j;
+            v = __fmul_rn(static_cast<float>(q[(static_cast<size_t>(o) * Cin + ci) * k * k + tap]), scale[scale_per_channel ? o : 0]);
+        }
+        wp[idx] = __float2half_rn(v);
+    }
+}
+
+template <typename CodeT>
+__global__ void pack_bias_q_kernel(const CodeT* __restrict__ q, const float* __restrict__ scale, int scale_per_channel,
+                                   int Cout, int s, int cout_p, float* __restrict__ bp) {
+    const int np = s * s * cout_p;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < np; n += gridDim.x * blockDim.x) {
+        int c, i, j;
+        packed_row_to_cij(n, s, cout_p, c, i, j);
+        const int o = c * s * s + i * s + j;
+        bp[n] = (q != nullptr && c < Cout) ? __fmul_rn(static_cast<float>(q[o]), scale[scale_per_channel ? o : 0]) : 0.0f;
+    }
+}
+
 __global__ void pack_bias_kernel(const float* __restrict__ bias, int Cout, int s, int cout_p, float* __restrict__ bp) {
     const int np = s * s * cout_p;
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < np; n += gridDim.x * blockDim.x) {
@@ -248,6 +288,36 @@ extern "C" int bnerv_pack_conv_weight(const float* w_oihw, const float* bias, in
     if (rc) return rc;
     pack_bias_kernel<<<grid_for(static_cast<size_t>(s) * s * cout_p, 256), 256, 0, st>>>(bias, Cout, s, cout_p, bias_packed);
     return check_launch("pack_bias_kernel");
+}
+
+template <typename CodeT>
+static int pack_q(const void* wq, const float* w_scale, int w_pc, const void* bq, const float* b_scale, int b_pc, int Cout,
+                  int Cin, int k, int s, void* w_packed, float* bias_packed, cudaStream_t st) {
+    const int cout_p = round_up(Cout, 16), cin_p = round_up(Cin, 16);
+    const size_t total = bnerv_packed_weight_numel(Cout, Cin, k, s);
+    pack_weight_q_kernel<CodeT><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const CodeT*>(wq), w_scale, w_pc, Cout, Cin, k, s,
+                                                                      cout_p, cin_p, static_cast<__half*>(w_packed));
+    int rc = check_launch("pack_weight_q_kernel");
+    if (rc) return rc;
+    pack_bias_q_kernel<CodeT><<<grid_for(static_cast<size_t>(s) * s * cout_p, 256), 256, 0, st>>>(
+        static_cast<const CodeT*>(bq), b_scale, b_pc, Cout, s, cout_p, bias_packed);
+    return check_launch("pack_bias_q_kernel");
+}
+
+extern "C" int bnerv_pack_conv_weight_q(const void* w_codes, const float* w_scale, int w_scale_per_channel,
+                                        const void* b_codes, const float* b_scale, int b_scale_per_channel, int code_bytes,
+                                        int Cout, int Cin, int k, int s, void* w_packed, float* bias_packed, void* stream) {
+    if (!w_codes || !w_scale || !w_packed || !bias_packed) return set_error(BNERV_E_BADARG, "pack_conv_weight_q: null pointer");
+    if (b_codes && !b_scale) return set_error(BNERV_E_BADARG, "pack_conv_weight_q: bias codes without a bias scale");
+    if (Cout <= 0 || Cin <= 0 || s <= 0) return set_error(BNERV_E_BADARG, "pack_conv_weight_q: non-positive size");
+    if (k != 1 && k != 3) return set_error(BNERV_E_UNSUPPORTED, "pack_conv_weight_q: kernel size %d (only 1 and 3)", k);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (code_bytes) {
+        case 1: return pack_q<int8_t>(w_codes, w_scale, w_scale_per_channel, b_codes, b_scale, b_scale_per_channel, Cout, Cin, k, s, w_packed, bias_packed, st);
+        case 2: return pack_q<int16_t>(w_codes, w_scale, w_scale_per_channel, b_codes, b_scale, b_scale_per_channel, Cout, Cin, k, s, w_packed, bias_packed, st);
+        case 4: return pack_q<int32_t>(w_codes, w_scale, w_scale_per_channel, b_codes, b_scale, b_scale_per_channel, Cout, Cin, k, s, w_packed, bias_packed, st);
+        default: return set_error(BNERV_E_UNSUPPORTED, "pack_conv_weight_q: code_bytes %d (1, 2 or 4)", code_bytes);
+    }
 }
 
 extern "C" int bnerv_nchw_to_c8(const float* x, int B, int C, int H, int W, void* y_c8, void* stream) {

@@ -63,6 +63,17 @@ uint64_t    bnerv_launch_count(void);
 int bnerv_pack_conv_weight(const float* w_oihw, const float* bias, int Cout, int Cin, int k, int s,
                            void* w_packed, float* bias_packed, void* stream);
 
+/* Quantised-weight ingest: the compression path's effective weight is
+ * dequant_w = round(w / scale) * scale (Scale_T, lib/transform_ops.py:239-251; consumed at lib/quant_ops.py:40).
+ * Given the integer codes round(w/scale) and the scale(s) this packs (float)code * scale - the same f32 product torch
+ * forms - so the result is bit-identical to bnerv_pack_conv_weight(dequant_w, dequant_b) without materialising them.
+ *   w_codes : [Cout*s*s][Cin][k][k] signed integers of `code_bytes` (1, 2 or 4) bytes (Scale_T does not clamp, so
+ *             8-bit quantisation can exceed int8; the caller picks the narrowest type that holds its codes)
+ *   w_scale : 1 float, or [Cout*s*s] when w_scale_per_channel;  b_codes/b_scale : same for the bias, b_codes may be NULL */
+int bnerv_pack_conv_weight_q(const void* w_codes, const float* w_scale, int w_scale_per_channel,
+                             const void* b_codes, const float* b_scale, int b_scale_per_channel, int code_bytes,
+                             int Cout, int Cin, int k, int s, void* w_packed, float* bias_packed, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused conv (the hot op).  One launch computes, for a stride-1 'same' conv with k in {1,3}:
  *     y   = conv_k(x; W, b)                        CustomConv2d.forward, lib/quant_ops.py:39-41
@@ -193,6 +204,15 @@ int bnerv_block_front_bwd(const void* du, const void* dout, const void* x0, cons
 
 /* PixelShuffle(s) transposed on C8 maps: src [B][Cp/8][H*s][W*s][8] -> dst [B][s*s*Cp/8][H][W][8] (un-shuffled order). */
 int bnerv_unshuffle_c8(const void* src, int B, int C, int H, int W, int s, void* dst, void* stream);
+
+/* Per-frame error metrics on the device (hnerv_utils.py:338-341 'L2'/'L1' pixel losses and
+ * psnr_fn_single :400-403) without the reference's per-step .cpu() synchronisation:
+ *   out[b] = { mean((img-gt)^2), mean(|img-gt|), -10*log10(mse + 1e-9) }   (3 floats per frame)
+ * img, gt : f32 [B][n_per_frame]; scratch : bnerv_frame_metrics_scratch_doubles(B) doubles.  Deterministic
+ * (fixed-order two-stage reduction with f64 partial sums). */
+int bnerv_frame_metrics(const float* img, const float* gt, int B, size_t n_per_frame, double* scratch, float* out,
+                        void* stream);
+size_t bnerv_frame_metrics_scratch_doubles(int B);
 
 /* Sizes (in elements) of the buffers the caller must provide. */
 size_t bnerv_c8_numel(int B, int C, int H, int W);                 /* __half elements            */

@@ -232,3 +232,42 @@ def test_argument_errors_are_reported_not_launched(ops):
     ops.conv_fused(ops.nchw_to_c8(xf), wide, 1400, 6, 7, out_pre=out)
     ref = torch.nn.functional.conv2d(xf.half().float(), w.half().float(), None, 1, 1)
     assert max_rel(ops.c8_to_nchw(out, 16), ref) < 6e-4
+
+
+def test_quantised_ingest_is_bit_identical_to_packing_dequantised_weights(ops):
+    """bnerv_pack_conv_weight_q vs Scale_T (lib/transform_ops.py:239-251): codes = round(w/scale), dequant = codes*scale."""
+    torch.manual_seed(0)
+    for (cout, cin, k, s, per_ch, dt) in [(21, 43, 3, 1, False, torch.int8), (13, 27, 3, 2, True, torch.int16), (33, 40, 1, 5, False, torch.int32)]:
+        w = torch.randn(cout * s * s, cin, k, k, device="cuda") * 0.1
+        b = torch.randn(cout * s * s, device="cuda") * 0.1
+        if per_ch:
+            w_scale = (w.amax((1, 2, 3)) - w.amin((1, 2, 3))) / 255
+            sc = w_scale[:, None, None, None]
+        else:
+            w_scale = ((w.max() - w.min()) / 255).reshape(1)
+            sc = w_scale
+        b_scale = ((b.max() - b.min()) / 255).reshape(1)
+        codes, b_codes = (w / sc).round(), (b / b_scale).round()
+        if dt == torch.int8:                     # Scale_T does not clamp; int8 storage is valid only for codes that fit
+            codes, b_codes = codes.clamp(-128, 127), b_codes.clamp(-128, 127)
+        ref = ops.PackedConv(codes * sc, b_codes * b_scale, s)          # what the reference materialises as dequant_w / dequant_b
+        got = ops.PackedConv(torch.zeros_like(w), None, s)
+        got.repack_codes(codes.to(dt), w_scale, b_codes.to(dt), b_scale)
+        assert torch.equal(got.w, ref.w) and torch.equal(got.b, ref.b)
+    with pytest.raises(TypeError):
+        got.repack_codes(codes, w_scale)                                # float codes are refused
+
+
+def test_frame_metrics_match_reference_formulas(ops):
+    torch.manual_seed(0)
+    img = torch.rand(3, 3, 90, 160, device="cuda")
+    gt = (img + 0.05 * torch.randn_like(img)).clamp(0, 1)
+    out = ops.frame_metrics(img, gt)
+    mse = torch.nn.functional.mse_loss(img, gt, reduction="none").flatten(1).double().mean(1)
+    mae = (img - gt).abs().flatten(1).double().mean(1)
+    psnr = -10 * torch.log10(mse.float() + 1e-9)
+    assert max_rel(out[:, 0], mse) < 1e-6 and max_rel(out[:, 1], mae) < 1e-6
+    assert (out[:, 2] - psnr).abs().max().item() < 1e-4
+    assert torch.equal(out, ops.frame_metrics(img, gt))          # deterministic
+    same = ops.frame_metrics(img, img)
+    assert same[:, 0].abs().max().item() == 0.0 and abs(same[0, 2].item() - 90.0) < 1e-3     # -10*log10(1e-9)
