@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--config", default="hnerv_l", help="preset name in bnerv_b200.config (default: the metric's workload)")
     ap.add_argument("--batch", type=int, default=1, help="frames per launch (reference scripts use -b 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the extra training-step measurement (N=1 only)")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="wall-clock budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -355,9 +356,55 @@ def run_b200(opt):
             ts.append(time.perf_counter() - t0)
         line["cpu_baseline"] = {"value": frac / statistics.median(ts), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"median of 2 decodes (1 warm-up) of a {crop[0]}x{crop[1]} crop of the 9x16 stem grid = {frac:.3f} of a frame, oracle port (torch CPU f32, oneDNN)"}
+    if world == 1 and not opt.no_train:
+        # extra, outside the metric: one training step (forward + MSE + backward, batch 1) of the same workload on the
+        # native backward kernels vs torch autograd with cuDNN TF32 allowed (the reference's default GPU arithmetic)
+        try:
+            line["train_step"] = train_step_times(opt.config, dev)
+        except Exception as ex:  # never let the extra measurement take the metric line down
+            line["train_step"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_times(cfg_name, dev, steps=5):
+    out = {"what": "forward + MSE loss + backward, batch 1, CUDA-event timed, ms per step (SURVEY.md §8f rank 1)"}
+    for mode, tf32 in (("b200", False), ("torch", True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        model, args = build_model(cfg_name)
+        model = model.to(dev).train()
+        model.train_backend = mode
+        is_h = args.model == "HNeRV_Boost"
+        fh, fw = [int(v) for v in args.fc_hw.split("_")]
+        emb = torch.rand(1, 16, fh, fw, device=dev) if is_h else None
+        t = torch.tensor([0.5], dtype=torch.float64, device=dev)
+        target = None
+
+        def step():
+            nonlocal target
+            model.zero_grad(set_to_none=True)
+            img = (model.forward_decoder(emb, t) if is_h else model(t))[0]
+            if target is None:
+                target = torch.rand_like(img)
+            ((img - target) ** 2).mean().backward()
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        out["native_ms" if mode == "b200" else "torch_autograd_cudnn_tf32_ms"] = e0.elapsed_time(e1) / steps
+        del model
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return out
 
 
 if __name__ == "__main__":

@@ -158,3 +158,28 @@ def test_full_resolution_properties_hnerv_1080p():
     finally:
         orc.EMULATE = None
     assert max_rel(img[:, :, :96, :216].cpu(), emu[:, :, :96, :216]) < 2e-4
+
+
+@pytest.mark.parametrize("name", ["hnerv_l", "enerv_m", "nerv_s"])
+def test_benchmarked_presets_full_frame_against_oracle(name):
+    """The configurations bench.py measures (BASELINE.json configs 2-4: full width, full resolution, random-init
+    weights under manual_seed(1)) decoded natively vs the CPU oracle on the same frame: 1e-3 gate + PSNR."""
+    import bench
+    from bnerv_b200 import preset
+    model, a = bench.build_model(name)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    cfg = orc.cfg_from_args(a)
+    fh, fw = [int(v) for v in a.fc_hw.split("_")]
+    t = torch.tensor([312 / 600], dtype=torch.float64)
+    emb = torch.rand(1, 16, fh, fw, generator=torch.Generator().manual_seed(9))
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    with torch.no_grad():
+        if a.model == "HNeRV_Boost":
+            ref, _ = orc.hnerv_boost_decode(sd, cfg, emb, t)
+        else:
+            ref, _ = orc.forward(a.model, sd, cfg, t)
+        model = model.cuda()
+        img = (model.forward_decoder(emb.cuda(), t.cuda()) if a.model == "HNeRV_Boost" else model(t.cuda()))[0]
+    assert img.shape == ref.shape and img.shape[-1] in (1280, 1920)
+    assert max_rel(img.cpu(), ref) < REL
+    assert orc.psnr(img.cpu(), ref) > 60.0
