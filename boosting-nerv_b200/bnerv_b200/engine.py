@@ -15,6 +15,8 @@ by programmatic dependent launch.  ``engine.use_graph = False`` runs the same se
 Weights are re-packed only when the effective tensor (``dequant_w ?? weight``) changed — detected through
 tensor identity + in-place version counters, so optimiser steps and ``cal_params`` invalidate the cache.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -33,7 +35,7 @@ def _tensor_key(t):
 class _ConvSlot:
     """One conv of the cascade: module + geometry + lazily (re)packed weights."""
 
-    def __init__(self, module, s=1):
+    def __init__(self, module, s=1, head=False):
         if not isinstance(module, nn.Conv2d) or module.stride != (1, 1) or module.dilation != (1, 1) or module.groups != 1:
             raise Unsupported(f"conv {module} is not a stride-1 dense conv")
         k = module.kernel_size[0]
@@ -42,6 +44,8 @@ class _ConvSlot:
         self.m, self.k, self.s = module, k, s
         self.cin, self.cout = module.in_channels, module.out_channels // (s * s)
         self.key, self.pc = None, None
+        # HNeRV's 3x3 head to 3 channels has its own kernel form (bnerv_head_conv3); BNERV_NO_HEAD_KERNEL=1 = generic path
+        self.head3 = bool(head and k == 3 and self.cout <= 3 and not os.environ.get("BNERV_NO_HEAD_KERNEL"))
 
     def packed(self, force=False):
         """force: re-pack unconditionally (inside a captured training graph the pack kernels ARE the per-step ingest)."""
@@ -49,7 +53,7 @@ class _ConvSlot:
         key = (_tensor_key(w), _tensor_key(b))
         if key != self.key or force:
             if self.pc is None:
-                self.pc = ops.PackedConv(w, b, self.s)
+                self.pc = ops.PackedHead(w, b) if self.head3 else ops.PackedConv(w, b, self.s)
             else:
                 self.pc.repack(w, b)
             self.key = key
@@ -138,7 +142,7 @@ class DecoderEngine:
         if model.out_bias != "tanh":
             raise Unsupported(f"out_bias {model.out_bias!r}: only 'tanh' is accelerated")
         self.blocks = [_BlockPlan(b) for b in blocks]
-        self.head = _ConvSlot(model.head_layer)
+        self.head = _ConvSlot(model.head_layer, head=True)
         self._ws = {}          # workspaces per (B, h, w)
         self._sft = {}         # SftTable per B
         self._sft_key = None

@@ -100,6 +100,29 @@ class PackedConv:
                                            self.s, ptr(self.w), ptr(self.b), _stream()))
 
 
+class PackedHead:
+    """Weights of a 3x3 conv to <= 3 channels in the head kernel's layout (bnerv_pack_head_weight): one [Kp][32] slab
+    whose column tap*Cout + c holds W[c][:, tap]; the bias stays a raw f32 vector."""
+
+    def __init__(self, weight, bias):
+        _need_cuda(weight, bias)
+        self.cout, self.cin, k, k2 = weight.shape
+        assert k == 3 and k2 == 3 and self.cout <= 3
+        self.k, self.s = 3, 1
+        dev = weight.device
+        self.w = torch.empty(32 * round_up(self.cin, 16), dtype=torch.float16, device=dev)
+        self.b = torch.zeros(self.cout, dtype=torch.float32, device=dev)
+        self.repack(weight, bias)
+
+    def repack(self, weight, bias):
+        w = weight.detach().contiguous().float()
+        check("bnerv_pack_head_weight", lib.bnerv_pack_head_weight(ptr(w), self.cout, self.cin, ptr(self.w), _stream()))
+        if bias is None:
+            self.b.zero_()
+        else:
+            self.b.copy_(bias.detach())
+
+
 # When set to a list, every conv_fused launch appends (algorithmic_flops, start_event, end_event) — used by
 # bench.py to time the dominant kernel inside the timed region on the launching stream.
 TIMING = None
@@ -119,7 +142,12 @@ def conv_fused(x_c8, pc, cin, H, W, act="none", resid=None, g1p=None, beta=None,
     if TIMING is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    if out_deriv is None:
+    if isinstance(pc, PackedHead):
+        if out_nchw is None or resid is not None or g1p is not None or out_pre is not None or out_deriv is not None:
+            raise ValueError("the head kernel writes the NCHW f32 image only")
+        check("bnerv_head_conv3", lib.bnerv_head_conv3(ptr(x_c8), B, cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, ACT_CODES[act],
+                                                       ptr(out_nchw), _stream()))
+    elif out_deriv is None:
         check("bnerv_conv_fused",
               lib.bnerv_conv_fused(ptr(x_c8), B, cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, pc.k, pc.s, ACT_CODES[act],
                                    ptr(resid), ptr(g1p), ptr(beta), ptr(out_pre), ptr(out_aff), ptr(out_nchw), _stream()))

@@ -129,6 +129,13 @@ __device__ __forceinline__ WorkRange work_range(const ConvTcArgs& a, uint32_t pa
 constexpr int F_RESID = 1, F_AFF = 2, F_PRE = 4, F_NCHW = 8, F_SHUF = 16;
 constexpr int F_WIDE = 32;   // s == 2 row packing: the two chunks of a group are 32 contiguous output bytes
 constexpr int F_DERIV = 64;  // also write act'(pre-activation) (training forward)
+constexpr int F_HEAD = 128;  // 3x3 conv to <= 3 channels as ONE 1x1 contraction to 9*Cout columns + shift-sum (see mma_role_head)
+
+// Head mode geometry: P[q][(tap, c)] for the 18 x 18 halo pixels q of a 16 x 16 output tile, staged in shared memory
+constexpr int HEAD_N     = 32;                    // UMMA N (27 used for Cout = 3)
+constexpr int HEAD_PSTR  = 27;                    // floats per halo pixel (odd: conflict-free across a pixel row)
+constexpr int HEAD_PBUF_FLOATS = 18 * 18 * HEAD_PSTR;
+constexpr int HEAD_SMEM_BYTES  = 2 * HEAD_PBUF_FLOATS * 4;
 
 template <int ACT>
 __device__ __forceinline__ float2 act2_rt(float2 x, int act) {
@@ -371,6 +378,130 @@ __device__ __forceinline__ void mma_role(const ConvTcArgs& a, const Pipe& p) {
     }
 }
 
+// ===================== MMA issuer, head mode =====================
+// out[p, c] = sum_tap sum_k W[c][k][tap] X[p + tap, k]  is evaluated as  P[q, (tap, c)] = sum_k X[q, k] W[c][k][tap]
+// for every HALO pixel q (one 1x1 contraction, N = 9*Cout <= 32) followed by out[p, c] = sum_tap P[p + tap, (tap, c)]
+// in the epilogue: 6 UMMAs (M = 256, N = 32) per K step cover the 18 x 18 halo with 16-row x 8-px blocks at row
+// offsets {0, 2} and px offsets {0, 8, 10} - against 18 UMMAs (9 taps x 2 blocks, N = 16) of the generic path, whose
+// cost is the A-operand read, not the math.
+template <int MT>
+__device__ __forceinline__ void mma_role_head(const ConvTcArgs& a, const Pipe& p) {
+    using G = Geo<MT>;
+    int stage = 0;
+    uint32_t phase = 0;
+    int abuf = 0;
+    uint32_t aphase = 0;
+    const uint32_t idesc   = umma_idesc_f16(256, HEAD_N);
+    const uint32_t b_ks16  = static_cast<uint32_t>(a.b_kstep_bytes) >> 4;
+    const uint64_t a_hi    = umma_desc_hi_noswz(G::A_GROUP_B, G::HALO_W * 16);
+    const uint64_t b_hi    = umma_desc_hi_noswz(a.n_half * 16u, 128u);
+    const uint32_t wb16    = (p.w_base & 0x3FFFFu) >> 4;
+    const uint32_t ab16    = (p.a_base & 0x3FFFFu) >> 4;
+    const WorkRange wr = work_range(a, p.pair);
+    if (wr.begin < wr.end) {
+        mbar_wait(p.wfull, 0);                    // one n-tile: the weights are loaded once
+        tc_fence_after();
+    }
+    for (int it = wr.begin; it < wr.end; ++it) {
+        mbar_wait(p.tempty + abuf * 8, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = p.tmem_base + abuf * BUF_COLS;
+        for (int kc = 0; kc < a.ksteps; ++kc) {
+            mbar_wait(p.full + stage * 8, phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sa16 = ab16 + stage * (static_cast<uint32_t>(a.stage_bytes) >> 4);
+                const uint64_t bdesc = b_hi | static_cast<uint64_t>(wb16 + kc * b_ks16);
+#pragma unroll
+                for (int blk = 0; blk < 6; ++blk) {
+                    const int ro = (blk / 3) * 2, po = (blk % 3 == 0) ? 0 : (blk % 3 == 1 ? 8 : 10);
+                    const uint64_t adesc = a_hi | static_cast<uint64_t>(sa16 + ro * G::HALO_W + po);
+                    umma_f16_pair(d0 + blk * HEAD_N, adesc, bdesc, idesc, kc > 0 ? 1u : 0u);
+                }
+                umma_commit_pair(p.empty + stage * 8);
+                if (kc == a.ksteps - 1) umma_commit_pair(p.tfull + abuf * 8);
+            }
+            __syncwarp();
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        abuf ^= 1;
+        if (abuf == 0) aphase ^= 1;
+    }
+}
+
+// ===================== epilogue, head mode (all 16 epilogue warps) =====================
+template <int MT, int ACT>
+__device__ __forceinline__ void epilogue_head(const ConvTcArgs& a, const Pipe& p, float* pbuf, int warp, int lane) {
+    const int e   = warp - 2;
+    const int q   = warp & 3;
+    const int sub = e >> 2;                         // 0..3: blocks {sub, sub + 4}
+    const int m   = q * 32 + lane;                  // row of a 16-row x 8-px P block
+    const int et  = threadIdx.x - 64;
+    const uint32_t tempty_leader = map_to_cta(p.tempty, 0);
+    const WorkRange wr = work_range(a, p.pair);
+    const int ntap_c = 9 * a.cout;
+    int abuf = 0;
+    uint32_t aphase = 0;
+    float bias_c[2] = {0.0f, 0.0f};                 // this thread's output channels: c = (et >> 8) + 2*i
+    for (int i = 0; i < 2; ++i) {
+        const int c = (et >> 8) + 2 * i;
+        if (c < a.cout) bias_c[i] = __ldg(a.bias + c);
+    }
+    pdl_wait();
+    for (int it = wr.begin; it < wr.end; ++it) {
+        const TileCoord t = decode_tile<MT>(a, it, p.rank);      // n_tiles == 1: item == pixel pair-tile
+        float* pb = pbuf + abuf * HEAD_PBUF_FLOATS;
+        mbar_wait(p.tfull + abuf * 8, aphase);
+        tc_fence_after();
+        // phase A: P blocks TMEM -> shared memory (only the pixels a block is the first to cover)
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+            const int blk = sub + 4 * rep;
+            if (blk < 6) {                           // warp-uniform
+                const int ro = (blk / 3) * 2, pj = blk % 3, po = (pj == 0) ? 0 : (pj == 1 ? 8 : 10);
+                const uint32_t taddr = p.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + abuf * BUF_COLS + blk * HEAD_N;
+                uint32_t v0[16], v1[16];
+                tmem_ld16(taddr, v0);
+                tmem_ld16(taddr + 16, v1);
+                tmem_ld_wait();
+                const bool fresh = (ro == 0 || (m >> 3) >= 14) && (pj != 2 || (m & 7) >= 6);
+                if (fresh) {
+                    float* dst = pb + ((ro + (m >> 3)) * 18 + po + (m & 7)) * HEAD_PSTR;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) dst[k] = __uint_as_float(v0[k]);
+#pragma unroll
+                    for (int k = 0; k < HEAD_PSTR - 16; ++k) dst[16 + k] = __uint_as_float(v1[k]);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader + abuf * 8);       // TMEM buffer free as soon as it is copied out
+        named_bar_sync(1, 32 * N_EPI_WARPS);
+        // phase B: shift-sum of the 9 taps, bias, activation, NCHW f32 store
+        {
+            const int pidx = et & 255, hh = pidx >> 4, ww = pidx & 15;
+            const int h = t.h0 + hh, w = t.w0 + ww;
+            const bool valid = (h < a.H) && (w < a.W);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int c = (et >> 8) + 2 * i;
+                if (c < a.cout) {
+                    float acc = bias_c[i];
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap)
+                        acc += pb[((hh + tap / 3) * 18 + ww + tap % 3) * HEAD_PSTR + tap * a.cout + c];
+                    const float2 o = act2_rt<ACT>(make_float2(acc, 0.0f), a.act);
+                    if (valid) a.out_nchw[(static_cast<size_t>(t.b * a.cout + c) * a.H + h) * a.W + w] = o.x;
+                }
+            }
+        }
+        (void)ntap_c;
+        abuf ^= 1;
+        if (abuf == 0) aphase ^= 1;
+    }
+}
+
 template <int MT, int ACT, int FLAGS>
 __global__ void __launch_bounds__(N_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcArgs a) {
@@ -425,9 +556,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         producer_role<MT>(a, p, &tmA, &tmB);
     } else if (warp == 1) {
         if (p.rank == 0) {
-            if (a.taps == 9) mma_role<MT, 9>(a, p); else mma_role<MT, 1>(a, p);
+            if (flags & F_HEAD) mma_role_head<MT>(a, p);
+            else if (a.taps == 9) mma_role<MT, 9>(a, p);
+            else mma_role<MT, 1>(a, p);
         }
     } else {
+      if (flags & F_HEAD) {
+        epilogue_head<MT, ACT>(a, p, reinterpret_cast<float*>(cst + 2), warp, lane);
+      } else {
         // ===================== epilogue: 16 warps per CTA =====================
         // warp -> (TMEM lane quarter q = warp%4 [hardware rule], row block mt, column slot cs of CS):
         // a warp owns the 16-column groups g16 = cs, cs+CS, cs+2CS, cs+3CS of its row block.
@@ -565,6 +701,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (abuf == 0) aphase ^= 1;
             }
         }
+      }
     }
 
     // both CTAs done (the leader's MMAs write the peer's TMEM; the peer's loads credit the leader's barriers)
@@ -679,6 +816,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
     BNERV_PICK(10, BNERV_ACT_SIN, F_AFF | F_PRE | F_SHUF | F_WIDE | F_DERIV)
     BNERV_PICK(11, BNERV_ACT_GELU, F_AFF | F_PRE | F_DERIV)
     BNERV_PICK(12, BNERV_ACT_NONE, F_PRE)                       // dgrad
+    BNERV_PICK(13, BNERV_ACT_TANH01, F_NCHW | F_HEAD)           // 3x3 head conv, 1x1-contraction + shift-sum form
 #undef BNERV_PICK
     static bool smem_set[16] = {};
     if (!smem_set[slot]) {
@@ -806,4 +944,62 @@ extern "C" int bnerv_conv_fused_ex(const void* x, int B, int Cin, int H, int W, 
     const size_t smem_bytes = static_cast<size_t>(a.b_bytes) + static_cast<size_t>(stages) * a_stage + fixed_smem_bytes();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return mt == 2 ? launch_conv<2>(tmA, tmB, a, act, smem_bytes, st) : launch_conv<1>(tmA, tmB, a, act, smem_bytes, st);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// head mode entry point
+// ---------------------------------------------------------------------------------------------
+extern "C" int bnerv_head_conv3(const void* x, int B, int Cin, int H, int W, const void* w_head_packed, const float* bias,
+                                int Cout, int act, float* out_nchw, void* stream) {
+    if (!x || !w_head_packed || !bias || !out_nchw) return set_error(BNERV_E_BADARG, "head_conv3: null pointer");
+    if (B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || Cout <= 0) return set_error(BNERV_E_BADARG, "head_conv3: non-positive size");
+    if (9 * Cout > HEAD_PSTR) return set_error(BNERV_E_UNSUPPORTED, "head_conv3: Cout = %d (at most 3)", Cout);
+    if (act < BNERV_ACT_NONE || act > BNERV_ACT_TANH01) return set_error(BNERV_E_UNSUPPORTED, "head_conv3: act %d", act);
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_head_packed)) & 15)
+        return set_error(BNERV_E_BADARG, "head_conv3: pointers must be 16-byte aligned");
+    const int cin_p = round_up(Cin, 16);
+    ConvTcArgs a{};
+    a.B = B; a.H = H; a.W = W;
+    a.cin_groups = cin_p / 8;
+    a.ksteps = cin_p / 16;
+    a.taps = 1;                                   // the packed weight is one [Kp][32] slab
+    a.n_total = HEAD_N; a.n_acc = HEAD_N; a.n_half = HEAD_N / 2; a.n_tiles = 1;
+    a.cout = Cout; a.cout_p = 16; a.s = 1; a.act = act;
+    a.flags = F_NCHW | F_HEAD;
+    const int tile_w = 16;
+    a.tiles_x = (W + tile_w - 1) / tile_w;
+    a.tiles_y = (H + TILE_H - 1) / TILE_H;
+    a.pairs_x = (a.tiles_x + 1) / 2;
+    const long long pair_tiles = 1LL * B * a.tiles_y * a.pairs_x;
+    if (pair_tiles > 0x3fffffffLL) return set_error(BNERV_E_UNSUPPORTED, "head_conv3: too many tiles");
+    a.pair_tiles = static_cast<int>(pair_tiles);
+    a.work_total = a.pair_tiles;
+    a.b_stream = 0;
+    a.b_kstep_bytes = 2 * a.n_half * 16;
+    a.b_bytes = a.ksteps * a.b_kstep_bytes;
+    a.stage_bytes = a_stage_bytes(2);
+    int stages = (SMEM_LIMIT - fixed_smem_bytes() - HEAD_SMEM_BYTES - a.b_bytes) / a.stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < MIN_STAGES) return set_error(BNERV_E_UNSUPPORTED, "head_conv3: Cin = %d too wide", Cin);
+    a.stages = stages;
+    a.bias = bias;
+    a.out_nchw = out_nchw;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    const int max_pairs = g_num_sms / 2;
+    a.n_pairs = a.work_total < max_pairs ? a.work_total : max_pairs;
+    CUtensorMap tmA, tmB;
+    int rc = make_map_u64_3d(&tmA, x, 2ull * W, H, 1ull * B * a.cin_groups, 16ull * W, 16ull * W * H, 2 * (tile_w + 2), HALO_H, 2);
+    if (rc) return rc;
+    rc = make_map_u64_3d(&tmB, w_head_packed, 2ull * HEAD_N, a.cin_groups, 1, 16ull * HEAD_N, 16ull * HEAD_N * a.cin_groups,
+                         2 * a.n_half, 2, 1);
+    if (rc) return rc;
+    const size_t smem_bytes = static_cast<size_t>(a.b_bytes) + static_cast<size_t>(stages) * a.stage_bytes + fixed_smem_bytes() +
+                              HEAD_SMEM_BYTES;
+    return launch_conv<2>(tmA, tmB, a, act, smem_bytes, static_cast<cudaStream_t>(stream));
 }

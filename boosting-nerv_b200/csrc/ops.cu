@@ -72,6 +72,23 @@ __global__ void pack_bias_q_kernel(const CodeT* __restrict__ q, const float* __r
     }
 }
 
+// head weights for bnerv_head_conv3: [Kp/8][32][8] f16, column n = tap*Cout + c holds W[c][k][tap]
+__global__ void pack_head_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int cin_p, __half* __restrict__ wp) {
+    const int total = cin_p * 32;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int kk = idx & 7;
+        const int n = (idx >> 3) & 31;
+        const int kg = idx >> 8;
+        const int ci = kg * 8 + kk;
+        float v = 0.0f;
+        if (n < 9 * Cout && ci < Cin) {
+            const int tap = n / Cout, c = n - tap * Cout;
+            v = w[(static_cast<size_t>(c) * Cin + ci) * 9 + tap];
+        }
+        wp[idx] = __float2half_rn(v);
+    }
+}
+
 __global__ void pack_bias_kernel(const float* __restrict__ bias, int Cout, int s, int cout_p, float* __restrict__ bp) {
     const int np = s * s * cout_p;
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < np; n += gridDim.x * blockDim.x) {
@@ -318,6 +335,16 @@ extern "C" int bnerv_pack_conv_weight_q(const void* w_codes, const float* w_scal
         case 4: return pack_q<int32_t>(w_codes, w_scale, w_scale_per_channel, b_codes, b_scale, b_scale_per_channel, Cout, Cin, k, s, w_packed, bias_packed, st);
         default: return set_error(BNERV_E_UNSUPPORTED, "pack_conv_weight_q: code_bytes %d (1, 2 or 4)", code_bytes);
     }
+}
+
+extern "C" int bnerv_pack_head_weight(const float* w_oihw, int Cout, int Cin, void* w_head_packed, void* stream) {
+    if (!w_oihw || !w_head_packed) return set_error(BNERV_E_BADARG, "pack_head_weight: null pointer");
+    if (Cout <= 0 || Cin <= 0) return set_error(BNERV_E_BADARG, "pack_head_weight: non-positive size");
+    if (Cout > 3) return set_error(BNERV_E_UNSUPPORTED, "pack_head_weight: Cout = %d (at most 3)", Cout);
+    const int cin_p = round_up(Cin, 16);
+    pack_head_weight_kernel<<<grid_for(static_cast<size_t>(cin_p) * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w_oihw, Cout, Cin, cin_p, static_cast<__half*>(w_head_packed));
+    return check_launch("pack_head_weight_kernel");
 }
 
 extern "C" int bnerv_nchw_to_c8(const float* x, int B, int C, int H, int W, void* y_c8, void* stream) {

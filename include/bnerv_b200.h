@@ -109,6 +109,15 @@ int bnerv_conv_fused_ex(const void* x, int B, int Cin, int H, int W,
                         int act, const void* resid, const float* g1p, const float* beta,
                         void* out_pre, void* out_aff, float* out_nchw, void* out_deriv, void* stream);
 
+/* The 3x3 head conv to <= 3 channels (HNeRV_Boost.head_layer, model_hnerv.py:214,273) + OutImg (model_blocks.py:57-63)
+ * in its own form: out[p,c] = act(b[c] + sum_tap P[p+tap][(tap,c)]) with P = X . Wp ONE 1x1 tensor-core contraction to
+ * 9*Cout (<= 27) columns over the halo tile, summed over the taps from shared memory.  Same result as
+ * bnerv_conv_fused(k = 3, out_nchw) with a third of the UMMAs (the N = 16 launch is bound by its A-operand reads).
+ *   w_head_packed : bnerv_pack_head_weight output, [Kp/8][32][8] f16 (32*Kp halves); bias : the raw f32 [Cout]. */
+int bnerv_pack_head_weight(const float* w_oihw, int Cout, int Cin, void* w_head_packed, void* stream);
+int bnerv_head_conv3(const void* x, int B, int Cin, int H, int W, const void* w_head_packed, const float* bias,
+                     int Cout, int act, float* out_nchw, void* stream);
+
 /* Same contract and operand layouts as bnerv_conv_fused, computed by an f32 CUDA-core kernel on the
  * reference's own layouts (NCHW f32 activations, OIHW f32 weights) — the exact-arithmetic path used
  * for tiny layers and as the on-device cross-check of the tensor-core kernel.

@@ -271,3 +271,25 @@ def test_frame_metrics_match_reference_formulas(ops):
     assert torch.equal(out, ops.frame_metrics(img, gt))          # deterministic
     same = ops.frame_metrics(img, img)
     assert same[:, 0].abs().max().item() == 0.0 and abs(same[0, 2].item() - 90.0) < 1e-3     # -10*log10(1e-9)
+
+
+@pytest.mark.parametrize("B,cin,cout,H,W,act", [(1, 16, 3, 16, 32, "tanh01"), (2, 21, 3, 37, 53, "tanh01"), (1, 40, 2, 20, 70, "none"),
+                                                 (1, 112, 3, 50, 17, "tanh01"), (1, 13, 1, 5, 3, "none")])
+def test_head_kernel_matches_reference_and_generic_path(ops, B, cin, cout, H, W, act):
+    """bnerv_head_conv3 (1x1 contraction to 9*Cout columns + shift-sum) == 3x3 conv + OutImg (model_hnerv.py:214,273;
+    model_blocks.py:57-63), and agrees with the generic fused conv on the same inputs."""
+    torch.manual_seed(0)
+    x = torch.randn(B, cin, H, W, device="cuda")
+    w = torch.randn(cout, cin, 3, 3, device="cuda") / (cin * 9) ** 0.5
+    b = torch.randn(cout, device="cuda") * 0.1
+    xc = ops.nchw_to_c8(x)
+    out_h = torch.full((B, cout, H, W), float("nan"), device="cuda")
+    out_g = torch.full((B, cout, H, W), float("nan"), device="cuda")
+    ops.conv_fused(xc, ops.PackedHead(w, b), cin, H, W, act=act, out_nchw=out_h)
+    ops.conv_fused(xc, ops.PackedConv(w, b, 1), cin, H, W, act=act, out_nchw=out_g)
+    ref = torch.nn.functional.conv2d(x.half().float(), w.half().float(), b, 1, 1)
+    ref = torch.tanh(ref) * 0.5 + 0.5 if act == "tanh01" else ref
+    assert max_rel(out_h, ref) < 1e-5                 # same f16 operands, f32 accumulation: only summation order differs
+    assert max_rel(out_h, out_g) < 1e-5
+    with pytest.raises(Exception):
+        ops.PackedHead(torch.zeros(4, 16, 3, 3, device="cuda"), None)      # more than 3 output channels: not this kernel

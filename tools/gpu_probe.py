@@ -29,7 +29,8 @@ def ref_conv(x, w, b, s, act, resid, g1p, beta):
     return y, aff
 
 
-def run_case(name, B, cin, cout, H, W, k, s, act="none", resid=False, affine=False, nchw=False, time_it=False, scale=1.0, pre=True):
+def run_case(name, B, cin, cout, H, W, k, s, act="none", resid=False, affine=False, nchw=False, time_it=False, scale=1.0, pre=True,
+             head=False):
     torch.manual_seed(0)
     x = torch.randn(B, cin, H, W, device=dev)
     w = torch.randn(cout * s * s, cin, k, k, device=dev) * (scale / (cin * k * k) ** 0.5)
@@ -40,7 +41,7 @@ def run_case(name, B, cin, cout, H, W, k, s, act="none", resid=False, affine=Fal
     if affine:
         g1p = torch.zeros(B, cp, device=dev); beta = torch.zeros(B, cp, device=dev)
         g1p[:, :cout] = 1 + 0.3 * torch.randn(B, cout, device=dev); beta[:, :cout] = 0.3 * torch.randn(B, cout, device=dev)
-    pc = ops.PackedConv(w, b, s)
+    pc = ops.PackedHead(w, b) if head else ops.PackedConv(w, b, s)
     xc = ops.nchw_to_c8(x)
     rc = ops.nchw_to_c8(r) if resid else None
     out_pre = torch.full(ops.c8_shape(B, cout, H * s, W * s), float("nan"), dtype=torch.float16, device=dev) if pre else None
@@ -93,6 +94,10 @@ CASES = {
     "k3_gelu":     dict(B=1, cin=43, cout=43, H=30, W=50, k=3, s=1, act="gelu", affine=True),
     "head_k3":     dict(B=1, cin=21, cout=3, H=36, W=64, k=3, s=1, act="tanh01", nchw=True),
     "head_k1":     dict(B=1, cin=12, cout=3, H=36, W=64, k=1, s=1, act="tanh01", nchw=True),
+    "headk_min":   dict(B=1, cin=16, cout=3, H=16, W=32, k=3, s=1, act="tanh01", nchw=True, pre=False, head=True),
+    "headk_odd":   dict(B=2, cin=21, cout=3, H=37, W=53, k=3, s=1, act="tanh01", nchw=True, pre=False, head=True),
+    "headk_c2":    dict(B=1, cin=40, cout=2, H=20, W=70, k=3, s=1, act="none", nchw=True, pre=False, head=True),
+    "L_headk":     dict(B=1, cin=112, cout=3, H=1080, W=1920, k=3, s=1, act="tanh01", nchw=True, pre=False, head=True, time_it=True),
     "n144":        dict(B=1, cin=135, cout=135, H=64, W=64, k=3, s=1, act="gelu", affine=True),
     "big_in":      dict(B=1, cin=16, cout=16, H=16, W=16, k=3, s=1, scale=300.0, act="sin"),
     # HNeRV-L shapes, timed
