@@ -267,7 +267,7 @@ class DecoderEngine:
         self._body(cap.inputs, keep)            # eager warm-up: packs weights, builds workspaces / SFT tables, sets attributes
         torch.cuda.synchronize()
         cap.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cap.graph):
+        with torch.cuda.graph(cap.graph, capture_error_mode="thread_local"):   # DataLoader pin-memory threads may call CUDA meanwhile
             cap.outputs = self._body(cap.inputs, keep)
         return cap
 

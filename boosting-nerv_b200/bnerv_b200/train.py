@@ -290,11 +290,11 @@ class _TrainGraph:
         del st, img
         torch.cuda.synchronize()
         self.gf = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.gf):
+        with torch.cuda.graph(self.gf, capture_error_mode="thread_local"):
             self.img, self.first, self.st = _forward_body(eng, lay, self.x, self.scale, self.shift, True)
         self.dimg = torch.zeros_like(self.img)
         self.gb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.gb, pool=self.gf.pool()):
+        with torch.cuda.graph(self.gb, pool=self.gf.pool(), capture_error_mode="thread_local"):
             self.gx, self.gscale, self.gshift, self.gconv = _backward_body(eng, lay, self.st, self.dimg, need_x, True)
 
     def busy(self):
