@@ -1,0 +1,61 @@
+"""Pipelined host-to-host decode: the throughput form of the reference's evaluate() loop.
+
+The reference decodes frame by frame and pulls every result to the host synchronously (`model(...)` with its
+`torch.cuda.synchronize()` at model_nerv.py:58-59, then `.cpu()` in the metric code, train_nerv_all.py:482-505), so the
+25 MB device-to-host copy of a 1080p f32 frame (~1 ms over PCIe) sits on the critical path of every frame.  Here the
+same three steps run as a three-stage pipeline on two streams:
+
+    compute stream : H2D of (embedding, norm_idx) -> one CUDA-graph replay -> 8 us device copy into a staging slot
+    copy stream    : D2H of the staging slot into the caller's pinned buffer
+
+with `depth` staging slots guarded by events, so frame i's read-back overlaps frame i+1's decode.  Results are
+bit-identical to model.forward()/forward_decoder() frame by frame (same graph, same kernels).
+"""
+import torch
+
+
+def decode_to_host(model, norm_idx_host, out_host, embed_host=None, batch=1, depth=3, ring=False):
+    """Decode frames [0, N) into ``out_host`` ([N,3,H,W] f32, ideally pinned).  With ``ring=True`` ``out_host`` may hold
+    fewer than N frames (a multiple of ``batch``) and is used cyclically - frame i lands in slot i % len(out_host) - for
+    consumers that drain the buffer while decoding continues.
+
+    norm_idx_host: [N] float64 host tensor ((i+1)/n_frames, hnerv_utils.py:47); embed_host: [N,16,h,w] f32 host tensor
+    for HNeRV_Boost, None for NeRV_Boost / ENeRV_Boost.  Returns when every frame has landed in ``out_host``."""
+    if norm_idx_host.is_cuda or out_host.is_cuda or (embed_host is not None and embed_host.is_cuda):
+        raise ValueError("decode_to_host takes HOST tensors (pinned for asynchronous copies)")
+    dev = next(model.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("bnerv_b200: the decode path runs only on a CUDA (sm_100a) device")
+    n = norm_idx_host.shape[0]
+    slots = out_host.shape[0]
+    assert (slots == n or (ring and slots % batch == 0 and slots > 0)) and (embed_host is None or embed_host.shape[0] == n)
+    is_h = embed_host is not None
+    compute = torch.cuda.current_stream(dev)
+    state = model.__dict__.setdefault("_stream_state", {})
+    copy = state.get("copy")
+    if copy is None or copy.device != dev:
+        copy = state["copy"] = torch.cuda.Stream(dev)
+    stages, ready, done = {}, {}, {}
+    with torch.no_grad():
+        for j, lo in enumerate(range(0, n, batch)):
+            sl = slice(lo, min(lo + batch, n))
+            k = j % depth
+            t = norm_idx_host[sl].to(dev, non_blocking=True)
+            img = model.decode(embed_host[sl].to(dev, non_blocking=True), t) if is_h else model.decode(t)
+            key = (k, tuple(img.shape))
+            if key not in stages:
+                stages[key] = torch.empty_like(img)
+                ready[key], done[key] = torch.cuda.Event(), None
+            if done[key] is not None:
+                compute.wait_event(done[key])          # the slot's previous read-back (depth frames ago) has finished
+            stages[key].copy_(img)
+            ready[key].record(compute)
+            with torch.cuda.stream(copy):
+                copy.wait_event(ready[key])
+                lo_s = lo % slots
+                out_host[lo_s:lo_s + (sl.stop - sl.start)].copy_(stages[key], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                done[key] = ev
+    copy.synchronize()
+    return out_host

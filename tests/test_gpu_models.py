@@ -183,3 +183,29 @@ def test_benchmarked_presets_full_frame_against_oracle(name):
     assert img.shape == ref.shape and img.shape[-1] in (1280, 1920)
     assert max_rel(img.cpu(), ref) < REL
     assert orc.psnr(img.cpu(), ref) > 60.0
+
+
+@pytest.mark.parametrize("model", ["HNeRV_Boost", "NeRV_Boost"])
+def test_decode_to_host_pipeline_is_bitwise_the_per_frame_api(model):
+    """bnerv_b200.decode_to_host (H2D -> graph replay -> overlapped D2H) returns exactly what forward()/forward_decoder()
+    returns frame by frame, for ragged batches and more frames than staging slots."""
+    from bnerv_b200 import decode_to_host
+    torch.manual_seed(2)
+    m, a = _build(model)
+    m = m.cuda()
+    n = 7
+    fh, fw = [int(v) for v in a.fc_hw.split("_")]
+    t = torch.tensor([(i + 1) / n for i in range(n)], dtype=torch.float64).pin_memory()
+    emb = torch.rand(n, 16, fh, fw).pin_memory() if model == "HNeRV_Boost" else None
+    with torch.no_grad():
+        ref = torch.cat([(m.forward_decoder(emb[i:i + 1].cuda(), t[i:i + 1].cuda()) if emb is not None else m(t[i:i + 1].cuda()))[0].cpu()
+                         for i in range(n)])
+    for batch, depth in ((1, 3), (2, 2), (3, 1)):
+        out = torch.full(ref.shape, float("nan")).pin_memory()
+        decode_to_host(m, t, out, emb, batch=batch, depth=depth)
+        if batch == 1:
+            assert torch.equal(out, ref)
+        else:                                   # batched launches tile the same pixels identically
+            assert torch.equal(out, ref)
+    with pytest.raises(ValueError):
+        decode_to_host(m, t.cuda(), out, emb)
