@@ -65,8 +65,8 @@ def _load():
     lib.bnerv_bias_finalize.argtypes = [vp, i, i, vp, i, vp, vp]
     lib.bnerv_channel_sum.argtypes = [vp, i, i, i, i, i, vp, vp]
     lib.bnerv_resblock_mid_bwd.argtypes = [vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
-    lib.bnerv_block_front_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
-    lib.bnerv_unshuffle_c8.argtypes = [vp, i, i, i, i, i, vp, vp]
+    lib.bnerv_block_front_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp, vp]
+    lib.bnerv_unshuffle_c8.argtypes = [vp, i, i, i, i, i, vp, vp, vp]
     lib.bnerv_conv_fused_f32.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp, i, vp, vp, vp]
     lib.bnerv_sft_affine.argtypes = [vp, i, vp, i, i, vp]
     lib.bnerv_linear_act.argtypes = [vp, i, i, vp, vp, i, i, vp, vp]

@@ -4,6 +4,7 @@ torch is used for device memory and the current stream only; every computation b
 libbnerv_b200.so.  All functions raise on CPU tensors — there is no fallback.
 """
 import ctypes
+import os
 
 import torch
 
@@ -304,35 +305,39 @@ def resblock_mid_bwd(dw, v, dact, g1p, C):
     B, G, H, W, _ = dw.shape
     dev = dw.device
     dc0 = torch.empty_like(dw)
-    dG = torch.zeros((B, G * 8), dtype=torch.float32, device=dev)
-    dB = torch.zeros((B, G * 8), dtype=torch.float32, device=dev)
-    db = torch.zeros(G * 8, dtype=torch.float32, device=dev)
+    red = torch.zeros((2 * B + 1, G * 8), dtype=torch.float32, device=dev)
+    dG, dB, db = red[:B], red[B:2 * B], red[2 * B]
     check("bnerv_resblock_mid_bwd", lib.bnerv_resblock_mid_bwd(ptr(dw), ptr(v), ptr(dact), ptr(g1p), B, C, H, W, ptr(dc0),
                                                                ptr(dG), ptr(dB), ptr(db), _stream()))
     return dc0, dG, dB, db
 
 
-def block_front_bwd(du, dout, x0, dact, g0p, C):
-    """-> (dy C8 at the block's output resolution, dG, dB, dbias1)."""
+def block_front_bwd(du, dout, x0, dact, g0p, C, want_dy_sums=False):
+    """-> (dy C8 at the block's output resolution, dG, dB, dbias1, channel sums of dy or None)."""
     B, G, H, W, _ = du.shape
     dev = du.device
     dy = torch.empty_like(du)
-    dG = torch.zeros((B, G * 8), dtype=torch.float32, device=dev)
-    dB = torch.zeros((B, G * 8), dtype=torch.float32, device=dev)
-    db = torch.zeros(G * 8, dtype=torch.float32, device=dev)
+    red = torch.zeros((2 * B + 2, G * 8), dtype=torch.float32, device=dev)       # one memset: dG | dB | dbias1 | dy sums
+    dG, dB, db, dsum = red[:B], red[B:2 * B], red[2 * B], red[2 * B + 1]
     check("bnerv_block_front_bwd", lib.bnerv_block_front_bwd(ptr(du), ptr(dout), ptr(x0), ptr(dact), ptr(g0p), B, C, H, W,
-                                                             ptr(dy), ptr(dG), ptr(dB), ptr(db), _stream()))
-    return dy, dG, dB, db
+                                                             ptr(dy), ptr(dG), ptr(dB), ptr(db),
+                                                             ptr(dsum) if want_dy_sums else None, _stream()))
+    return dy, dG, dB, db, (dsum if want_dy_sums else None)
 
 
-def unshuffle_c8(src, C, s):
-    """PixelShuffle(s) transposed: [B][Cp/8][H*s][W*s][8] -> [B][s*s*Cp/8][H][W][8]."""
+def unshuffle_c8(src, C, s, want_sums=False):
+    """PixelShuffle(s) transposed: [B][Cp/8][H*s][W*s][8] -> [B][s*s*Cp/8][H][W][8].
+    want_sums: also return the channel sums of the result (f32 [s*s*Cp]) from the same pass (s = 2, 3) or a second one."""
     if s == 1:
-        return src
+        return (src, channel_sum(src)) if want_sums else src
     B, G, Hs, Ws, _ = src.shape
     H, W = Hs // s, Ws // s
     dst = torch.empty((B, s * s * G, H, W, 8), dtype=torch.float16, device=src.device)
-    check("bnerv_unshuffle_c8", lib.bnerv_unshuffle_c8(ptr(src), B, C, H, W, s, ptr(dst), _stream()))
+    fused = want_sums and s in (2, 3) and not os.environ.get("BNERV_NO_FUSED_SUMS")
+    sums = torch.zeros(s * s * G * 8, dtype=torch.float32, device=src.device) if fused else None
+    check("bnerv_unshuffle_c8", lib.bnerv_unshuffle_c8(ptr(src), B, C, H, W, s, ptr(dst), ptr(sums), _stream()))
+    if want_sums:
+        return dst, (sums if fused else channel_sum(dst))
     return dst
 
 

@@ -211,7 +211,8 @@ def _backward_body(eng, lay, st, dimg, need_x, force):
         param_grads(blk.c0, rec["u"], dc0, inv, dbias_acc=db0)
         du = _dgrad(blk.c0, dc0, Ho, Wo, force)
         del dc0
-        dy, dG0, dB0, db1 = ops.block_front_bwd(du, dout, rec["x0"], rec["d0"], rec["g0p"], Cb)
+        dy, dG0, dB0, db1, dy_sums = ops.block_front_bwd(du, dout, rec["x0"], rec["d0"], rec["g0p"], Cb,
+                                                         want_dy_sums=(blk.up.s == 1))
         del du, dout
         if gb1 is not None:
             ops.bias_finalize(db1, Cb, 1, inv, out=gb1)
@@ -220,16 +221,19 @@ def _backward_body(eng, lay, st, dimg, need_x, force):
         # up-conv (input: block input or the E-NeRV pre-conv's output)
         up_in = rec.get("mid", rec["in"])
         Hi, Wi = rec.get("mid_hw", rec["in_hw"])
-        dyu = ops.unshuffle_c8(dy, Cb, blk.up.s)
+        if blk.up.s == 1:
+            dyu = dy
+        else:                                    # un-shuffle and the up-conv's bias sums in one pass
+            dyu, dy_sums = ops.unshuffle_c8(dy, Cb, blk.up.s, want_sums=True)
         del dy
-        param_grads(blk.up, up_in, dyu, inv)
+        param_grads(blk.up, up_in, dyu, inv, dbias_acc=dy_sums)
         first_conv = bi == 0 and blk.pre is None
         dprev = _dgrad(blk.up, dyu, Hi, Wi, force) if (not first_conv or need_x) else None
         del dyu
         if blk.pre is not None:
             Hi0, Wi0 = rec["in_hw"]
-            dmu = ops.unshuffle_c8(dprev, blk.pre.cout, blk.pre.s)
-            param_grads(blk.pre, rec["in"], dmu, inv)
+            dmu, dm_sums = ops.unshuffle_c8(dprev, blk.pre.cout, blk.pre.s, want_sums=True)
+            param_grads(blk.pre, rec["in"], dmu, inv, dbias_acc=dm_sums)
             dprev = _dgrad(blk.pre, dmu, Hi0, Wi0, force) if (bi > 0 or need_x) else None
         dout = dprev
     gx = ops.c8_to_nchw(dout, C) * inv if need_x else None

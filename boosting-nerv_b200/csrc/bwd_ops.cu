@@ -158,15 +158,15 @@ __global__ void mid_bwd_kernel(const __half* __restrict__ dw, const __half* __re
 __global__ void front_bwd_kernel(const __half* __restrict__ du, const __half* __restrict__ dout, const __half* __restrict__ x0,
                                  const __half* __restrict__ dact, const float* __restrict__ g0p, int cp, size_t hw,
                                  __half* __restrict__ dy, float* __restrict__ dG, float* __restrict__ dB,
-                                 float* __restrict__ dbias1) {
+                                 float* __restrict__ dbias1, float* __restrict__ dbias_up) {
     const int g = blockIdx.y, b = blockIdx.z;
     const size_t base = (static_cast<size_t>(b) * (cp >> 3) + g) * hw;
     float gg[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) gg[k] = g0p[static_cast<size_t>(b) * cp + g * 8 + k];
-    float acc[24];
+    float acc[32];
 #pragma unroll
-    for (int k = 0; k < 24; ++k) acc[k] = 0.0f;
+    for (int k = 0; k < 32; ++k) acc[k] = 0.0f;
     for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < hw; p += static_cast<size_t>(gridDim.x) * blockDim.x) {
         float a[8], e[8], xx[8], d[8], o[8];
         unpack8(reinterpret_cast<const uint4*>(du)[base + p], a);
@@ -179,16 +179,20 @@ __global__ void front_bwd_kernel(const __half* __restrict__ du, const __half* __
             acc[k] += a[k] * xx[k];
             acc[8 + k] += a[k];
             acc[16 + k] += e[k];
+            acc[24 + k] += o[k];
         }
         reinterpret_cast<uint4*>(dy)[base + p] = pack8f(o);
     }
     float* const pG = dG + static_cast<size_t>(b) * cp + g * 8;
     float* const pB = dB + static_cast<size_t>(b) * cp + g * 8;
     float* const pb = dbias1 + g * 8;
-    float* const dst[24] = {pG, pG + 1, pG + 2, pG + 3, pG + 4, pG + 5, pG + 6, pG + 7,
+    float* const pu = dbias_up ? dbias_up + g * 8 : nullptr;       // s == 1 up-conv: its bias gradient is the channel sum of dy
+    float* const dst[32] = {pG, pG + 1, pG + 2, pG + 3, pG + 4, pG + 5, pG + 6, pG + 7,
                             pB, pB + 1, pB + 2, pB + 3, pB + 4, pB + 5, pB + 6, pB + 7,
-                            pb, pb + 1, pb + 2, pb + 3, pb + 4, pb + 5, pb + 6, pb + 7};
-    block_reduce_atomic<24>(acc, dst);
+                            pb, pb + 1, pb + 2, pb + 3, pb + 4, pb + 5, pb + 6, pb + 7,
+                            pu, pu ? pu + 1 : pu, pu ? pu + 2 : pu, pu ? pu + 3 : pu, pu ? pu + 4 : pu, pu ? pu + 5 : pu,
+                            pu ? pu + 6 : pu, pu ? pu + 7 : pu};
+    block_reduce_atomic<32>(acc, dst);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -211,6 +215,43 @@ __global__ void unshuffle_c8_kernel(const uint4* __restrict__ src, int B, int cp
         const int i = ij / s, j = ij - i * s;
         dst[idx] = src[((static_cast<size_t>(b) * g8 + g) * (static_cast<size_t>(H) * s) + (h * s + i)) * Wo + (w * s + j)];
     }
+}
+
+// Same permutation with a thread per LOW-resolution pixel: the s x s source chunks of one pixel are s runs of s*16
+// contiguous bytes (coalesced across neighbouring pixels), every destination plane is written densely, and the channel
+// sums of the un-shuffled map (= the up-conv's bias gradient) come out of the same pass.  grid (chunks, Cp/8, B).
+template <int S>
+__global__ void unshuffle_sum_kernel(const uint4* __restrict__ src, int cp, int H, int W, uint4* __restrict__ dst,
+                                     float* __restrict__ sums) {
+    const int g = blockIdx.y, b = blockIdx.z, g8 = cp >> 3;
+    const size_t hw = static_cast<size_t>(H) * W;
+    const int Wo = W * S;
+    const uint4* sp = src + (static_cast<size_t>(b) * g8 + g) * hw * S * S;
+    float acc[S * S * 8];
+#pragma unroll
+    for (int k = 0; k < S * S * 8; ++k) acc[k] = 0.0f;
+    for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < hw; p += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int h = static_cast<int>(p / W), w = static_cast<int>(p - static_cast<size_t>(h) * W);
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const uint4 v = sp[static_cast<size_t>(h * S + i) * Wo + (w * S + j)];
+                dst[(static_cast<size_t>(b) * S * S * g8 + (i * S + j) * g8 + g) * hw + p] = v;
+                float f[8];
+                unpack8(v, f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[(i * S + j) * 8 + k] += f[k];
+            }
+        }
+    }
+    float* dptr[S * S * 8];
+#pragma unroll
+    for (int ij = 0; ij < S * S; ++ij)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dptr[ij * 8 + k] = sums + ij * cp + g * 8 + k;
+    float* const (&dref)[S * S * 8] = dptr;
+    block_reduce_atomic<S * S * 8>(acc, dref);
 }
 
 // packed weight of the dgrad conv (see bnerv_pack_conv_weight_dgrad)
@@ -349,21 +390,36 @@ extern "C" int bnerv_resblock_mid_bwd(const void* dw, const void* v, const void*
 }
 
 extern "C" int bnerv_block_front_bwd(const void* du, const void* dout, const void* x0, const void* dact, const float* g0p,
-                                     int B, int C, int H, int W, void* dy, float* dG, float* dB, float* dbias1, void* stream) {
+                                     int B, int C, int H, int W, void* dy, float* dG, float* dB, float* dbias1,
+                                     float* dbias_up, void* stream) {
     if (!du || !dout || !x0 || !dact || !g0p || !dy || !dG || !dB || !dbias1) return set_error(BNERV_E_BADARG, "block_front_bwd: null pointer");
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return set_error(BNERV_E_BADARG, "block_front_bwd: non-positive size");
     const int cp = round_up(C, 16);
     const size_t hw = static_cast<size_t>(H) * W;
     front_bwd_kernel<<<grid_planes(B, cp, hw), BW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __half*>(du), static_cast<const __half*>(dout), static_cast<const __half*>(x0),
-        static_cast<const __half*>(dact), g0p, cp, hw, static_cast<__half*>(dy), dG, dB, dbias1);
+        static_cast<const __half*>(dact), g0p, cp, hw, static_cast<__half*>(dy), dG, dB, dbias1, dbias_up);
     return check_launch("front_bwd_kernel");
 }
 
-extern "C" int bnerv_unshuffle_c8(const void* src, int B, int C, int H, int W, int s, void* dst, void* stream) {
+extern "C" int bnerv_unshuffle_c8(const void* src, int B, int C, int H, int W, int s, void* dst, float* sums, void* stream) {
     if (!src || !dst) return set_error(BNERV_E_BADARG, "unshuffle_c8: null pointer");
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || s <= 0) return set_error(BNERV_E_BADARG, "unshuffle_c8: non-positive size");
     const int cp = round_up(C, 16);
+    if (sums != nullptr) {
+        const size_t hw = static_cast<size_t>(H) * W;
+        const dim3 grid = grid_planes(B, cp, hw);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (s == 2) {
+            unshuffle_sum_kernel<2><<<grid, BW_THREADS, 0, st>>>(static_cast<const uint4*>(src), cp, H, W, static_cast<uint4*>(dst), sums);
+            return check_launch("unshuffle_sum_kernel<2>");
+        }
+        if (s == 3) {
+            unshuffle_sum_kernel<3><<<grid, BW_THREADS, 0, st>>>(static_cast<const uint4*>(src), cp, H, W, static_cast<uint4*>(dst), sums);
+            return check_launch("unshuffle_sum_kernel<3>");
+        }
+        return set_error(BNERV_E_UNSUPPORTED, "unshuffle_c8: fused channel sums only for s = 2, 3 (got %d); pass sums = NULL and use bnerv_channel_sum", s);
+    }
     const size_t total = static_cast<size_t>(B) * s * s * (cp / 8) * H * W;
     unshuffle_c8_kernel<<<grid_1d(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint4*>(src), B, cp, H, W, s, static_cast<uint4*>(dst));

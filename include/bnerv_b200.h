@@ -207,12 +207,15 @@ int bnerv_resblock_mid_bwd(const void* dw, const void* v, const void* dact, cons
 /* NeRVBlock front transposed (model_blocks.py:37,85,89; forward x0 = act(y), u = x0*g0p + beta0, out = x0 + conv1(..)):
  *   dy = (dout + du*g0p) * dact;  dG[b][c] += sum du*x0;  dB[b][c] += sum du;  dbias1[c] += sum dout
  *   (dout is also dL/d conv1-output, hence conv1's bias gradient).  dy is at the block's output resolution;
- *   bnerv_unshuffle_c8 turns it into the up-conv's gradient map when s > 1. */
+ *   bnerv_unshuffle_c8 turns it into the up-conv's gradient map when s > 1.  dbias_up (f32 [Cp], may be NULL):
+ *   += sum dy, the up-conv's bias gradient when it has no PixelShuffle (s = 1). */
 int bnerv_block_front_bwd(const void* du, const void* dout, const void* x0, const void* dact, const float* g0p,
-                          int B, int C, int H, int W, void* dy, float* dG, float* dB, float* dbias1, void* stream);
+                          int B, int C, int H, int W, void* dy, float* dG, float* dB, float* dbias1, float* dbias_up,
+                          void* stream);
 
-/* PixelShuffle(s) transposed on C8 maps: src [B][Cp/8][H*s][W*s][8] -> dst [B][s*s*Cp/8][H][W][8] (un-shuffled order). */
-int bnerv_unshuffle_c8(const void* src, int B, int C, int H, int W, int s, void* dst, void* stream);
+/* PixelShuffle(s) transposed on C8 maps: src [B][Cp/8][H*s][W*s][8] -> dst [B][s*s*Cp/8][H][W][8] (un-shuffled order).
+ * sums (f32 [s*s*Cp], may be NULL; s = 2, 3 only): += channel sums of dst = the up-conv's un-shuffled bias gradient. */
+int bnerv_unshuffle_c8(const void* src, int B, int C, int H, int W, int s, void* dst, float* sums, void* stream);
 
 /* Per-frame error metrics on the device (hnerv_utils.py:338-341 'L2'/'L1' pixel losses and
  * psnr_fn_single :400-403) without the reference's per-step .cpu() synchronisation:

@@ -74,6 +74,9 @@ def test_dgrad_and_unshuffle_match_autograd(B, cin, cout, H, W, k, s):
     y.backward(dy)
     un = ops.unshuffle_c8(ops.nchw_to_c8(dy), cout, s)
     assert torch.equal(un, ops.nchw_to_c8(_unshuffle_ref(dy, s)))     # pure index permutation: bit-exact
+    un2, sums = ops.unshuffle_c8(ops.nchw_to_c8(dy), cout, s, want_sums=True)     # fused pass (s = 2, 3) or two passes
+    assert torch.equal(un2, un)
+    assert max_rel(sums, _unshuffle_ref(dy, s).sum((0, 2, 3))) < 1e-5
     pd = ops.PackedDgrad(w, s)
     dx = torch.empty(ops.c8_shape(B, cin, H, W), dtype=torch.float16, device="cuda")
     ops.conv_fused(un, pd, pd.cin, H, W, act="none", out_pre=dx)
@@ -115,7 +118,10 @@ def test_elementwise_transposes_and_reductions():
     g[:, :C] = 1 + 0.3 * torch.randn(B, C, device="cuda")
     gb = g[:, :C, None, None]
     c8 = ops.nchw_to_c8
-    dy, dG, dB, db1 = ops.block_front_bwd(c8(du), c8(dout), c8(x0), c8(dact), g, C)
+    dy, dG, dB, db1, none = ops.block_front_bwd(c8(du), c8(dout), c8(x0), c8(dact), g, C)
+    assert none is None
+    dy2, _, _, _, dsum = ops.block_front_bwd(c8(du), c8(dout), c8(x0), c8(dact), g, C, want_dy_sums=True)
+    assert torch.equal(dy, dy2) and max_rel(dsum[:C], ((dout + du * gb) * dact).sum((0, 2, 3))) < 1e-5
     assert max_rel(ops.c8_to_nchw(dy, C), (dout + du * gb) * dact) < 6e-4
     assert max_rel(dG[:, :C], (du * x0).sum((2, 3))) < 1e-5 and max_rel(dB[:, :C], du.sum((2, 3))) < 1e-5
     assert max_rel(db1[:C], dout.sum((0, 2, 3))) < 1e-5
@@ -240,3 +246,36 @@ def test_native_training_refuses_cpu_fallback_semantics():
     m.train_backend = "bogus"
     with pytest.raises(ValueError):
         m(t)
+
+
+def test_quant_aware_style_training_through_dequant_weights_runs_eagerly_and_reaches_the_leaf():
+    """train_nerv_compression.py re-creates dequant_w / dequant_b from the parameters every step (cal_params,
+    model_nerv.py:67-78): the effective weights are then non-leaf tensors without stable storage, so the cascade must
+    take the eager Function (no captured graph) and the gradient must flow through them to `weight` / `bias`."""
+    from bnerv_b200.layers import CustomConv2d
+    m, a = _build("HNeRV_Boost")
+    fh, fw = [int(v) for v in a.fc_hw.split("_")]
+    t = torch.tensor([0.25, 0.75], dtype=torch.float64, device="cuda")
+    emb = torch.rand(2, 16, fh, fw, device="cuda")
+    target = torch.rand(2, 3, fh * 20, fw * 20, device="cuda")
+    convs = [mod for mod in m.modules() if isinstance(mod, CustomConv2d)]
+
+    def fake_cal_params():
+        for c in convs:                          # a differentiable "quantiser": scale by a power of two and back, plus STE-like identity
+            c.dequant_w = (c.weight * 4.0) * 0.25
+            c.dequant_b = None if c.bias is None else (c.bias * 2.0) * 0.5
+
+    res = {}
+    for mode in ("torch", "b200"):
+        m.train_backend = mode
+        m.zero_grad(set_to_none=True)
+        fake_cal_params()
+        _, _, loss = _loss(m, "HNeRV_Boost", t, emb, target)
+        loss.backward()
+        res[mode] = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    assert not getattr(m.engine(), "_train_graphs", {})            # nothing was captured for non-leaf weights
+    assert set(res["b200"]) == set(res["torch"])
+    for n in res["torch"]:
+        assert max_rel(res["b200"][n], res["torch"][n]) < 1e-2, n
+    for c in convs:
+        c.dequant_w, c.dequant_b = None, None

@@ -108,7 +108,7 @@ def case_elementwise(B=2, C=21, H=18, W=30):
     du, dout, x0, dact, dw, v = mk(), mk(), mk(), mk(), mk(), mk()
     g = torch.zeros(B, cp, device=dev); g[:, :C] = 1 + 0.3 * torch.randn(B, C, device=dev)
     c8 = ops.nchw_to_c8
-    dy, dG, dB, db1 = ops.block_front_bwd(c8(du), c8(dout), c8(x0), c8(dact), g, C)
+    dy, dG, dB, db1, _ = ops.block_front_bwd(c8(du), c8(dout), c8(x0), c8(dact), g, C)
     gb = g[:, :C, None, None]
     e = [rel(ops.c8_to_nchw(dy, C), (dout + du * gb) * dact), rel(dG[:, :C], (du * x0).sum((2, 3))), rel(dB[:, :C], du.sum((2, 3))),
          rel(db1[:C], dout.sum((0, 2, 3)))]

@@ -95,7 +95,7 @@ g = torch.ones(1, ops.round_up(cout, 16), device=dev)
 ms = timed(lambda: ops.resblock_mid_bwd(dy, dy, dy, g, cout), 10)
 nbytes = 4 * dy.numel() * 2
 print(f"mid_bwd   @{H}x{W}x{cout}: {ms:.3f} ms  {nbytes / ms / 1e6:.0f} GB/s (3 maps read, 1 written)")
-ms = timed(lambda: ops.block_front_bwd(dy, dy, dy, dy, g, cout), 10)
+ms = timed(lambda: ops.block_front_bwd(dy, dy, dy, dy, g, cout, want_dy_sums=True), 10)
 nbytes = 5 * dy.numel() * 2
 print(f"front_bwd @{H}x{W}x{cout}: {ms:.3f} ms  {nbytes / ms / 1e6:.0f} GB/s (4 maps read, 1 written)")
 ms = timed(lambda: ops.channel_sum(dy), 10)
