@@ -167,7 +167,9 @@ def run_reference(opt):
         fn(opt.warmup + i)
     dt = time.perf_counter() - t0
     fps = opt.steps * frac / dt
-    sample = f"{opt.steps} steps, each a {crop[0]}x{crop[1]} crop of the 9x16 stem grid = {frac:.3f} of a 1080p frame (fully convolutional decoder)"
+    fh_, fw_ = [int(v) for v in args.fc_hw.split("_")]
+    sample = (f"{opt.steps} steps, each a {crop[0]}x{crop[1]} crop of the {fh_}x{fw_} stem grid = {frac:.3f} of a frame "
+              "(fully convolutional decoder), oracle port of the reference forward (torch CPU f32, oneDNN)")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": opt.gpus, "steps": opt.steps,
             "warmup": opt.warmup, "ms_per_step": dt / opt.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -178,8 +180,12 @@ def run_reference(opt):
 
 
 def workload_name(cfg_name, args):
-    hw = {"hnerv_l": "1080x1920", "hnerv_m": "1080x1920", "enerv_m": "1080x1920"}.get(cfg_name, "720x1280")
-    return f"{args.model} {cfg_name} (modelsize {args.modelsize}, fc_dim {args.fc_dim}) decode @{hw}, {N_FRAMES}-frame synthetic sequence"
+    fh, fw = [int(v) for v in args.fc_hw.split("_")]
+    up = 1
+    for s_ in args.dec_strds:
+        up *= s_
+    return (f"{args.model} {cfg_name} (modelsize {args.modelsize}, fc_dim {args.fc_dim}) decode @{fh * up}x{fw * up}, "
+            f"{N_FRAMES}-frame synthetic sequence")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -378,7 +384,7 @@ def run_b200(opt):
             fn(1 + i)
             ts.append(time.perf_counter() - t0)
         line["cpu_baseline"] = {"value": frac / statistics.median(ts), "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"median of 2 decodes (1 warm-up) of a {crop[0]}x{crop[1]} crop of the 9x16 stem grid = {frac:.3f} of a frame, oracle port (torch CPU f32, oneDNN)"}
+                                "sample": f"median of 2 decodes (1 warm-up) of a {crop[0]}x{crop[1]} crop of the {fh}x{fw} stem grid = {frac:.3f} of a frame, oracle port (torch CPU f32, oneDNN)"}
     if world == 1 and not opt.no_train:
         # extra, outside the metric: one training step (forward + MSE + backward, batch 1) of the same workload on the
         # native backward kernels vs torch autograd with cuDNN TF32 allowed (the reference's default GPU arithmetic)

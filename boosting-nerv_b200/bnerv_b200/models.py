@@ -84,7 +84,7 @@ class _BoostBase(nn.Module):
         if self.backend != "b200":
             raise ValueError(f"unknown backend {self.backend!r}")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            return False            # training: autograd through torch ops
+            return False            # training: the forward() bodies go on to _use_native_train
         if not ref_tensor.is_cuda:
             raise RuntimeError("bnerv_b200: the decode path runs only on a CUDA (sm_100a) device; got a CPU tensor. "
                                "Set model.backend = 'torch' explicitly for the plain-torch debugging path.")
@@ -96,7 +96,10 @@ class _BoostBase(nn.Module):
             return False
         if self.train_backend != "b200":
             raise ValueError(f"unknown train_backend {self.train_backend!r}")
-        return ref_tensor.is_cuda and torch.is_grad_enabled()
+        if not ref_tensor.is_cuda:
+            raise RuntimeError("bnerv_b200: native training runs only on a CUDA (sm_100a) device; got a CPU tensor.  Set "
+                               "model.train_backend = 'torch' (or model.backend = 'torch') explicitly for torch autograd.")
+        return torch.is_grad_enabled()
 
     def _cascade_train(self, x, cond):
         from .train import cascade_train

@@ -233,6 +233,11 @@ def test_short_fit_tracks_torch_and_trained_weights_decode_parity():
                 m.backend = "torch"
                 ref = m.forward_decoder(emb, t)[0]
             assert max_rel(nat, ref) < 1e-3
+            # north_star: PSNR against the ground-truth frames within 0.01 dB of the fp32 forward (hnerv_utils.py:400-403)
+            psnr = lambda o: (-10 * torch.log10(((o - target) ** 2).flatten(1).mean(1) + 1e-9))
+            assert (psnr(nat) - psnr(ref)).abs().max().item() < 0.01
+            from bnerv_b200 import ops
+            assert (ops.frame_metrics(nat, target)[:, 2] - psnr(nat)).abs().max().item() < 1e-3      # device-side metric agrees
     lt, ln = final["torch"], final["b200"]
     assert ln[-1] < 0.25 * ln[0]                                   # it learns
     assert abs(ln[10] - lt[10]) < 0.02 * lt[10]                    # early trajectory identical to 2 %

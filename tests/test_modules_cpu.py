@@ -70,10 +70,17 @@ def test_b200_backend_refuses_cpu_tensors():
     m = _build("NeRV_Boost").eval()
     with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU|CUDA"):
         m(torch.tensor([0.5], dtype=torch.float64))
+    m.train()
+    with pytest.raises(RuntimeError, match="CUDA"):            # no silent CPU fallback under autograd either
+        m(torch.tensor([0.5], dtype=torch.float64))
+    m.train_backend = "bogus"
+    with pytest.raises(ValueError):
+        m(torch.tensor([0.5], dtype=torch.float64))
 
 
 def test_training_mode_uses_autograd_path_and_deepcopy_is_clean():
     m = _build("NeRV_Boost")
+    m.train_backend = "torch"                                  # explicit opt-out: plain torch autograd (runs on CPU)
     img, _, _ = m(torch.tensor([0.5], dtype=torch.float64))
     img.mean().backward()
     assert m.head_layer.weight.grad is not None
