@@ -12,6 +12,12 @@
 // (8 rows x 16 px; one UMMA M=128,N=Nc,K=16 per tile row and tap), then adds the partial sums into the f32
 // accumulation buffer with vector reductions (red.global.add.v4.f32).  Jobs are equal-cost, CTA c takes job c % J.
 //
+// Narrow layers (3*Cin_p <= 256, i.e. Cin <= 80: every NeRV-S / E-NeRV-M stage above 135p): an N = Cin_p UMMA costs
+// the same ~45 issue cycles as a wide one, so the three column taps of a kernel row are STACKED IN N: the X tile is
+// loaded three times at px offsets -1, 0, +1 into consecutive channel-group planes ("replicas"), which keeps the
+// MN-major group stride uniform, and one UMMA (N = 3*Cin_p) does what three did.  When 9*Cin_p <= 512 TMEM columns
+// (Cin <= 48) all three kernel rows live in one job, so dY is fetched once instead of three times.
+//
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
 #include <cuda.h>
 #include <cstdlib>
@@ -42,6 +48,12 @@ struct WgradArgs {
     int stages;
     int dy_bytes, x_bytes, stage_bytes;
     int swap_lbo_sbo;    // debugging switch (BNERV_WGRAD_SWAP)
+    int stack;           // 1: column taps stacked in N through replicated X planes
+    int rows_per_job;    // kernel rows handled inside one job (3 in stacked mode when 9*Cin_p <= 512, else 1)
+    int reps;            // X replicas per stage (stacked: 3 * rows_per_job)
+    int rep_bytes;       // bytes of one replica
+    int n_mma;           // UMMA N
+    int tap_cols;        // accumulator columns per tap
     float* acc;          // [taps][M_p][Cin_p] f32, accumulated into
 };
 
@@ -125,8 +137,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                     const uint32_t dst = s_base + stage * a.stage_bytes;
                     mbar_expect_tx(full + stage * 8, static_cast<uint32_t>(a.dy_bytes + a.x_bytes));
                     tma_load_3d(dst, &tmDY, full + stage * 8, 2 * w0, h0, b * a.m_groups + j.m_blk * 16);
-                    tma_load_3d(dst + a.dy_bytes, &tmX, full + stage * 8, 2 * (w0 - a.pad), h0 + j.r - a.pad,
-                                b * a.c_groups + j.c_chunk * (a.nc >> 3));
+                    if (a.stack) {
+                        for (int rp = 0; rp < a.reps; ++rp) {
+                            const int rr = (a.rows_per_job == 3) ? rp / 3 : j.r, sx = rp % 3;
+                            tma_load_3d(dst + a.dy_bytes + rp * a.rep_bytes, &tmX, full + stage * 8, 2 * (w0 + sx - 1), h0 + rr - 1,
+                                        b * a.c_groups);
+                        }
+                    } else {
+                        tma_load_3d(dst + a.dy_bytes, &tmX, full + stage * 8, 2 * (w0 - a.pad), h0 + j.r - a.pad,
+                                    b * a.c_groups + j.c_chunk * (a.nc >> 3));
+                    }
                 }
                 __syncwarp();
                 if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -136,8 +156,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         // ===================== MMA issuer =====================
         int stage = 0;
         uint32_t phase = 0, jphase = 0;
-        const uint32_t idesc = umma_idesc_f16(128, a.nc) | (1u << 15) | (1u << 16);      // A and B MN-major
-        const int xw = WG_TILE_W + 2 * a.pad;                                             // X tile row length (px)
+        const uint32_t idesc = umma_idesc_f16(128, a.n_mma) | (1u << 15) | (1u << 16);   // A and B MN-major
+        const int xw = a.stack ? WG_TILE_W : WG_TILE_W + 2 * a.pad;                       // X tile row length (px)
+        const int n_grp = a.stack ? a.rows_per_job : a.T;                                 // UMMAs per tile row
+        const uint32_t grp16 = a.stack ? 3u * (static_cast<uint32_t>(a.rep_bytes) >> 4) : 1u;   // B start step between them (16 B units)
         const uint64_t a_hi = desc_hi_mn(128u, static_cast<uint32_t>(a.R) * WG_TILE_W * 16u, a.swap_lbo_sbo);
         const uint64_t b_hi = desc_hi_mn(128u, static_cast<uint32_t>(a.R) * xw * 16u, a.swap_lbo_sbo);
         for (int jj = blockIdx.x; jj < jj_end; jj += gridDim.x) {
@@ -153,9 +175,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                     const uint32_t sx16  = sdy16 + (static_cast<uint32_t>(a.dy_bytes) >> 4);
                     for (int y = 0; y < a.R; ++y) {
                         const uint64_t adesc = a_hi | static_cast<uint64_t>(sdy16 + y * WG_TILE_W);
-                        for (int s = 0; s < a.T; ++s) {
-                            const uint64_t bdesc = b_hi | static_cast<uint64_t>(sx16 + y * xw + s);
-                            umma_f16(tmem_base + s * a.nc, adesc, bdesc, idesc, (t > j.t0 || y > 0) ? 1u : 0u);
+                        for (int s = 0; s < n_grp; ++s) {
+                            const uint64_t bdesc = b_hi | static_cast<uint64_t>(sx16 + y * xw + s * grp16);
+                            umma_f16(tmem_base + s * a.n_mma, adesc, bdesc, idesc, (t > j.t0 || y > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(empty + stage * 8);
@@ -179,12 +201,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             const int mch = j.m_blk * 128 + m;
             const int c0 = j.c_chunk * a.nc;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-            for (int s = 0; s < a.T; ++s) {
-                const int tap = (a.taps == 1) ? 0 : j.r * 3 + s;
+            const int n_taps_job = a.stack ? 3 * a.rows_per_job : a.T;      // tap blocks of tap_cols columns each
+            for (int s = 0; s < n_taps_job; ++s) {
+                const int tap = (a.taps == 1) ? 0 : ((a.stack && a.rows_per_job == 3) ? s : j.r * 3 + s);
                 float* row = a.acc + (static_cast<size_t>(tap) * a.m_p + mch) * a.cin_p + c0;
-                for (int g = 0; g < a.nc; g += 16) {
+                for (int g = 0; g < a.tap_cols; g += 16) {
                     uint32_t v[16];
-                    tmem_ld16(taddr + s * a.nc + g, v);          // warp-collective: every lane takes part
+                    tmem_ld16(taddr + s * a.tap_cols + g, v);    // warp-collective: every lane takes part
                     tmem_ld_wait();
                     if (mch < a.m_p && c0 + g < a.cin_p) {
 #pragma unroll
@@ -281,13 +304,29 @@ extern "C" int bnerv_conv_wgrad(const void* x, const void* dy, int B, int Cin, i
     a.c_chunks = (a.cin_p + nc_max - 1) / nc_max;
     a.nc = round_up((a.cin_p + a.c_chunks - 1) / a.c_chunks, 16);
     a.m_blocks = (M_p + 127) / 128;
+    static const bool no_stack = getenv("BNERV_WGRAD_NO_STACK") != nullptr;      // A/B switch
+    a.stack = (k == 3 && 3 * a.cin_p <= 256 && !no_stack) ? 1 : 0;
+    a.rows_per_job = 1;
+    a.n_mma = a.nc;
+    a.tap_cols = a.nc;
+    a.reps = 1;
+    if (a.stack) {
+        a.c_chunks = 1;
+        a.nc = a.cin_p;
+        a.rows_per_job = (9 * a.cin_p <= 512) ? 3 : 1;
+        a.r_jobs = (a.rows_per_job == 3) ? 1 : 3;
+        a.reps = 3 * a.rows_per_job;
+        a.n_mma = 3 * a.cin_p;
+        a.tap_cols = a.cin_p;
+    }
     a.jobs = a.m_blocks * a.c_chunks * a.r_jobs;
-    const int xw = WG_TILE_W + 2 * a.pad;
+    const int xw = a.stack ? WG_TILE_W : WG_TILE_W + 2 * a.pad;
     // rows per tile: 8 when at least 3 stages fit, else 4
     a.R = 8;
     for (;;) {
         a.dy_bytes = 16 * a.R * WG_TILE_W * 16;
-        a.x_bytes = (a.nc / 8) * a.R * xw * 16;
+        a.rep_bytes = (a.nc / 8) * a.R * xw * 16;
+        a.x_bytes = a.reps * a.rep_bytes;
         a.stage_bytes = a.dy_bytes + a.x_bytes;
         a.stages = (WG_SMEM_LIMIT - WG_BAR_BYTES) / a.stage_bytes;
         if (a.stages >= 3 || a.R == 4) break;

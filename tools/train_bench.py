@@ -77,6 +77,30 @@ for mode, tf32, label in (("b200", False, "native sm_100a fwd+bwd"), ("torch", T
         print(f"{label:58s}: FAILED {type(ex).__name__}: {str(ex)[:200]}", flush=True)
         torch.cuda.empty_cache()
 
+# HNeRV: the reference trains THROUGH the ConvNeXt encoder (model(frame) -> encoder -> decoder, train_nerv_all.py:342);
+# the encoder stays a torch module, so this is what a full step costs with it in the loop
+if cfg.startswith("hnerv"):
+    for mode, tf32, label in (("b200", True, "full step incl. torch encoder: native decoder"), ("torch", True, "full step incl. torch encoder: torch decoder (TF32)")):
+        torch.backends.cudnn.allow_tf32 = tf32
+        model, args = bench.build_model(cfg)
+        model = model.to(dev).train()
+        model.train_backend = mode
+        frame = torch.rand(1, 3, 1080, 1920, device=dev)
+        t = torch.tensor([0.5], dtype=torch.float64, device=dev)
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            img = model(frame, norm_idx=t)[0]
+            ((img - frame) ** 2).mean().backward()
+
+        try:
+            print(f"{label:58s}: {timed(step, steps):8.2f} ms/step", flush=True)
+        except Exception as ex:
+            print(f"{label:58s}: FAILED {type(ex).__name__}: {str(ex)[:200]}", flush=True)
+        del model
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = False
+
 # individual backward kernels at the biggest layer of the preset
 shapes = {"hnerv_l": (112, 112, 1080, 1920), "hnerv_m": (89, 89, 1080, 1920), "enerv_m": (21, 21, 1080, 1920)}.get(cfg, (12, 12, 720, 1280))
 cin, cout, H, W = shapes
