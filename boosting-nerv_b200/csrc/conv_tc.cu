@@ -503,7 +503,7 @@ __device__ __forceinline__ void epilogue_head(const ConvTcArgs& a, const Pipe& p
 }
 
 template <int MT, int ACT, int FLAGS>
-__global__ void __launch_bounds__(N_THREADS, 1)
+__global__ void __launch_bounds__(N_THREADS, 1)     // 18 warps = 5 on two of the four SM sub-partitions (16 K registers each): <= 96 registers/thread
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcArgs a) {
     using G = Geo<MT>;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -582,6 +582,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const size_t plane = static_cast<size_t>(Ho) * Wo * 8;      // halves per 8-channel plane
         const uint32_t tempty_leader = map_to_cta(p.tempty, 0);
         const WorkRange wr = work_range(a, p.pair);
+        int cst_key0 = -1, cst_key1 = -1;        // (n-tile, batch) the two constant buffers currently hold
         pdl_wait();            // residual / TAT tables come from earlier kernels; our stores must not overtake their readers
         for (int it = wr.begin; it < wr.end; ++it) {
             const int nt = it / a.pair_tiles, pt = it - nt * a.pair_tiles;
@@ -594,10 +595,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const size_t base_b = static_cast<size_t>(t.b) * cout_groups * plane;
                 const size_t pix = (static_cast<size_t>(h) * s * Wo + static_cast<size_t>(w) * s) * 8;
 
-                // Stage this tile's per-row constants (bias, TAT scale+1, TAT shift) and per-16-column-group
-                // addressing in shared memory: one global load per constant, issued before the accumulator wait.
+                // Stage the per-row constants (bias, TAT scale+1, TAT shift) and per-16-column-group addressing in
+                // shared memory.  They depend on (n-tile, batch index) only, so a buffer is re-staged only when that
+                // key changes: narrow layers (one K step per tile) would otherwise pay a global-load latency and a
+                // 512-thread barrier per tile - 2/3 of their epilogue time.
                 Cst* cb = cst + abuf;
-                if (et < a.n_acc) {
+                const int ckey = nt * a.B + t.b;
+                const bool restage = ((abuf ? cst_key1 : cst_key0) != ckey);     // uniform over the epilogue warps
+                if (restage) {
+                  if (abuf) cst_key1 = ckey; else cst_key0 = ckey;
+                  named_bar_sync(1, 32 * N_EPI_WARPS);                     // every warp is done reading this buffer (any earlier tile)
+                  if (et < a.n_acc) {
                     const int nn = n0 + et;
                     float bv = 0.0f, gv = 0.0f, ev = 0.0f;
                     if (nn < a.n_total) {
@@ -610,7 +618,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     cb->bias[et] = bv; cb->g1p[et] = gv; cb->beta[et] = ev;
-                } else if (et >= 256 && et < 256 + 2 * MAX_GROUPS) {
+                  } else if (et >= 256 && et < 256 + 2 * MAX_GROUPS) {
                     const int ch = et - 256;                    // chunk = 8 packed rows
                     const int nn = n0 + ch * 8;
                     int cc = nn, i = 0, j = 0;
@@ -620,11 +628,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     ci.cc = cc;
                     ci.ij = i | (j << 16);
                     cb->chk[ch] = ci;
+                  }
+                  named_bar_sync(1, 32 * N_EPI_WARPS);                     // constants visible to all epilogue warps
                 }
-
-                // constants visible to all epilogue warps; also orders this tile's writes to cb after every warp's
-                // reads of the same buffer two tiles ago
-                named_bar_sync(1, 32 * N_EPI_WARPS);
 
                 bool act16[4];
 #pragma unroll
