@@ -549,8 +549,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     p.tfull = smem_u32(tfull_bar);   p.tempty = smem_u32(tempty_bar);
     p.wfull = smem_u32(wfull_bar);   p.wempty = smem_u32(wempty_bar);
     p.tmem_base = *tmem_slot;
-    p.rank = cluster_ctarank();
-    p.pair = cluster_id_x();
+    // clusters of (2,1,1) are consecutive blocks in x: taking rank / pair index from blockIdx (not from the %cluster_ctarank /
+    // %clusterid.x special registers) lets the compiler keep all tile arithmetic derived from them - work ranges, the
+    // div/mod of the tile decode - on the uniform datapath instead of replicating ~150 integer instructions per tile in
+    // every thread (half of a narrow layer's epilogue instruction stream)
+    p.rank = blockIdx.x & 1u;
+    p.pair = blockIdx.x >> 1;
 
     if (warp == 0) {
         producer_role<MT>(a, p, &tmA, &tmB);
