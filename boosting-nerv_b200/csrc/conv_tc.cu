@@ -248,6 +248,57 @@ __device__ __forceinline__ void epilogue_group(const ConvTcArgs& a, int flags, c
     }
 }
 
+// Same for ONE chunk of 8 channels (narrow layers: n_acc == 16, where the two chunks of the only accumulator group go to
+// different warps so that all 16 epilogue warps work instead of 8).
+template <int ACT, int FLAGS>
+__device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, const uint32_t* v, const Cst* cb, int col, int b,
+                                               size_t off, int cc, int ho, int wo, bool valid, const uint4& rr, int Ho, int Wo) {
+    const float4 b0 = *reinterpret_cast<const float4*>(cb->bias + col), b1 = *reinterpret_cast<const float4*>(cb->bias + col + 4);
+    float2 x[4];
+    x[0] = add2(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(b0.x, b0.y));
+    x[1] = add2(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(b0.z, b0.w));
+    x[2] = add2(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(b1.x, b1.y));
+    x[3] = add2(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(b1.z, b1.w));
+    float4 gg[2], ee[2];
+    if (flags & F_AFF) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            gg[p] = *reinterpret_cast<const float4*>(cb->g1p + col + 4 * p);
+            ee[p] = *reinterpret_cast<const float4*>(cb->beta + col + 4 * p);
+        }
+    }
+    float2 dv[4];
+    if (flags & F_DERIV) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) x[p] = act2_with_deriv(x[p], (ACT >= 0) ? ACT : a.act, dv[p]);
+    } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) x[p] = act2_rt<ACT>(x[p], a.act);
+    }
+    if (flags & F_RESID) {
+        x[0] = add2(x[0], unpack_h2(rr.x)); x[1] = add2(x[1], unpack_h2(rr.y));
+        x[2] = add2(x[2], unpack_h2(rr.z)); x[3] = add2(x[3], unpack_h2(rr.w));
+    }
+    if (!valid) return;
+    if (flags & F_DERIV) *reinterpret_cast<uint4*>(a.out_deriv + off) = pack8(dv);
+    if (flags & F_PRE) *reinterpret_cast<uint4*>(a.out_pre + off) = pack8(x);
+    if (flags & F_NCHW) {
+        const float xs[8] = {x[0].x, x[0].y, x[1].x, x[1].y, x[2].x, x[2].y, x[3].x, x[3].y};
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (cc + k < a.cout) a.out_nchw[(static_cast<size_t>(b * a.cout + cc + k) * Ho + ho) * Wo + wo] = xs[k];
+    }
+    if (flags & F_AFF) {
+        float2 y[4];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            y[2 * p]     = fma2(x[2 * p],     make_float2(gg[p].x, gg[p].y), make_float2(ee[p].x, ee[p].y));
+            y[2 * p + 1] = fma2(x[2 * p + 1], make_float2(gg[p].z, gg[p].w), make_float2(ee[p].z, ee[p].w));
+        }
+        *reinterpret_cast<uint4*>(a.out_aff + off) = pack8(y);
+    }
+}
+
 struct Pipe {
     uint32_t w_base;         // shared-window address of the resident weight half
     uint32_t a_base;         // ... of the activation stage ring
@@ -502,7 +553,7 @@ __device__ __forceinline__ void epilogue_head(const ConvTcArgs& a, const Pipe& p
     }
 }
 
-template <int MT, int ACT, int FLAGS>
+template <int MT, int ACT, int FLAGS, bool NARROW>
 __global__ void __launch_bounds__(N_THREADS, 1)     // 18 warps = 5 on two of the four SM sub-partitions (16 K registers each): <= 96 registers/thread
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcArgs a) {
     using G = Geo<MT>;
@@ -636,6 +687,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   named_bar_sync(1, 32 * N_EPI_WARPS);                     // constants visible to all epilogue warps
                 }
 
+              if (NARROW) {                 // compile-time: MT == 2 && n_acc == 16 (launch_conv)
+                // ---- narrow layers: one 16-column group; warp (mt, cs) takes its chunk cs (8 channels) ----
+                size_t off;
+                int cc, ho, wo;
+                if (flags & F_SHUF) {
+                    const ChunkInfo ci = cb->chk[(flags & F_WIDE) ? 0 : cs];
+                    off = base_b + pix + static_cast<size_t>(ci.goff) + ((flags & F_WIDE) ? 8 * cs : 0);
+                    cc = ci.cc;
+                    ho = h * s + (ci.ij & 0xffff);
+                    wo = w * s + (ci.ij >> 16) + ((flags & F_WIDE) ? cs : 0);
+                } else {
+                    cc = n0 + cs * 8;
+                    off = base_b + pix + static_cast<size_t>(cc >> 3) * plane;
+                    ho = h;
+                    wo = w;
+                }
+                uint4 rr = make_uint4(0, 0, 0, 0);
+                if ((flags & F_RESID) && valid) rr = __ldg(reinterpret_cast<const uint4*>(a.resid + off));
+                mbar_wait(p.tfull + abuf * 8, aphase);
+                tc_fence_after();
+                uint32_t v8[8];
+                tmem_ld8(p.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + abuf * BUF_COLS + mt * G::ACC_STRIDE + cs * 8, v8);
+                tmem_ld_wait();
+                epilogue_chunk<ACT, FLAGS>(a, flags, v8, cb, cs * 8, t.b, off, cc, ho, wo, valid, rr, Ho, Wo);
+              } else {
                 bool act16[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -703,6 +779,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         epilogue_group<ACT, FLAGS>(a, flags, v[j & 1], bs, cb, col, t.b, ga, valid, rres[j], Ho, Wo);
                     }
                 }
+              }
                 // all TMEM reads of this warp for this buffer are complete -> hand it back to the leader's MMA warp
                 tc_fence_before();
                 __syncwarp();
@@ -803,16 +880,16 @@ int choose_n_acc_stream(int n_total, int taps) {
     return best;
 }
 
-template <int MT>
-static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& a, int act, size_t smem_bytes,
-                       cudaStream_t stream) {
+template <int MT, bool NARROW>
+static int launch_conv_n(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& a, int act, size_t smem_bytes,
+                         cudaStream_t stream) {
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const ConvTcArgs);
     // specialised epilogues for the launch shapes of the decoder cascade, generic otherwise
-    KernelFn fn = conv_tc_kernel<MT, -1, -1>;
+    KernelFn fn = conv_tc_kernel<MT, -1, -1, NARROW>;
     int slot = 0;
     const int fl = a.flags;
 #define BNERV_PICK(ID, ACT_, FL_)                                              \
-    if (act == (ACT_) && fl == (FL_)) { fn = conv_tc_kernel<MT, (ACT_), (FL_)>; slot = (ID); }
+    if (act == (ACT_) && fl == (FL_)) { fn = conv_tc_kernel<MT, (ACT_), (FL_), NARROW>; slot = (ID); }
     BNERV_PICK(1, BNERV_ACT_SIN, F_AFF | F_PRE)                 // up-conv 1x1 / s=1 (+sin, x0 and u)
     BNERV_PICK(2, BNERV_ACT_SIN, F_AFF | F_PRE | F_SHUF)        // up-conv + PixelShuffle (s = 3, 5)
     BNERV_PICK(7, BNERV_ACT_SIN, F_AFF | F_PRE | F_SHUF | F_WIDE)   // up-conv + PixelShuffle(2), 32-byte stores
@@ -855,6 +932,14 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
         return set_error(static_cast<int>(e), "conv_tc_kernel launch: %s", cudaGetErrorString(e));
     }
     return check_launch("conv_tc_kernel");
+}
+
+// NARROW (one 16-column accumulator group, MT = 2): the two 8-channel chunks go to different epilogue warps
+template <int MT>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& a, int act, size_t smem_bytes,
+                       cudaStream_t stream) {
+    if (MT == 2 && a.n_acc == 16 && !(a.flags & F_HEAD)) return launch_conv_n<2, true>(tmA, tmB, a, act, smem_bytes, stream);
+    return launch_conv_n<MT, false>(tmA, tmB, a, act, smem_bytes, stream);
 }
 
 }  // namespace bnerv
