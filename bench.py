@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=1, help="frames per launch (reference scripts use -b 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the extra training-step measurement (N=1 only)")
+    ap.add_argument("--no-others", action="store_true", help="skip the short decode runs of the other BASELINE presets (N=1 only)")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="wall-clock budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -392,9 +393,43 @@ def run_b200(opt):
             line["train_step"] = train_step_times(opt.config, dev)
         except Exception as ex:  # never let the extra measurement take the metric line down
             line["train_step"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+    if world == 1 and not opt.no_others:
+        # extra, outside the metric: device-resident decode frames/s of the other BASELINE.json presets (configs 1-2),
+        # same timing rules (CUDA-graph replay per frame, CUDA events, 10 warm-up + 200 timed frames)
+        others = {}
+        for name in ("enerv_m", "nerv_s"):
+            if name == opt.config:
+                continue
+            try:
+                others[name] = other_preset_fps(name, dev)
+            except Exception as ex:
+                others[name] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+        line["other_presets"] = others
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_preset_fps(name, dev, steps=200, warm=10):
+    model, args = build_model(name)
+    model = model.to(dev)
+    t = torch.tensor([[(i + 1) / N_FRAMES] for i in range(steps + warm)], dtype=torch.float64, device=dev)
+    with torch.no_grad():
+        for j in range(warm):
+            model.decode(t[j])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for j in range(steps):
+            img = model.decode(t[warm + j])
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"workload": workload_name(name, args), "frames_per_s": 1e3 / ms, "ms_per_frame": ms,
+           "algorithmic_tflops": ALG_GFLOP[name] / ms, "steps": steps}
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 def train_step_times(cfg_name, dev, steps=5):

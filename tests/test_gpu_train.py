@@ -286,3 +286,32 @@ def test_quant_aware_style_training_through_dequant_weights_runs_eagerly_and_rea
         assert max_rel(res["b200"][n], res["torch"][n]) < 1e-2, n
     for c in convs:
         c.dequant_w, c.dequant_b = None, None
+
+
+def test_two_forwards_before_backward_fall_back_to_the_eager_function():
+    """Gradient accumulation over two frames with both forwards issued before either backward: the captured graph owns
+    one set of activation maps, so the second forward must take the eager Function and both backwards must be right."""
+    m, a = _build("HNeRV_Boost")
+    fh, fw = [int(v) for v in a.fc_hw.split("_")]
+    emb = torch.rand(2, 16, fh, fw, device="cuda")
+    ts = [torch.tensor([0.2], dtype=torch.float64, device="cuda"), torch.tensor([0.9], dtype=torch.float64, device="cuda")]
+    target = torch.rand(1, 3, fh * 20, fw * 20, device="cuda")
+    res = {}
+    for mode in ("torch", "b200"):
+        m.train_backend = mode
+        for rep in range(2):                      # rep 0 also captures the graphs in b200 mode
+            m.zero_grad(set_to_none=True)
+            l0 = _loss(m, "HNeRV_Boost", ts[0], emb[0:1], target)[2]
+            l1 = _loss(m, "HNeRV_Boost", ts[1], emb[1:2], target)[2]     # issued while l0 still awaits its backward
+            l1.backward()
+            l0.backward()
+        res[mode] = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    for n in res["torch"]:
+        assert max_rel(res["b200"][n], res["torch"][n]) < 1e-2, n
+    # a second backward through the same forward is refused, not silently wrong
+    m.train_backend = "b200"
+    m.zero_grad(set_to_none=True)
+    l0 = _loss(m, "HNeRV_Boost", ts[0], emb[0:1], target)[2]
+    l0.backward(retain_graph=True)
+    with pytest.raises(RuntimeError):
+        l0.backward()
