@@ -352,3 +352,17 @@ def frame_metrics(img, gt):
     out = torch.empty((B, 3), dtype=torch.float32, device=img.device)
     check("bnerv_frame_metrics", lib.bnerv_frame_metrics(ptr(img), ptr(gt), B, n, ptr(scratch), ptr(out), _stream()))
     return out
+
+
+def nerv_block_fwd(x_c8, up, c0, c1, cin, H, W, act_up, act_inner, g0p, beta0, g1p, beta1):
+    """One NeRVBlock through bnerv_nerv_block_fwd.  up / c0 / c1: PackedConv.  Returns (out, x0) C8 f16."""
+    _need_cuda(x_c8)
+    B = x_c8.shape[0]
+    C, s = up.cout, up.s
+    mk = lambda: torch.empty(c8_shape(B, C, H * s, W * s), dtype=torch.float16, device=x_c8.device)
+    x0, u, wmap, out = mk(), mk(), mk(), mk()
+    check("bnerv_nerv_block_fwd",
+          lib.bnerv_nerv_block_fwd(ptr(x_c8), B, cin, H, W, ptr(up.w), ptr(up.b), up.k, s, ACT_CODES[act_up], ptr(c0.w), ptr(c0.b),
+                                   ptr(c1.w), ptr(c1.b), C, ACT_CODES[act_inner], ptr(g0p), ptr(beta0), ptr(g1p), ptr(beta1),
+                                   ptr(x0), ptr(u), ptr(wmap), ptr(out), _stream()))
+    return out, x0

@@ -59,3 +59,28 @@ def decode_to_host(model, norm_idx_host, out_host, embed_host=None, batch=1, dep
                 done[key] = ev
     copy.synchronize()
     return out_host
+
+
+def evaluate_psnr(model, norm_idx_host, gt_host, embed_host=None, batch=1):
+    """Mean PSNR of this rank's frames against ground truth, then over all ranks - the metric half of the reference's
+    evaluate() (train_nerv_all.py:482-505, 554-556) without a host synchronisation per frame: ground-truth frames are
+    copied H2D ahead of the decode, mse/psnr come from `bnerv_frame_metrics` on the device (psnr_fn_single,
+    hnerv_utils.py:400-403), the per-frame values are summed on the device and ONE all_reduce(SUM) of (sum, count)
+    runs at the end (hnerv_utils.py:213-229) when torch.distributed is initialised.  Returns (mean_psnr, n_frames_total)."""
+    from . import ops
+    from .shard import reduce_metric
+    dev = next(model.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("bnerv_b200: the decode path runs only on a CUDA (sm_100a) device")
+    n = norm_idx_host.shape[0]
+    assert gt_host.shape[0] == n and gt_host.dtype == torch.float32
+    is_h = embed_host is not None
+    total = torch.zeros((), dtype=torch.float64, device=dev)
+    with torch.no_grad():
+        for lo in range(0, n, batch):
+            sl = slice(lo, min(lo + batch, n))
+            gt = gt_host[sl].to(dev, non_blocking=True)
+            t = norm_idx_host[sl].to(dev, non_blocking=True)
+            img = model.decode(embed_host[sl].to(dev, non_blocking=True), t) if is_h else model.decode(t)
+            total += ops.frame_metrics(img, gt)[:, 2].double().sum()
+    return reduce_metric(total.item(), n, device=dev)

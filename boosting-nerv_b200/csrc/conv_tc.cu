@@ -1098,3 +1098,24 @@ extern "C" int bnerv_head_conv3(const void* x, int B, int Cin, int H, int W, con
                               HEAD_SMEM_BYTES;
     return launch_conv<2>(tmA, tmB, a, act, smem_bytes, static_cast<cudaStream_t>(stream));
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// One NeRVBlock = three fused-conv launches chained by programmatic dependent launch
+// ---------------------------------------------------------------------------------------------
+extern "C" int bnerv_nerv_block_fwd(const void* x, int B, int Cin, int H, int W, const void* w_up, const float* b_up, int k_up,
+                                    int s, int act_up, const void* w_c0, const float* b_c0, const void* w_c1, const float* b_c1,
+                                    int C, int act_inner, const float* g0p, const float* beta0, const float* g1p,
+                                    const float* beta1, void* x0, void* u, void* wmap, void* out, void* stream) {
+    if (!x0 || !u || !wmap || !out) return set_error(BNERV_E_BADARG, "nerv_block_fwd: null workspace / output");
+    if (!g0p || !beta0 || !g1p || !beta1) return set_error(BNERV_E_BADARG, "nerv_block_fwd: the four TAT tables are required");
+    // x0 = act(PS_s(conv_k(x))) and u = x0*g0p + beta0          model_blocks.py:37,216-217 + :105
+    int rc = bnerv_conv_fused(x, B, Cin, H, W, w_up, b_up, C, k_up, s, act_up, nullptr, g0p, beta0, x0, u, nullptr, stream);
+    if (rc) return rc;
+    const int Ho = H * s, Wo = W * s;
+    // w = act_inner(conv3(u))*g1p + beta1                          model_blocks.py:86-87
+    rc = bnerv_conv_fused(u, B, C, Ho, Wo, w_c0, b_c0, C, 3, 1, act_inner, nullptr, g1p, beta1, nullptr, wmap, nullptr, stream);
+    if (rc) return rc;
+    // out = x0 + conv3(w)                                          model_blocks.py:88-89
+    return bnerv_conv_fused(wmap, B, C, Ho, Wo, w_c1, b_c1, C, 3, 1, BNERV_ACT_NONE, x0, nullptr, nullptr, out, nullptr, nullptr, stream);
+}

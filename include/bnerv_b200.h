@@ -109,6 +109,18 @@ int bnerv_conv_fused_ex(const void* x, int B, int Cin, int H, int W,
                         int act, const void* resid, const float* g1p, const float* beta,
                         void* out_pre, void* out_aff, float* out_nchw, void* out_deriv, void* stream);
 
+/* One NeRVBlock (model_blocks.py:34-46 with the ResBlock_SFT of :74-89) = the three fused-conv launches above issued
+ * back to back on `stream` and chained by programmatic dependent launch:
+ *     x0 = act_up(PS_s(conv_k(x; w_up)))         u   = x0*g0p + beta0
+ *     w  = act_inner(conv3(u; w_c0))*g1p + beta1 out = x0 + conv3(w; w_c1)
+ * x: C8 f16 [B][Cin_p/8][H][W][8]; w_*: packed by bnerv_pack_conv_weight (w_up with k_up and s, the others k = 3, s = 1);
+ * g0p/beta0/g1p/beta1: f32 [B][C_p] from bnerv_sft_affine; x0, u, wmap (workspaces the caller may reuse afterwards; x0
+ * is also the block's pre-residual activation) and out: C8 f16 [B][C_p/8][H*s][W*s][8]. */
+int bnerv_nerv_block_fwd(const void* x, int B, int Cin, int H, int W, const void* w_up, const float* b_up, int k_up,
+                         int s, int act_up, const void* w_c0, const float* b_c0, const void* w_c1, const float* b_c1,
+                         int C, int act_inner, const float* g0p, const float* beta0, const float* g1p,
+                         const float* beta1, void* x0, void* u, void* wmap, void* out, void* stream);
+
 /* The 3x3 head conv to <= 3 channels (HNeRV_Boost.head_layer, model_hnerv.py:214,273) + OutImg (model_blocks.py:57-63)
  * in its own form: out[p,c] = act(b[c] + sum_tap P[p+tap][(tap,c)]) with P = X . Wp ONE 1x1 tensor-core contraction to
  * 9*Cout (<= 27) columns over the halo tile, summed over the taps from shared memory.  Same result as

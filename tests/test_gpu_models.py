@@ -209,3 +209,20 @@ def test_decode_to_host_pipeline_is_bitwise_the_per_frame_api(model):
             assert torch.equal(out, ref)
     with pytest.raises(ValueError):
         decode_to_host(m, t.cuda(), out, emb)
+
+
+def test_evaluate_psnr_matches_per_frame_reference_formula():
+    from bnerv_b200 import evaluate_psnr
+    torch.manual_seed(4)
+    m, a = _build("HNeRV_Boost")
+    m = m.cuda()
+    n = 5
+    fh, fw = [int(v) for v in a.fc_hw.split("_")]
+    t = torch.tensor([(i + 1) / n for i in range(n)], dtype=torch.float64).pin_memory()
+    emb = torch.rand(n, 16, fh, fw).pin_memory()
+    gt = torch.rand(n, 3, fh * 20, fw * 20).pin_memory()
+    with torch.no_grad():
+        imgs = torch.cat([m.forward_decoder(emb[i:i + 1].cuda(), t[i:i + 1].cuda())[0].cpu() for i in range(n)])
+    ref = (-10 * torch.log10(((imgs - gt) ** 2).flatten(1).mean(1) + 1e-9)).mean().item()       # psnr_fn_single, averaged
+    got, cnt = evaluate_psnr(m, t, gt, emb, batch=2)
+    assert cnt == n and abs(got - ref) < 1e-4

@@ -210,6 +210,9 @@ def test_nerv_block_against_reference_golden(ops, name):
     ops.conv_fused(wv, c1, new_ngf, Ho, Wo, act="none", resid=x0, out_pre=out)
     assert max_rel(ops.c8_to_nchw(x0, new_ngf).cpu(), torch.from_numpy(c["x0"])) < REL_GATE
     assert max_rel(ops.c8_to_nchw(out, new_ngf).cpu(), torch.from_numpy(c["y"])) < REL_GATE
+    # the block-level C-ABI entry (bnerv_nerv_block_fwd) issues the same three launches: bit-identical
+    out_b, x0_b = ops.nerv_block_fwd(ops.nchw_to_c8(x), up, c0, c1, ngf, H, W, "sin", "gelu", tab.g1p[0], tab.beta[0], tab.g1p[1], tab.beta[1])
+    assert torch.equal(out_b, out) and torch.equal(x0_b, x0)
 
 
 def test_argument_errors_are_reported_not_launched(ops):
