@@ -20,7 +20,7 @@ EXPORTS = [
     "bnerv_conv_fused_ex", "bnerv_head_bwd", "bnerv_pack_conv_weight_dgrad", "bnerv_conv_wgrad", "bnerv_wgrad_acc_numel",
     "bnerv_wgrad_finalize", "bnerv_bias_finalize", "bnerv_channel_sum", "bnerv_resblock_mid_bwd", "bnerv_block_front_bwd",
     "bnerv_unshuffle_c8", "bnerv_pack_conv_weight_q", "bnerv_frame_metrics", "bnerv_frame_metrics_scratch_doubles",
-    "bnerv_pack_head_weight", "bnerv_head_conv3", "bnerv_nerv_block_fwd",
+    "bnerv_pack_head_weight", "bnerv_head_conv3", "bnerv_nerv_block_fwd", "bnerv_head_conv1",
 ]
 
 
@@ -56,6 +56,7 @@ def _load():
     lib.bnerv_pack_head_weight.argtypes = [vp, i, i, vp, vp]
     lib.bnerv_head_conv3.argtypes = [vp, i, i, i, i, vp, vp, i, i, vp, vp]
     lib.bnerv_nerv_block_fwd.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.bnerv_head_conv1.argtypes = [vp, i, i, i, i, vp, vp, i, i, vp, vp]
     lib.bnerv_conv_fused_ex.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.bnerv_head_bwd.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp]
     lib.bnerv_pack_conv_weight_dgrad.argtypes = [vp, i, i, i, i, vp, vp]

@@ -46,6 +46,8 @@ class _ConvSlot:
         self.key, self.pc = None, None
         # HNeRV's 3x3 head to 3 channels has its own kernel form (bnerv_head_conv3); BNERV_NO_HEAD_KERNEL=1 = generic path
         self.head3 = bool(head and k == 3 and self.cout <= 3 and not os.environ.get("BNERV_NO_HEAD_KERNEL"))
+        # NeRV / E-NeRV's 1x1 head: HBM-bound CUDA-core kernel (bnerv_head_conv1)
+        self.head1 = bool(head and k == 1 and self.cout <= 4 and not os.environ.get("BNERV_NO_HEAD_KERNEL"))
 
     def packed(self, force=False):
         """force: re-pack unconditionally (inside a captured training graph the pack kernels ARE the per-step ingest)."""
@@ -53,7 +55,8 @@ class _ConvSlot:
         key = (_tensor_key(w), _tensor_key(b))
         if key != self.key or force:
             if self.pc is None:
-                self.pc = ops.PackedHead(w, b) if self.head3 else ops.PackedConv(w, b, self.s)
+                self.pc = (ops.PackedHead(w, b) if self.head3 else ops.PackedHead1(w, b) if self.head1
+                           else ops.PackedConv(w, b, self.s))
             else:
                 self.pc.repack(w, b)
             self.key = key

@@ -124,6 +124,27 @@ class PackedHead:
             self.b.copy_(bias.detach())
 
 
+class PackedHead1:
+    """A 1x1 head conv to <= 4 channels for bnerv_head_conv1: the raw f32 weights [Cout, Cin] and bias (copies, so that
+    a captured graph reads stable storage)."""
+
+    def __init__(self, weight, bias):
+        _need_cuda(weight, bias)
+        self.cout, self.cin, k, k2 = weight.shape
+        assert k == 1 and k2 == 1 and self.cout <= 4
+        self.k, self.s = 1, 1
+        self.w = torch.empty((self.cout, self.cin), dtype=torch.float32, device=weight.device)
+        self.b = torch.zeros(self.cout, dtype=torch.float32, device=weight.device)
+        self.repack(weight, bias)
+
+    def repack(self, weight, bias):
+        self.w.copy_(weight.detach().reshape(self.cout, self.cin))
+        if bias is None:
+            self.b.zero_()
+        else:
+            self.b.copy_(bias.detach())
+
+
 # When set to a list, every conv_fused launch appends (algorithmic_flops, start_event, end_event) — used by
 # bench.py to time the dominant kernel inside the timed region on the launching stream.
 TIMING = None
@@ -143,7 +164,12 @@ def conv_fused(x_c8, pc, cin, H, W, act="none", resid=None, g1p=None, beta=None,
     if TIMING is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    if isinstance(pc, PackedHead):
+    if isinstance(pc, PackedHead1):
+        if out_nchw is None or resid is not None or g1p is not None or out_pre is not None or out_deriv is not None:
+            raise ValueError("the head kernel writes the NCHW f32 image only")
+        check("bnerv_head_conv1", lib.bnerv_head_conv1(ptr(x_c8), B, cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, ACT_CODES[act],
+                                                       ptr(out_nchw), _stream()))
+    elif isinstance(pc, PackedHead):
         if out_nchw is None or resid is not None or g1p is not None or out_pre is not None or out_deriv is not None:
             raise ValueError("the head kernel writes the NCHW f32 image only")
         check("bnerv_head_conv3", lib.bnerv_head_conv3(ptr(x_c8), B, cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, ACT_CODES[act],

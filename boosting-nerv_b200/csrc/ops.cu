@@ -282,6 +282,51 @@ __global__ void conv_f32_kernel(const float* __restrict__ x, int B, int Cin, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 1x1 head conv to <= 4 channels + OutImg (NeRV_Boost / ENeRV_Boost head_layer, model_nerv.py:41,56-57): HBM-bound
+// CUDA-core kernel.  Through the tensor-core path this launch is a chain of tiny N = 16 UMMAs bound by per-tile
+// latency (NeRV-S 720p: 43 us, E-NeRV-M 1080p: 88 us); here one thread owns one pixel, reads its Cin_p/8 16-byte
+// chunks (coalesced across the pixels of a warp), multiplies by the f32 weights held in shared memory and writes the
+// NCHW f32 pixels - the read of the last activation map is all that is left.
+// ---------------------------------------------------------------------------------------------
+constexpr int HEAD1_MAX_COUT = 4;
+
+__global__ void head1x1_kernel(const uint4* __restrict__ x, int B, int Cin, int cin_p, size_t hw, const float* __restrict__ w,
+                               const float* __restrict__ bias, int Cout, int act, float* __restrict__ out) {
+    extern __shared__ float sw[];                 // [Cout][cin_p] (zero beyond Cin) | bias[Cout]
+    for (int i = threadIdx.x; i < Cout * cin_p; i += blockDim.x) {
+        const int c = i / cin_p, k = i - c * cin_p;
+        sw[i] = (k < Cin) ? w[c * Cin + k] : 0.0f;
+    }
+    if (threadIdx.x < Cout) sw[Cout * cin_p + threadIdx.x] = bias ? bias[threadIdx.x] : 0.0f;
+    __syncthreads();
+    const int groups = cin_p >> 3;
+    const size_t total = static_cast<size_t>(B) * hw;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t b = idx / hw, p = idx - b * hw;
+        float acc[HEAD1_MAX_COUT];
+#pragma unroll
+        for (int c = 0; c < HEAD1_MAX_COUT; ++c) acc[c] = (c < Cout) ? sw[Cout * cin_p + c] : 0.0f;
+        for (int g = 0; g < groups; ++g) {
+            const uint4 u = x[(b * groups + g) * hw + p];
+            const float2 a0 = unpack_h2(u.x), a1 = unpack_h2(u.y), a2 = unpack_h2(u.z), a3 = unpack_h2(u.w);
+            const float v[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+            for (int c = 0; c < HEAD1_MAX_COUT; ++c) {
+                if (c < Cout) {
+                    const float* wr = sw + c * cin_p + g * 8;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[c] = fmaf(v[k], wr[k], acc[c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < HEAD1_MAX_COUT; ++c)
+            if (c < Cout) out[(b * Cout + c) * hw + p] = apply_act(acc[c], act);
+    }
+}
+
 static int grid_for(size_t total, int block) {
     size_t g = (total + block - 1) / block;
     const size_t cap = 148 * 32;
@@ -345,6 +390,21 @@ extern "C" int bnerv_pack_head_weight(const float* w_oihw, int Cout, int Cin, vo
     pack_head_weight_kernel<<<grid_for(static_cast<size_t>(cin_p) * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         w_oihw, Cout, Cin, cin_p, static_cast<__half*>(w_head_packed));
     return check_launch("pack_head_weight_kernel");
+}
+
+extern "C" int bnerv_head_conv1(const void* x, int B, int Cin, int H, int W, const float* w_oihw, const float* bias, int Cout,
+                                int act, float* out_nchw, void* stream) {
+    if (!x || !w_oihw || !out_nchw) return set_error(BNERV_E_BADARG, "head_conv1: null pointer");
+    if (B <= 0 || Cin <= 0 || H <= 0 || W <= 0 || Cout <= 0) return set_error(BNERV_E_BADARG, "head_conv1: non-positive size");
+    if (Cout > HEAD1_MAX_COUT) return set_error(BNERV_E_UNSUPPORTED, "head_conv1: Cout = %d (at most %d)", Cout, HEAD1_MAX_COUT);
+    if (act < BNERV_ACT_NONE || act > BNERV_ACT_TANH01) return set_error(BNERV_E_UNSUPPORTED, "head_conv1: act %d", act);
+    const int cin_p = round_up(Cin, 16);
+    const size_t smem = (static_cast<size_t>(Cout) * cin_p + Cout) * sizeof(float);
+    if (smem > 48 * 1024) return set_error(BNERV_E_UNSUPPORTED, "head_conv1: Cin = %d too wide", Cin);
+    const size_t hw = static_cast<size_t>(H) * W;
+    head1x1_kernel<<<grid_for(static_cast<size_t>(B) * hw, 256), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), B, Cin, cin_p, hw, w_oihw, bias, Cout, act, out_nchw);
+    return check_launch("head1x1_kernel");
 }
 
 extern "C" int bnerv_nchw_to_c8(const float* x, int B, int C, int H, int W, void* y_c8, void* stream) {

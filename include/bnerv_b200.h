@@ -130,6 +130,12 @@ int bnerv_pack_head_weight(const float* w_oihw, int Cout, int Cin, void* w_head_
 int bnerv_head_conv3(const void* x, int B, int Cin, int H, int W, const void* w_head_packed, const float* bias,
                      int Cout, int act, float* out_nchw, void* stream);
 
+/* The 1x1 head conv to <= 4 channels + OutImg (NeRV_Boost / ENeRV_Boost head_layer, model_nerv.py:41,56-57) as an
+ * HBM-bound CUDA-core kernel: x C8 f16, w_oihw the RAW f32 [Cout][Cin] weights (no packing, no f16 rounding of the
+ * weights), bias f32 [Cout] or NULL, out NCHW f32.  Replaces a chain of latency-bound N = 16 UMMAs. */
+int bnerv_head_conv1(const void* x, int B, int Cin, int H, int W, const float* w_oihw, const float* bias, int Cout,
+                     int act, float* out_nchw, void* stream);
+
 /* Same contract and operand layouts as bnerv_conv_fused, computed by an f32 CUDA-core kernel on the
  * reference's own layouts (NCHW f32 activations, OIHW f32 weights) — the exact-arithmetic path used
  * for tiny layers and as the on-device cross-check of the tensor-core kernel.

@@ -296,3 +296,38 @@ def test_head_kernel_matches_reference_and_generic_path(ops, B, cin, cout, H, W,
     assert max_rel(out_h, out_g) < 1e-5
     with pytest.raises(Exception):
         ops.PackedHead(torch.zeros(4, 16, 3, 3, device="cuda"), None)      # more than 3 output channels: not this kernel
+
+
+@pytest.mark.parametrize("scale", [30.0, 300.0])
+def test_sin_and_its_derivative_stay_accurate_at_large_pre_activations(ops, scale):
+    """Trained NeRV stems drive the pre-sin values far beyond +-pi: the epilogue's two-constant
+    Cody-Waite reduction + MUFU.SIN/COS must hold |err| <= 6e-4 there (pre-activations up to ~4*scale)."""
+    torch.manual_seed(0)
+    B, cin, cout, H, W = 1, 16, 16, 24, 40
+    x = torch.randn(B, cin, H, W, device="cuda")
+    w = torch.randn(cout, cin, 3, 3, device="cuda") * (scale / (cin * 9) ** 0.5)
+    cp = ops.round_up(cout, 16)
+    g1p, beta = torch.ones(B, cp, device="cuda"), torch.zeros(B, cp, device="cuda")
+    shp = ops.c8_shape(B, cout, H, W)
+    pre, aff, der = [torch.empty(shp, dtype=torch.float16, device="cuda") for _ in range(3)]
+    ops.conv_fused(ops.nchw_to_c8(x), ops.PackedConv(w, None, 1), cin, H, W, act="sin", g1p=g1p, beta=beta, out_pre=pre, out_aff=aff,
+                   out_deriv=der)
+    z = F.conv2d(x.half().double(), w.half().double(), None, 1, 1)
+    assert z.abs().max() > 2.5 * scale
+    assert (ops.c8_to_nchw(pre, cout).double() - torch.sin(z)).abs().max().item() < 6e-4 + 2 ** -11
+    assert (ops.c8_to_nchw(der, cout).double() - torch.cos(z)).abs().max().item() < 6e-4 + 2 ** -11
+
+
+@pytest.mark.parametrize("B,cin,cout,H,W,act", [(1, 12, 3, 36, 64, "tanh01"), (2, 21, 3, 17, 33, "tanh01"), (1, 40, 4, 9, 5, "none"), (1, 7, 1, 3, 3, "tanh01")])
+def test_head1x1_kernel_matches_reference(ops, B, cin, cout, H, W, act):
+    """bnerv_head_conv1 == 1x1 conv + OutImg (model_nerv.py:41,56-57; model_blocks.py:57-63) on the f16 activations with
+    the exact f32 weights."""
+    torch.manual_seed(0)
+    x = torch.randn(B, cin, H, W, device="cuda")
+    w = torch.randn(cout, cin, 1, 1, device="cuda") / cin ** 0.5
+    b = torch.randn(cout, device="cuda") * 0.1
+    out = torch.full((B, cout, H, W), float("nan"), device="cuda")
+    ops.conv_fused(ops.nchw_to_c8(x), ops.PackedHead1(w, b), cin, H, W, act=act, out_nchw=out)
+    ref = F.conv2d(x.half().float(), w, b)
+    ref = torch.tanh(ref) * 0.5 + 0.5 if act == "tanh01" else ref
+    assert max_rel(out, ref) < 2e-6
