@@ -490,7 +490,6 @@ __device__ __forceinline__ void epilogue_head(const ConvTcArgs& a, const Pipe& p
     const int et  = threadIdx.x - 64;
     const uint32_t tempty_leader = map_to_cta(p.tempty, 0);
     const WorkRange wr = work_range(a, p.pair);
-    const int ntap_c = 9 * a.cout;
     int abuf = 0;
     uint32_t aphase = 0;
     float bias_c[2] = {0.0f, 0.0f};                 // this thread's output channels: c = (et >> 8) + 2*i
@@ -547,7 +546,6 @@ __device__ __forceinline__ void epilogue_head(const ConvTcArgs& a, const Pipe& p
                 }
             }
         }
-        (void)ntap_c;
         abuf ^= 1;
         if (abuf == 0) aphase ^= 1;
     }
