@@ -21,6 +21,7 @@ EXPORTS = [
     "bnerv_wgrad_finalize", "bnerv_bias_finalize", "bnerv_channel_sum", "bnerv_resblock_mid_bwd", "bnerv_block_front_bwd",
     "bnerv_unshuffle_c8", "bnerv_pack_conv_weight_q", "bnerv_frame_metrics", "bnerv_frame_metrics_scratch_doubles",
     "bnerv_pack_head_weight", "bnerv_head_conv3", "bnerv_nerv_block_fwd", "bnerv_head_conv1",
+    "bnerv_ssim_stats", "bnerv_ssim_grad", "bnerv_ssim_scratch_floats",
 ]
 
 
@@ -57,6 +58,10 @@ def _load():
     lib.bnerv_head_conv3.argtypes = [vp, i, i, i, i, vp, vp, i, i, vp, vp]
     lib.bnerv_nerv_block_fwd.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.bnerv_head_conv1.argtypes = [vp, i, i, i, i, vp, vp, i, i, vp, vp]
+    lib.bnerv_ssim_stats.argtypes = [vp, vp, i, i, i, f, f, vp, vp]
+    lib.bnerv_ssim_grad.argtypes = [vp, vp, i, i, i, f, f, vp, vp, i, vp, vp]
+    lib.bnerv_ssim_scratch_floats.argtypes = [i, i, i]
+    lib.bnerv_ssim_scratch_floats.restype = ctypes.c_size_t
     lib.bnerv_conv_fused_ex.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.bnerv_head_bwd.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp]
     lib.bnerv_pack_conv_weight_dgrad.argtypes = [vp, i, i, i, i, vp, vp]

@@ -244,6 +244,19 @@ int bnerv_frame_metrics(const float* img, const float* gt, int B, size_t n_per_f
                         void* stream);
 size_t bnerv_frame_metrics_scratch_doubles(int B);
 
+/* SSIM statistics of one pyramid level and their gradient: the device side of the `ssim` /
+ * `ms_ssim` terms of hnerv_utils.loss_fn (:338-395), which the reference takes from pytorch_msssim==0.2.1 (not vendored;
+ * algorithm restated in oracle/msssim_oracle.py, parity unpinned).  11-tap Gaussian window (sigma 1.5), 'valid' extent.
+ *   x, y  : f32 [planes][H][W] (planes = batch * channels), H, W > 10
+ *   stats : f64 [planes][2], caller-zeroed; += {sum ssim_map, sum cs_map} over the (H-10) x (W-10) valid pixels
+ *   gw    : f32 [planes][2] = dL/d{mean ssim, mean cs} / ((H-10)*(W-10));  scratch: bnerv_ssim_scratch_floats floats
+ *   dx    : f32 [planes][H][W] (=|+=) dL/dx  (y is treated as a constant, hnerv_utils.py:336) */
+int bnerv_ssim_stats(const float* x, const float* y, int planes, int H, int W, float C1, float C2, double* stats,
+                     void* stream);
+int bnerv_ssim_grad(const float* x, const float* y, int planes, int H, int W, float C1, float C2, const float* gw,
+                    float* scratch, int accumulate, float* dx, void* stream);
+size_t bnerv_ssim_scratch_floats(int planes, int H, int W);
+
 /* Sizes (in elements) of the buffers the caller must provide. */
 size_t bnerv_c8_numel(int B, int C, int H, int W);                 /* __half elements            */
 size_t bnerv_packed_weight_numel(int Cout, int Cin, int k, int s); /* __half elements            */

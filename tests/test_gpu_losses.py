@@ -1,0 +1,78 @@
+"""GPU: device-side SSIM / MS-SSIM (csrc/loss_ops.cu, bnerv_b200/losses.py) against the restatement of
+pytorch_msssim==0.2.1 in oracle/msssim_oracle.py - values and gradients w.r.t. the prediction.  PARITY UNPINNED: the
+package itself is neither in the reference tree nor installed, so the checker is the restated published algorithm."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import max_rel
+from oracle import msssim_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(B, C, H, W, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+    base = torch.stack([0.5 + 0.4 * torch.sin(6.28 * ((2 + c) * xx + (3 - c) * yy + 0.3 * b)) for b in range(B) for c in range(C)]).view(B, C, H, W)
+    target = (base + 0.05 * torch.rand(B, C, H, W, generator=g)).clamp(0, 1)
+    pred = (target + 0.08 * torch.randn(B, C, H, W, generator=g)).clamp(0, 1)
+    return pred.cuda(), target.cuda()
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 40, 64), (1, 3, 37, 53), (1, 1, 11, 12), (2, 3, 180, 320)])
+def test_ssim_value_and_gradient(shape):
+    from bnerv_b200 import losses
+    pred, target = _pair(*shape)
+    p1 = pred.clone().requires_grad_(True)
+    p2 = pred.clone().requires_grad_(True)
+    v1 = losses.ssim(p1, target, data_range=1, size_average=False)
+    v2 = mo.ssim(p2, target, data_range=1.0, size_average=False)
+    assert v1.shape == v2.shape and max_rel(v1, v2) < 2e-5
+    w = torch.linspace(0.5, 1.5, shape[0], device="cuda")
+    (v1 * w).sum().backward()
+    (v2 * w).sum().backward()
+    assert max_rel(p1.grad, p2.grad) < 2e-3
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 180, 320), (2, 3, 181, 203), (1, 3, 360, 640)])
+def test_ms_ssim_value_and_gradient_incl_odd_sizes(shape):
+    from bnerv_b200 import losses
+    pred, target = _pair(*shape, seed=1)
+    p1 = pred.clone().requires_grad_(True)
+    p2 = pred.clone().requires_grad_(True)
+    v1 = losses.ms_ssim(p1, target, data_range=1, size_average=False)
+    v2 = mo.ms_ssim(p2, target, data_range=1.0, size_average=False)
+    assert max_rel(v1, v2) < 5e-5
+    v1.sum().backward()
+    v2.sum().backward()
+    assert max_rel(p1.grad, p2.grad) < 2e-3
+    assert F.cosine_similarity(p1.grad.flatten().double(), p2.grad.flatten().double(), dim=0).item() > 0.99999
+
+
+@pytest.mark.parametrize("loss_type", ["L2", "L1", "SSIM", "Fusion6", "Fusion9", "Fusion10", "Fusion10_freq", "L1_ssim_freq"])
+def test_loss_fn_matches_the_reference_formulas(loss_type):
+    """hnerv_utils.loss_fn (:335-395) with pytorch_msssim replaced by the restatement."""
+    from bnerv_b200 import losses
+    pred, target = _pair(2, 3, 180, 320, seed=2)
+
+    def ref(p):
+        l1 = F.l1_loss(p, target, reduction="none").flatten(1).mean(1)
+        l2 = F.mse_loss(p, target, reduction="none").flatten(1).mean(1)
+        s1 = 1 - mo.ssim(p, target, 1.0, False)
+        ms = 1 - mo.ms_ssim(p, target, 1.0, False)
+        pf, tf = torch.fft.fft2(p, dim=(-2, -1)), torch.fft.fft2(target, dim=(-2, -1))
+        fr = F.l1_loss(torch.stack([pf.real, pf.imag], -1), torch.stack([tf.real, tf.imag], -1), reduction="none").flatten(1).mean(1)
+        return {"L2": l2, "L1": l1, "SSIM": s1, "Fusion6": 0.7 * l1 + 0.3 * s1, "Fusion9": 0.9 * l1 + 0.1 * s1,
+                "Fusion10": 0.7 * l1 + 0.3 * ms, "Fusion10_freq": 60 * (0.7 * l1 + 0.3 * ms) + fr,
+                "L1_ssim_freq": 60 * (0.7 * l1 + 0.3 * s1) + fr}[loss_type].mean()
+
+    p1 = pred.clone().requires_grad_(True)
+    p2 = pred.clone().requires_grad_(True)
+    a, b = losses.loss_fn(p1, target, loss_type), ref(p2)
+    assert abs(a.item() - b.item()) <= 2e-5 * abs(b.item())
+    a.backward()
+    b.backward()
+    assert max_rel(p1.grad, p2.grad) < 2e-3
+    with pytest.raises(KeyError):
+        losses.loss_fn(pred, target, "nope")

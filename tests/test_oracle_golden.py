@@ -76,3 +76,22 @@ def test_pixel_shuffle_golden_is_the_documented_permutation():
     s, C = 5, Cs // 25
     ref = x.view(B, C, s, s, H, W).permute(0, 1, 4, 2, 5, 3).reshape(B, C, H * s, W * s)   # out[c,hs+i,ws+j]=in[c*s*s+i*s+j,h,w]
     assert torch.equal(ref, y)
+
+
+def test_msssim_restatement_basic_properties():
+    """oracle/msssim_oracle.py restates pytorch_msssim==0.2.1 (parity unpinned: no vectors of the package exist here);
+    what can be checked without it: identity gives exactly 1, the window is normalised, values are symmetric in the
+    luminance/structure terms for swapped arguments, and the 5-level size rule is enforced."""
+    import pytest
+    import torch
+    from oracle import msssim_oracle as mo
+    torch.manual_seed(0)
+    x = torch.rand(2, 3, 176, 200)
+    y = (x + 0.1 * torch.randn_like(x)).clamp(0, 1)
+    assert abs(mo.gauss_1d().sum().item() - 1.0) < 1e-6
+    assert torch.allclose(mo.ssim(x, x), torch.ones(2), atol=1e-6) and torch.allclose(mo.ms_ssim(x, x), torch.ones(2), atol=1e-5)
+    assert torch.allclose(mo.ssim(x, y), mo.ssim(y, x), atol=1e-6)
+    v = mo.ms_ssim(x, y)
+    assert v.shape == (2,) and bool(((v > 0) & (v < 1)).all())
+    with pytest.raises(AssertionError):
+        mo.ms_ssim(x[..., :160, :], y[..., :160, :])
