@@ -1,5 +1,5 @@
-"""Loss forward+backward time at 1080p (batch 1): native SSIM / MS-SSIM kernels (bnerv_b200.losses) vs the torch restatement of
-pytorch_msssim (oracle/msssim_oracle.py run on the GPU - what the reference's loss_fn executes through the package).
+"""Loss forward+backward time at 1080p (batch 1): native SSIM / MS-SSIM kernels (bnerv_b200.losses) vs the torch formulation
+pytorch_msssim executes on the GPU (grouped separable conv2d per moment map, autograd backward).
 Usage: python tools/loss_bench.py"""
 import os
 import sys
@@ -11,7 +11,45 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "boosting-nerv_b200"))
 from bnerv_b200 import losses  # noqa: E402
-from oracle import msssim_oracle as mo  # noqa: E402  (tool = measurement harness, like bench.py's cpu leg)
+
+
+class mo:
+    """The torch formulation pytorch_msssim executes (grouped separable conv2d per moment map), inlined here so that the
+    tool does not import oracle/ (reserved for tests, smoke and bench.py's CPU leg)."""
+    W = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
+
+    @staticmethod
+    def _blur(x, win):
+        c = x.shape[1]
+        w = win.view(1, 1, 1, -1).repeat(c, 1, 1, 1)
+        return F.conv2d(F.conv2d(x, w.transpose(2, -1), groups=c), w, groups=c)
+
+    @staticmethod
+    def _stats(x, y):
+        co = torch.arange(11, dtype=x.dtype, device=x.device) - 5
+        win = torch.exp(-(co ** 2) / (2 * 1.5 ** 2))
+        win = win / win.sum()
+        c1, c2 = 0.01 ** 2, 0.03 ** 2
+        mu1, mu2 = mo._blur(x, win), mo._blur(y, win)
+        s11, s22, s12 = mo._blur(x * x, win) - mu1 * mu1, mo._blur(y * y, win) - mu2 * mu2, mo._blur(x * y, win) - mu1 * mu2
+        cs = (2 * s12 + c2) / (s11 + s22 + c2)
+        return (((2 * mu1 * mu2 + c1) / (mu1 * mu1 + mu2 * mu2 + c1)) * cs).flatten(2).mean(-1), cs.flatten(2).mean(-1)
+
+    @staticmethod
+    def ssim(x, y, data_range=1.0, size_average=False):
+        return torch.relu(mo._stats(x, y)[0]).mean(1)
+
+    @staticmethod
+    def ms_ssim(x, y, data_range=1.0, size_average=False):
+        mcs = []
+        for i in range(5):
+            s, cs = mo._stats(x, y)
+            if i < 4:
+                mcs.append(torch.relu(cs))
+                pad = [sz % 2 for sz in x.shape[2:]]
+                x, y = F.avg_pool2d(x, 2, padding=pad), F.avg_pool2d(y, 2, padding=pad)
+        vals = torch.stack(mcs + [torch.relu(s)], dim=0)
+        return torch.prod(vals ** torch.tensor(mo.W, device=x.device).view(-1, 1, 1), dim=0).mean(1)
 
 torch.manual_seed(0)
 target = torch.rand(1, 3, 1080, 1920, device="cuda")
