@@ -125,3 +125,28 @@ def test_batched_sft_tables_equal_per_layer_affine():
         for blk in eng.blocks:
             for layer in blk.sfts:
                 assert all(p.grad is not None for p in layer.parameters())
+
+
+def test_hnerv_utils_shim_re_exports_the_reference_module_and_overrides_loss_fn(tmp_path):
+    """boosting-nerv_b200/shims/hnerv_utils.py: executes the next hnerv_utils.py on sys.path, keeps every symbol, and
+    routes loss_fn to the device losses for CUDA tensors only."""
+    import importlib
+    import os
+    import sys
+    from conftest import ROOT
+    fake = tmp_path / "hnerv_utils.py"
+    fake.write_text("MARK = 41\n\ndef loss_fn(pred, target, loss_type='L2', batch_average=True):\n    return ('reference', loss_type)\n\n"
+                    "def psnr_fn_single(a, b):\n    return 'psnr'\n")
+    shim_dir = os.path.join(ROOT, "boosting-nerv_b200", "shims")
+    old_path, old_mod = list(sys.path), sys.modules.pop("hnerv_utils", None)
+    try:
+        sys.path[:0] = [shim_dir, str(tmp_path)]
+        mod = importlib.import_module("hnerv_utils")
+        assert mod.MARK == 41 and mod.psnr_fn_single(0, 0) == "psnr"
+        assert mod.loss_fn(torch.zeros(1), torch.zeros(1), "L1") == ("reference", "L1")       # CPU tensors: reference code
+        assert mod.loss_fn is not mod._reference_loss_fn
+    finally:
+        sys.path[:] = old_path
+        sys.modules.pop("hnerv_utils", None)
+        if old_mod is not None:
+            sys.modules["hnerv_utils"] = old_mod
