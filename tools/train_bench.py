@@ -79,19 +79,57 @@ for mode, tf32, label in (("b200", False, "native sm_100a fwd+bwd"), ("torch", T
 
 # HNeRV: the reference trains THROUGH the ConvNeXt encoder (model(frame) -> encoder -> decoder, train_nerv_all.py:342);
 # the encoder stays a torch module, so this is what a full step costs with it in the loop
+def _torch_fusion10_freq(p, target):
+    """The shipped loss (scripts/regression/UVG/hnerv_boost.sh: --loss Fusion10_freq) as the reference computes it:
+    pytorch_msssim's torch formulation (grouped separable conv2d per moment map) + cuFFT."""
+    import torch.nn.functional as F
+    from bnerv_b200 import losses
+
+    def blur(x, win):
+        c = x.shape[1]
+        w = win.view(1, 1, 1, -1).repeat(c, 1, 1, 1)
+        return F.conv2d(F.conv2d(x, w.transpose(2, -1), groups=c), w, groups=c)
+
+    co = torch.arange(11, dtype=p.dtype, device=p.device) - 5
+    win = torch.exp(-(co ** 2) / 4.5)
+    win = win / win.sum()
+    x, y, mcs = p, target, []
+    for i in range(5):
+        mu1, mu2 = blur(x, win), blur(y, win)
+        s11, s22, s12 = blur(x * x, win) - mu1 * mu1, blur(y * y, win) - mu2 * mu2, blur(x * y, win) - mu1 * mu2
+        cs = (2 * s12 + 9e-4) / (s11 + s22 + 9e-4)
+        ss = ((2 * mu1 * mu2 + 1e-4) / (mu1 * mu1 + mu2 * mu2 + 1e-4)) * cs
+        if i < 4:
+            mcs.append(torch.relu(cs.flatten(2).mean(-1)))
+            pad = [sz % 2 for sz in x.shape[2:]]
+            x, y = F.avg_pool2d(x, 2, padding=pad), F.avg_pool2d(y, 2, padding=pad)
+    vals = torch.stack(mcs + [torch.relu(ss.flatten(2).mean(-1))], dim=0)
+    ms = torch.prod(vals ** torch.tensor(losses.WEIGHTS, device=p.device).view(-1, 1, 1), dim=0).mean(1)
+    l1 = F.l1_loss(p, target, reduction="none").flatten(1).mean(1)
+    return (60 * (0.7 * l1 + 0.3 * (1 - ms)) + losses._freq_l1(p, target)).mean()
+
+
 if cfg.startswith("hnerv"):
-    for mode, tf32, label in (("b200", True, "full step incl. torch encoder: native decoder"), ("torch", True, "full step incl. torch encoder: torch decoder (TF32)")):
+    from bnerv_b200 import losses as _losses
+    for mode, tf32, label in (("b200", True, "full step incl. torch encoder: native decoder"), ("torch", True, "full step incl. torch encoder: torch decoder (TF32)"),
+                              ("b200+loss", True, "encoder + native decoder + native Fusion10_freq loss"),
+                              ("torch+loss", True, "encoder + torch decoder + torch Fusion10_freq loss")):
         torch.backends.cudnn.allow_tf32 = tf32
         model, args = bench.build_model(cfg)
         model = model.to(dev).train()
-        model.train_backend = mode
+        model.train_backend = mode.split("+")[0]
         frame = torch.rand(1, 3, 1080, 1920, device=dev)
         t = torch.tensor([0.5], dtype=torch.float64, device=dev)
 
         def step():
             model.zero_grad(set_to_none=True)
             img = model(frame, norm_idx=t)[0]
-            ((img - frame) ** 2).mean().backward()
+            if mode == "b200+loss":
+                _losses.loss_fn(img, frame, "Fusion10_freq").backward()
+            elif mode == "torch+loss":
+                _torch_fusion10_freq(img, frame).backward()
+            else:
+                ((img - frame) ** 2).mean().backward()
 
         try:
             print(f"{label:58s}: {timed(step, steps):8.2f} ms/step", flush=True)
