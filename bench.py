@@ -393,6 +393,12 @@ def run_b200(opt):
             line["train_step"] = train_step_times(opt.config, dev)
         except Exception as ex:  # never let the extra measurement take the metric line down
             line["train_step"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+    if world == 1 and not opt.no_train:
+        # extra: the "library" baseline SURVEY.md §8d asks for - stock PyTorch on this B200 (cuDNN), same module, same frame
+        try:
+            line["library_baseline"] = torch_decode_fps(opt.config, dev)
+        except Exception as ex:
+            line["library_baseline"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
     if world == 1 and not opt.no_others:
         # extra, outside the metric: device-resident decode frames/s of the other BASELINE.json presets (configs 1-2),
         # same timing rules (CUDA-graph replay per frame, CUDA events, 10 warm-up + 200 timed frames)
@@ -436,6 +442,36 @@ def other_preset_fps(name, dev, steps=200, warm=10):
         out["ms_per_frame" + key] = ms
         out["algorithmic_tflops" + key] = ALG_GFLOP[name] / ms
     out["frames_timed"] = steps
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def torch_decode_fps(cfg_name, dev, steps=5):
+    """Decode frames/s of the plain torch forward (model.backend = 'torch': F.conv2d / pixel_shuffle / sin / gelu, i.e. the
+    reference's own ops through cuDNN) on this GPU, TF32 convs allowed (PyTorch's default) and strict fp32."""
+    model, args = build_model(cfg_name)
+    model = model.to(dev).eval()
+    model.backend = "torch"
+    is_h = args.model == "HNeRV_Boost"
+    fh, fw = [int(v) for v in args.fc_hw.split("_")]
+    emb = torch.rand(1, 16, fh, fw, device=dev) if is_h else None
+    t = torch.tensor([0.5], dtype=torch.float64, device=dev)
+    out = {"what": "plain torch forward of the same module on this GPU (cuDNN), batch 1, frames/s"}
+    for tf32, key in ((True, "torch_cudnn_tf32"), (False, "torch_fp32")):
+        torch.backends.cudnn.allow_tf32 = tf32
+        with torch.no_grad():
+            for _ in range(2):
+                model.forward_decoder(emb, t) if is_h else model(t)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                model.forward_decoder(emb, t) if is_h else model(t)
+            e1.record()
+            torch.cuda.synchronize()
+        out[key] = 1e3 * steps / e0.elapsed_time(e1)
+    torch.backends.cudnn.allow_tf32 = True
     del model
     torch.cuda.empty_cache()
     return out
