@@ -127,19 +127,31 @@ __global__ void mid_bwd_kernel(const __half* __restrict__ dw, const __half* __re
     float acc[24];
 #pragma unroll
     for (int k = 0; k < 24; ++k) acc[k] = 0.0f;
-    for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < hw; p += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        float a[8], vv[8], d[8], o[8];
-        unpack8(reinterpret_cast<const uint4*>(dw)[base + p], a);
-        unpack8(reinterpret_cast<const uint4*>(v)[base + p], vv);
-        unpack8(reinterpret_cast<const uint4*>(dact)[base + p], d);
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;        // two pixels per iteration, see front_bwd_kernel
+    for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < hw; p += 2 * stride) {
+        const size_t p2 = p + stride;
+        const bool two = p2 < hw;
+        const size_t q = two ? p2 : p;
+        const uint4 ua0 = reinterpret_cast<const uint4*>(dw)[base + p], uv0 = reinterpret_cast<const uint4*>(v)[base + p];
+        const uint4 ud0 = reinterpret_cast<const uint4*>(dact)[base + p];
+        const uint4 ua1 = reinterpret_cast<const uint4*>(dw)[base + q], uv1 = reinterpret_cast<const uint4*>(v)[base + q];
+        const uint4 ud1 = reinterpret_cast<const uint4*>(dact)[base + q];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            o[k] = a[k] * gg[k] * d[k];
-            acc[k] += a[k] * vv[k];
-            acc[8 + k] += a[k];
-            acc[16 + k] += o[k];
+        for (int it = 0; it < 2; ++it) {
+            if (it == 1 && !two) break;
+            float a[8], vv[8], d[8], o[8];
+            unpack8(it ? ua1 : ua0, a);
+            unpack8(it ? uv1 : uv0, vv);
+            unpack8(it ? ud1 : ud0, d);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                o[k] = a[k] * gg[k] * d[k];
+                acc[k] += a[k] * vv[k];
+                acc[8 + k] += a[k];
+                acc[16 + k] += o[k];
+            }
+            reinterpret_cast<uint4*>(dc0)[base + (it ? p2 : p)] = pack8f(o);
         }
-        reinterpret_cast<uint4*>(dc0)[base + p] = pack8f(o);
     }
     float* const pG = dG + static_cast<size_t>(b) * cp + g * 8;
     float* const pB = dB + static_cast<size_t>(b) * cp + g * 8;
@@ -167,21 +179,35 @@ __global__ void front_bwd_kernel(const __half* __restrict__ du, const __half* __
     float acc[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) acc[k] = 0.0f;
-    for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < hw; p += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        float a[8], e[8], xx[8], d[8], o[8];
-        unpack8(reinterpret_cast<const uint4*>(du)[base + p], a);
-        unpack8(reinterpret_cast<const uint4*>(dout)[base + p], e);
-        unpack8(reinterpret_cast<const uint4*>(x0)[base + p], xx);
-        unpack8(reinterpret_cast<const uint4*>(dact)[base + p], d);
+    // two pixels per iteration: all eight 16-byte loads are in flight before the first is consumed (the one-pixel loop
+    // left ~50 KB per SM in flight, about the HBM latency-bandwidth product: 60 % of the copy bandwidth)
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < hw; p += 2 * stride) {
+        const size_t p2 = p + stride;
+        const bool two = p2 < hw;
+        const size_t q = two ? p2 : p;
+        const uint4 ua0 = reinterpret_cast<const uint4*>(du)[base + p], ue0 = reinterpret_cast<const uint4*>(dout)[base + p];
+        const uint4 ux0 = reinterpret_cast<const uint4*>(x0)[base + p], ud0 = reinterpret_cast<const uint4*>(dact)[base + p];
+        const uint4 ua1 = reinterpret_cast<const uint4*>(du)[base + q], ue1 = reinterpret_cast<const uint4*>(dout)[base + q];
+        const uint4 ux1 = reinterpret_cast<const uint4*>(x0)[base + q], ud1 = reinterpret_cast<const uint4*>(dact)[base + q];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            o[k] = (e[k] + a[k] * gg[k]) * d[k];
-            acc[k] += a[k] * xx[k];
-            acc[8 + k] += a[k];
-            acc[16 + k] += e[k];
-            acc[24 + k] += o[k];
+        for (int it = 0; it < 2; ++it) {
+            if (it == 1 && !two) break;
+            float a[8], e[8], xx[8], d[8], o[8];
+            unpack8(it ? ua1 : ua0, a);
+            unpack8(it ? ue1 : ue0, e);
+            unpack8(it ? ux1 : ux0, xx);
+            unpack8(it ? ud1 : ud0, d);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                o[k] = (e[k] + a[k] * gg[k]) * d[k];
+                acc[k] += a[k] * xx[k];
+                acc[8 + k] += a[k];
+                acc[16 + k] += e[k];
+                acc[24 + k] += o[k];
+            }
+            reinterpret_cast<uint4*>(dy)[base + (it ? p2 : p)] = pack8f(o);
         }
-        reinterpret_cast<uint4*>(dy)[base + p] = pack8f(o);
     }
     float* const pG = dG + static_cast<size_t>(b) * cp + g * 8;
     float* const pB = dB + static_cast<size_t>(b) * cp + g * 8;
