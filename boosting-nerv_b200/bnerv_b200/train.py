@@ -293,6 +293,7 @@ class _TrainGraph:
         _backward_body(eng, lay, st, torch.zeros_like(img), need_x, False)
         del st, img
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()                # the warm-up's maps would otherwise stay cached next to the graph's private pool
         self.gf = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.gf, capture_error_mode="thread_local"):
             self.img, self.first, self.st = _forward_body(eng, lay, self.x, self.scale, self.shift, True)
