@@ -11,7 +11,11 @@ same three steps run as a three-stage pipeline on two streams:
 with `depth` staging slots guarded by events, so frame i's read-back overlaps frame i+1's decode.  Results are
 bit-identical to model.forward()/forward_decoder() frame by frame (same graph, same kernels).
 """
+import weakref
+
 import torch
+
+_COPY_STREAMS = weakref.WeakKeyDictionary()
 
 
 def decode_to_host(model, norm_idx_host, out_host, embed_host=None, batch=1, depth=3, ring=False):
@@ -31,10 +35,9 @@ def decode_to_host(model, norm_idx_host, out_host, embed_host=None, batch=1, dep
     assert (slots == n or (ring and slots % batch == 0 and slots > 0)) and (embed_host is None or embed_host.shape[0] == n)
     is_h = embed_host is not None
     compute = torch.cuda.current_stream(dev)
-    state = model.__dict__.setdefault("_stream_state", {})
-    copy = state.get("copy")
+    copy = _COPY_STREAMS.get(model)              # kept outside the module: deepcopy(model) must stay a plain parameter copy
     if copy is None or copy.device != dev:
-        copy = state["copy"] = torch.cuda.Stream(dev)
+        copy = _COPY_STREAMS[model] = torch.cuda.Stream(dev)
     stages, ready, done = {}, {}, {}
     with torch.no_grad():
         for j, lo in enumerate(range(0, n, batch)):

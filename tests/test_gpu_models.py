@@ -209,6 +209,10 @@ def test_decode_to_host_pipeline_is_bitwise_the_per_frame_api(model):
             assert torch.equal(out, ref)
     with pytest.raises(ValueError):
         decode_to_host(m, t.cuda(), out, emb)
+    m2 = copy.deepcopy(m)                        # the reference deep-copies models (train_nerv_all.py:623): no stream / graph state inside
+    out2 = torch.empty_like(out)
+    decode_to_host(m2, t, out2, emb)
+    assert torch.equal(out2, ref)
 
 
 def test_evaluate_psnr_matches_per_frame_reference_formula():
