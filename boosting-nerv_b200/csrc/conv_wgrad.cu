@@ -54,6 +54,8 @@ struct WgradArgs {
     int rep_bytes;       // bytes of one replica
     int n_mma;           // UMMA N
     int tap_cols;        // accumulator columns per tap
+    int swapped;         // 1: operands exchanged (A = X, B = dY shifted), results written transposed with mirrored taps
+    int out_mp, out_cinp;   // the caller's M_p / Cin_p (layout of acc) in swapped mode
     float* acc;          // [taps][M_p][Cin_p] f32, accumulated into
 };
 
@@ -209,7 +211,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                     uint32_t v[16];
                     tmem_ld16(taddr + s * a.tap_cols + g, v);    // warp-collective: every lane takes part
                     tmem_ld_wait();
-                    if (mch < a.m_p && c0 + g < a.cin_p) {
+                    if (a.swapped) {
+                        // this thread's row is an X channel, its columns are gradient channels of tap' = 8 - tap
+                        if (mch < a.out_cinp && g < a.out_mp) {
+                            float* col = a.acc + (static_cast<size_t>(a.taps - 1 - tap) * a.out_mp + g) * a.out_cinp + mch;
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) atomicAdd(col + static_cast<size_t>(k) * a.out_cinp, __uint_as_float(v[k]));
+                        }
+                    } else if (mch < a.m_p && c0 + g < a.cin_p) {
 #pragma unroll
                         for (int k = 0; k < 16; k += 4)
                             red_add_v4(row + g + k, __uint_as_float(v[k]), __uint_as_float(v[k + 1]),
@@ -300,6 +309,19 @@ extern "C" int bnerv_conv_wgrad(const void* x, const void* dy, int B, int Cin, i
     a.r_jobs = k;
     a.m_p = M_p; a.m_groups = M_p / 8;
     a.cin_p = round_up(Cin, 16); a.c_groups = a.cin_p / 8;
+    // A conv to very few channels (the 3x3 head: M_p = 16) would spend a full M = 128, N = Cin_p UMMA per tap on 16 useful
+    // rows.  Exchange the operands instead: D'[c, m] of tap' = sum_p X[p, c] dY[p + tap', m] equals the wanted
+    // D[m, c] of tap = 8 - tap' (substitute q = p + tap'), the narrow dY becomes the tap-stacked N operand
+    // (N = 3 * 16 per kernel row, all rows in one job) and the epilogue writes the transpose with mirrored taps.
+    static const bool no_swap = getenv("BNERV_WGRAD_NO_SWAP") != nullptr;        // A/B switch
+    a.out_mp = a.m_p; a.out_cinp = a.cin_p;
+    a.swapped = (k == 3 && M_p <= 16 && a.cin_p >= 64 && !no_swap) ? 1 : 0;
+    if (a.swapped) {
+        const void* tmp = x; x = dy; dy = tmp;
+        a.m_p = a.out_cinp; a.m_groups = a.m_p / 8;
+        a.cin_p = a.out_mp; a.c_groups = a.cin_p / 8;
+        M_p = a.m_p;
+    }
     const int nc_max = 160;                   // T * nc <= 512 TMEM columns with T = 3
     a.c_chunks = (a.cin_p + nc_max - 1) / nc_max;
     a.nc = round_up((a.cin_p + a.c_chunks - 1) / a.c_chunks, 16);

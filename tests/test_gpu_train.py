@@ -37,6 +37,8 @@ WGRAD_CASES = [  # B, cin, cout, H, W, k, s
     (1, 16, 16, 8, 16, 1, 1), (1, 16, 16, 8, 16, 3, 1), (2, 21, 43, 19, 37, 3, 1), (1, 176, 162, 24, 40, 3, 1),
     (1, 43, 21, 10, 18, 3, 2), (1, 40, 33, 9, 16, 1, 5), (1, 200, 60, 6, 8, 3, 5), (1, 3, 5, 1, 1, 3, 1),
     # narrow layers: column taps stacked in N (Cin_p <= 80), all kernel rows in one job (Cin_p <= 48) or three jobs
+    # conv to very few channels (the 3x3 head): operands exchanged, transposed write-back with mirrored taps
+    (1, 112, 3, 37, 53, 3, 1), (2, 64, 10, 18, 40, 3, 1), (1, 200, 16, 9, 16, 3, 1),
     (2, 12, 12, 45, 70, 3, 1), (1, 30, 15, 23, 41, 3, 2), (1, 48, 130, 17, 33, 3, 1), (1, 64, 20, 20, 50, 3, 1), (1, 80, 80, 9, 16, 3, 1),
 ]
 
