@@ -37,6 +37,26 @@ METRIC = "decode frames/sec @1920x1080"
 ALG_GFLOP = {"hnerv_l": 4429.9, "enerv_m": 443.3, "nerv_s": 19.33, "nerv_xs": 19.04, "hnerv_m": 2782.0}
 
 
+def algorithmic_gflop(name, model=None, args=None):
+    """SURVEY.md §8d figure for the tabulated presets, else the same sum (2*Cout*s^2*Cin*k^2*H*W over the cascade's
+    convs, unpadded channels) computed from the model's conv list."""
+    if name in ALG_GFLOP:
+        return ALG_GFLOP[name]
+    from bnerv_b200.engine import DecoderEngine
+    if model is None:
+        model, args = build_model(name)
+    eng = DecoderEngine(model)
+    H, W = [int(v) for v in args.fc_hw.split("_")]
+    tot = 0.0
+    for blk in eng.blocks:
+        for slot in ([blk.pre] if blk.pre is not None else []) + [blk.up]:
+            tot += 2.0 * slot.cout * slot.s ** 2 * slot.cin * slot.k ** 2 * H * W
+            H, W = H * slot.s, W * slot.s
+        tot += 2 * (2.0 * blk.cout * blk.cout * 9 * H * W)
+    tot += 2.0 * eng.head.cout * eng.head.cin * eng.head.k ** 2 * H * W
+    return tot / 1e9
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,7 +351,7 @@ def run_b200(opt):
     pk, pk_src = peaks()
     frames = world * K * B
     value = frames / (ms / 1e3)
-    alg_gflop = ALG_GFLOP.get(opt.config)
+    alg_gflop = algorithmic_gflop(opt.config, model, args)
     peak_tf = pk["bf16_tflops_sustained"]       # kernel timed inside a long step -> sustained figure
     ach_tf = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
     traffic, traffic_note, alg_bytes = None, None, None
@@ -440,7 +460,7 @@ def other_preset_fps(name, dev, steps=200, warm=10):
         key = "" if B == 1 else f"_batch{B}"
         out["frames_per_s" + key] = 1e3 / ms
         out["ms_per_frame" + key] = ms
-        out["algorithmic_tflops" + key] = ALG_GFLOP[name] / ms
+        out["algorithmic_tflops" + key] = algorithmic_gflop(name, model, args) / ms
     out["frames_timed"] = steps
     del model
     torch.cuda.empty_cache()

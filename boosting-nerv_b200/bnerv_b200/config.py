@@ -62,6 +62,8 @@ def preset(name):
         return make_args("NeRV_Boost", 0.375, 640, 1280, 64, fc_hw="8_16")
     if name == "nerv_s":       # C2: NeRV-Boost 1.5M, 132 frames
         return make_args("NeRV_Boost", 0.8, 720, 1280, 132)
+    if name == "nerv_s_640":   # C2 at the literal 640x1280 of BASELINE.json (--fc_hw 8_16)
+        return make_args("NeRV_Boost", 0.8, 640, 1280, 132, fc_hw="8_16")
     if name == "enerv_m":      # C3: E-NeRV-Boost 10M, UVG 1080p (scripts/regression/UVG/enerv_boost.sh)
         return make_args("ENeRV_Boost", 4.3, 1080, 1920, 600, dec_strds=[5, 3, 2, 2, 2])
     if name == "hnerv_l":      # C4/C5: HNeRV-Boost 15M, UVG 1080p (scripts/regression/UVG/hnerv_boost.sh)
