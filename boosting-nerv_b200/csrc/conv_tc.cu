@@ -903,11 +903,14 @@ static int launch_conv_n(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     BNERV_PICK(12, BNERV_ACT_NONE, F_PRE)                       // dgrad
     BNERV_PICK(13, BNERV_ACT_TANH01, F_NCHW | F_HEAD)           // 3x3 head conv, 1x1-contraction + shift-sum form
 #undef BNERV_PICK
-    static bool smem_set[16] = {};
-    if (!smem_set[slot]) {
+    static bool smem_set_dev[16][32] = {};          // function attributes are per device (context)
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool& smem_set_flag = smem_set_dev[slot][cur_dev & 31];
+    if (!smem_set_flag) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return set_error(static_cast<int>(e), "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
-        smem_set[slot] = true;
+        smem_set_flag = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * a.n_pairs);

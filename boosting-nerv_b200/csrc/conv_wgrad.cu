@@ -384,7 +384,10 @@ extern "C" int bnerv_conv_wgrad(const void* x, const void* dy, int B, int Cin, i
     if (per_job > a.tiles) per_job = a.tiles;
     int grid = per_job >= 1 ? per_job * a.jobs : num_sms;
     const size_t smem_bytes = static_cast<size_t>(a.stages) * a.stage_bytes + WG_BAR_BYTES;
-    static bool attr_set = false;
+    static bool attr_set_dev[32] = {};              // function attributes are per device (context)
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    bool& attr_set = attr_set_dev[cur_dev & 31];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_LIMIT);
         if (e != cudaSuccess) return set_error(static_cast<int>(e), "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));

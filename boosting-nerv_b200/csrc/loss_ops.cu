@@ -187,7 +187,12 @@ __global__ void __launch_bounds__(SS_THREADS) ssim_grad_kernel(const float* __re
 }
 
 static int upload_window(float sigma) {
-    static float cur = -1.0f;
+    static float cur_dev[32];                       // __constant__ memory is per device
+    static bool init = false;
+    if (!init) { for (float& v : cur_dev) v = -1.0f; init = true; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    float& cur = cur_dev[dev & 31];
     if (cur == sigma) return 0;
     float g[SS_WIN];
     double sum = 0.0;
