@@ -247,10 +247,7 @@ class DecoderEngine:
         inputs = tuple(inputs)
         if not inputs[0].is_cuda:
             raise RuntimeError("bnerv_b200 engine needs CUDA tensors (no CPU path)")
-        with torch.cuda.device(inputs[0].device):       # the C-ABI launches on the CURRENT device's stream
-            return self._decode(inputs, keep, check_weights)
-
-    def _decode(self, inputs, keep, check_weights):
+        ops.require_current_device(inputs[0].device)
         if not self.use_graph:
             return self._body(inputs, keep)
         if check_weights:

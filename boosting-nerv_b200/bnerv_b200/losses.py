@@ -48,12 +48,12 @@ class _SsimStats(torch.autograd.Function):
         c1, c2 = (K1 * data_range) ** 2, (K2 * data_range) ** 2
         x, y = pred.detach().float().contiguous(), target.detach().float().contiguous()
         pyr, out = [], []
-        with torch.cuda.device(pred.device):         # the C-ABI launches on the CURRENT device's stream
-            for lv in range(levels):
-                pyr.append((x, y))
-                out.append(_stats_level(x, y, c1, c2))
-                if lv < levels - 1:
-                    x, y = _pool(x).contiguous(), _pool(y).contiguous()
+        ops.require_current_device(pred.device)
+        for lv in range(levels):
+            pyr.append((x, y))
+            out.append(_stats_level(x, y, c1, c2))
+            if lv < levels - 1:
+                x, y = _pool(x).contiguous(), _pool(y).contiguous()
         ctx.pyr, ctx.c = pyr, (c1, c2)
         return torch.stack(out)
 

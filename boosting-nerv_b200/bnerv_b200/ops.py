@@ -22,6 +22,18 @@ def _need_cuda(*tensors):
             raise RuntimeError("bnerv_b200 ops need CUDA tensors (no CPU path)")
 
 
+def require_current_device(dev):
+    """The C-ABI launches on the CURRENT device's stream (one process per GPU, as torchrun / DistributedDataParallel run
+    it); a tensor on another device would be dereferenced on the wrong GPU, so refuse it loudly."""
+    if dev.type != "cuda":
+        raise RuntimeError("bnerv_b200 needs CUDA tensors (no CPU path)")
+    cur = torch.cuda.current_device()
+    idx = cur if dev.index is None else dev.index
+    if idx != cur:
+        raise RuntimeError(f"bnerv_b200: tensors live on cuda:{idx} but the current device is cuda:{cur}; call "
+                           f"torch.cuda.set_device({idx}) first (one process per GPU)")
+
+
 def round_up(x, m):
     return (x + m - 1) // m * m
 

@@ -34,11 +34,6 @@ def decode_to_host(model, norm_idx_host, out_host, embed_host=None, batch=1, dep
     slots = out_host.shape[0]
     assert (slots == n or (ring and slots % batch == 0 and slots > 0)) and (embed_host is None or embed_host.shape[0] == n)
     is_h = embed_host is not None
-    with torch.cuda.device(dev):
-        return _decode_to_host(model, norm_idx_host, out_host, embed_host, batch, depth, dev, n, slots, is_h)
-
-
-def _decode_to_host(model, norm_idx_host, out_host, embed_host, batch, depth, dev, n, slots, is_h):
     compute = torch.cuda.current_stream(dev)
     copy = _COPY_STREAMS.get(model)              # kept outside the module: deepcopy(model) must stay a plain parameter copy
     if copy is None or copy.device != dev:
@@ -84,7 +79,7 @@ def evaluate_psnr(model, norm_idx_host, gt_host, embed_host=None, batch=1):
     assert gt_host.shape[0] == n and gt_host.dtype == torch.float32
     is_h = embed_host is not None
     total = torch.zeros((), dtype=torch.float64, device=dev)
-    with torch.no_grad(), torch.cuda.device(dev):
+    with torch.no_grad():
         for lo in range(0, n, batch):
             sl = slice(lo, min(lo + batch, n))
             gt = gt_host[sl].to(dev, non_blocking=True)

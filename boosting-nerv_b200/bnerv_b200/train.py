@@ -355,11 +355,7 @@ def cascade_train(eng, x, cond):
     Returns (img [B,3,H,W] f32, first block output NCHW f32 (non-differentiable))."""
     if not x.is_cuda:
         raise RuntimeError("bnerv_b200 native training needs CUDA tensors (no CPU path)")
-    with torch.cuda.device(x.device):                # the C-ABI launches on the CURRENT device's stream
-        return _cascade_train(eng, x, cond)
-
-
-def _cascade_train(eng, x, cond):
+    ops.require_current_device(x.device)
     B = x.shape[0]
     lays = eng.__dict__.setdefault("_train_layouts", {})
     lay = lays.get(B)

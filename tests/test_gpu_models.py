@@ -230,3 +230,13 @@ def test_evaluate_psnr_matches_per_frame_reference_formula():
     ref = (-10 * torch.log10(((imgs - gt) ** 2).flatten(1).mean(1) + 1e-9)).mean().item()       # psnr_fn_single, averaged
     got, cnt = evaluate_psnr(m, t, gt, emb, batch=2)
     assert cnt == n and abs(got - ref) < 1e-4
+
+
+def test_tensors_on_a_non_current_device_are_refused_not_dereferenced():
+    """One process per GPU: the C-ABI launches on the current device's stream, so a model on another device must raise."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    m, a = _build("NeRV_Boost")
+    m = m.to("cuda:1")
+    with torch.no_grad(), pytest.raises(RuntimeError, match="current device"):
+        m(torch.tensor([0.5], dtype=torch.float64, device="cuda:1"))
