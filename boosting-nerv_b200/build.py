@@ -16,12 +16,22 @@ FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=s
          "-std=c++17", "--cudart", "static"]
 
 
+def _source_hash():
+    """Content hash of everything the library is built from (mtimes do not survive a snapshot copy to another box)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(FLAGS + SOURCES).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "bnerv_b200.h")]
+    for d in deps:
+        with open(d, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(LIB + ".srchash"):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "bnerv_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(LIB + ".srchash") as fh:
+        return fh.read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
@@ -34,6 +44,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+    with open(LIB + ".srchash", "w") as fh:
+        fh.write(_source_hash())
     return LIB
 
 
