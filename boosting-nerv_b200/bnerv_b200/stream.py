@@ -70,6 +70,12 @@ def evaluate_psnr(model, norm_idx_host, gt_host, embed_host=None, batch=1):
     copied H2D ahead of the decode, mse/psnr come from `bnerv_frame_metrics` on the device (psnr_fn_single,
     hnerv_utils.py:400-403), the per-frame values are summed on the device and ONE all_reduce(SUM) of (sum, count)
     runs at the end (hnerv_utils.py:213-229) when torch.distributed is initialised.  Returns (mean_psnr, n_frames_total)."""
+    return evaluate_metrics(model, norm_idx_host, gt_host, embed_host, batch, with_msssim=False)[:2]
+
+
+def evaluate_metrics(model, norm_idx_host, gt_host, embed_host=None, batch=1, with_msssim=True):
+    """evaluate_psnr plus the mean MS-SSIM (msssim_fn_single, hnerv_utils.py:406-408) from the device kernels of
+    bnerv_b200.losses.  Returns (mean_psnr, n_frames_total, mean_msssim or None); one all_reduce per metric."""
     from . import ops
     from .shard import reduce_metric
     dev = next(model.parameters()).device
@@ -78,12 +84,19 @@ def evaluate_psnr(model, norm_idx_host, gt_host, embed_host=None, batch=1):
     n = norm_idx_host.shape[0]
     assert gt_host.shape[0] == n and gt_host.dtype == torch.float32
     is_h = embed_host is not None
-    total = torch.zeros((), dtype=torch.float64, device=dev)
+    total = torch.zeros(2, dtype=torch.float64, device=dev)
+    if with_msssim:
+        from .losses import ms_ssim
     with torch.no_grad():
         for lo in range(0, n, batch):
             sl = slice(lo, min(lo + batch, n))
             gt = gt_host[sl].to(dev, non_blocking=True)
             t = norm_idx_host[sl].to(dev, non_blocking=True)
             img = model.decode(embed_host[sl].to(dev, non_blocking=True), t) if is_h else model.decode(t)
-            total += ops.frame_metrics(img, gt)[:, 2].double().sum()
-    return reduce_metric(total.item(), n, device=dev)
+            total[0] += ops.frame_metrics(img, gt)[:, 2].double().sum()
+            if with_msssim:
+                total[1] += ms_ssim(img, gt, data_range=1, size_average=False).double().sum()
+    sums = total.tolist()
+    psnr, cnt = reduce_metric(sums[0], n, device=dev)
+    msssim = reduce_metric(sums[1], n, device=dev)[0] if with_msssim else None
+    return psnr, cnt, msssim

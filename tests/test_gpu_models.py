@@ -240,3 +240,22 @@ def test_tensors_on_a_non_current_device_are_refused_not_dereferenced():
     m = m.to("cuda:1")
     with torch.no_grad(), pytest.raises(RuntimeError, match="current device"):
         m(torch.tensor([0.5], dtype=torch.float64, device="cuda:1"))
+
+
+def test_evaluate_metrics_psnr_and_msssim():
+    """evaluate_metrics: mean PSNR + mean MS-SSIM over a frame list, against the per-frame formulas (MS-SSIM: the
+    restated pytorch_msssim, parity unpinned) on the frames the per-frame API returns."""
+    from bnerv_b200 import evaluate_metrics
+    from oracle import msssim_oracle as mo
+    torch.manual_seed(6)
+    m, a = _build("NeRV_Boost", tiny_args("NeRV_Boost", fc_dim=15, fc_hw="9_16", dec_strds=[5, 2, 2], dec_blks=[1, 1, 2], lower_width=12))
+    m = m.cuda()
+    n = 3
+    t = torch.tensor([(i + 1) / n for i in range(n)], dtype=torch.float64).pin_memory()
+    gt = torch.rand(n, 3, 180, 320).pin_memory()
+    with torch.no_grad():
+        imgs = torch.cat([m(t[i:i + 1].cuda())[0].cpu() for i in range(n)])
+    ref_psnr = (-10 * torch.log10(((imgs - gt) ** 2).flatten(1).mean(1) + 1e-9)).mean().item()
+    ref_ms = mo.ms_ssim(imgs, gt, 1.0, False).mean().item()
+    psnr, cnt, ms = evaluate_metrics(m, t, gt, None, batch=2)
+    assert cnt == n and abs(psnr - ref_psnr) < 1e-4 and abs(ms - ref_ms) < 1e-5
