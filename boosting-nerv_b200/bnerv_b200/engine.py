@@ -44,6 +44,7 @@ class _ConvSlot:
         self.m, self.k, self.s = module, k, s
         self.cin, self.cout = module.in_channels, module.out_channels // (s * s)
         self.key, self.pc = None, None
+        self.dkey, self.pd = None, None          # dgrad packing of the same weights (training path, train.py)
         # HNeRV's 3x3 head to 3 channels has its own kernel form (bnerv_head_conv3); BNERV_NO_HEAD_KERNEL=1 = generic path
         self.head3 = bool(head and k == 3 and self.cout <= 3 and not os.environ.get("BNERV_NO_HEAD_KERNEL"))
         # NeRV / E-NeRV's 1x1 head: HBM-bound CUDA-core kernel (bnerv_head_conv1)

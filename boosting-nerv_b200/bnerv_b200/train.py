@@ -117,9 +117,9 @@ def _table(t, cp, plus_one):
 def _dgrad_pack(slot, force):
     w, _ = effective_weight(slot.m)
     key = (id(w), w._version, w.data_ptr())
-    if getattr(slot, "pd", None) is None:
+    if slot.pd is None:
         slot.pd = ops.PackedDgrad(w, slot.s)
-    elif force or getattr(slot, "dkey", None) != key:
+    elif force or slot.dkey != key:
         slot.pd.repack(w)
     slot.dkey = key
     return slot.pd
@@ -337,7 +337,7 @@ class _CascadeGraphFn(torch.autograd.Function):
         return _unpack_grads(lay, ctx.needs_input_grad, gx, tg.gscale.clone(), tg.gshift.clone(), tg.gconv.clone())
 
 
-def _graph_key(lay, x, tensors):
+def _graph_key(lay, x):
     """Shapes + parameter storage: a captured graph bakes device pointers of the weights it packs."""
     key = [tuple(x.shape), bool(x.requires_grad)]
     for t in lay.conv_tensors():
@@ -364,7 +364,7 @@ def cascade_train(eng, x, cond):
     scale_all, shift_all = lay.sft_tables(cond)
     tensors = lay.conv_tensors()
     if getattr(eng, "train_graph", True):
-        key = _graph_key(lay, x, tensors)
+        key = _graph_key(lay, x)
         if key is not None:
             graphs = eng.__dict__.setdefault("_train_graphs", {})
             tg = graphs.get(key)
