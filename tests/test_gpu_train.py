@@ -245,7 +245,8 @@ def test_short_fit_tracks_torch_and_trained_weights_decode_parity():
     lt, ln = final["torch"], final["b200"]
     assert ln[-1] < 0.25 * ln[0]                                   # it learns
     assert abs(ln[10] - lt[10]) < 0.02 * lt[10]                    # early trajectory identical to 2 %
-    assert abs(ln[-1] - lt[-1]) < 0.5 * lt[-1]                     # late trajectory: same regime (optimisation is chaotic)
+    assert 0.5 * lt[-1] < ln[-1] < 2.0 * lt[-1]                    # late trajectory: same regime (optimisation is chaotic,
+                                                                   # and the f32 atomics of the reductions are unordered)
 
 
 def test_native_training_refuses_cpu_fallback_semantics():
