@@ -22,6 +22,8 @@ EXPORTS = [
     "bnerv_unshuffle_c8", "bnerv_pack_conv_weight_q", "bnerv_frame_metrics", "bnerv_frame_metrics_scratch_doubles",
     "bnerv_pack_head_weight", "bnerv_head_conv3", "bnerv_nerv_block_fwd", "bnerv_head_conv1",
     "bnerv_ssim_stats", "bnerv_ssim_grad", "bnerv_ssim_scratch_floats",
+    # post-training quantisation + Huffman statistics (ABI version 3)
+    "bnerv_ptq_plan_tensor", "bnerv_ptq_quant_tensor", "bnerv_histogram_u8", "bnerv_huffman_code_lengths",
 ]
 
 
@@ -36,6 +38,16 @@ class SftLayer(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("ws0", "bs0", "ws1", "bs1", "wh0", "bh0", "wh1", "bh1", "g1p", "beta")] + \
                [("C", ctypes.c_int), ("Cp", ctypes.c_int)]
+
+
+PTQ_MAX_CAND = 5
+
+
+class PtqPlan(ctypes.Structure):
+    """struct bnerv_ptq_plan"""
+    _fields_ = [("n_cand", ctypes.c_int32), ("axis", ctypes.c_int32 * PTQ_MAX_CAND), ("groups", ctypes.c_int64 * PTQ_MAX_CAND),
+                ("table_offset", ctypes.c_int64 * PTQ_MAX_CAND), ("table_floats", ctypes.c_int64),
+                ("scratch_doubles", ctypes.c_int64)]
 
 
 def _load():
@@ -62,6 +74,10 @@ def _load():
     lib.bnerv_ssim_grad.argtypes = [vp, vp, i, i, i, f, f, vp, vp, i, vp, vp]
     lib.bnerv_ssim_scratch_floats.argtypes = [i, i, i]
     lib.bnerv_ssim_scratch_floats.restype = ctypes.c_size_t
+    lib.bnerv_ptq_plan_tensor.argtypes = [vp, i, ctypes.POINTER(PtqPlan)]
+    lib.bnerv_ptq_quant_tensor.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp]
+    lib.bnerv_histogram_u8.argtypes = [vp, ctypes.c_size_t, vp, vp]
+    lib.bnerv_huffman_code_lengths.argtypes = [vp, i, vp]
     lib.bnerv_conv_fused_ex.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.bnerv_head_bwd.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp]
     lib.bnerv_pack_conv_weight_dgrad.argtypes = [vp, i, i, i, i, vp, vp]

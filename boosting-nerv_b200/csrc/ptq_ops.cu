@@ -1,0 +1,343 @@
+// Post-training quantisation of the decoder's tensors and the symbol statistics of the Huffman stage
+// (the on-disk format either side of the decode path).
+//
+//   bnerv_ptq_quant_tensor   quant_tensor, hnerv_utils.py:101-134: min/max tables for the whole tensor and for every
+//                            axis longer than 50, round-to-nearest codes, reconstruction, mean |error| per candidate,
+//                            best candidate chosen ON THE DEVICE (no host round trip between the passes)
+//   bnerv_histogram_u8       np.unique(quant_v_list, return_counts=True), train_nerv_all.py:592-593, without the
+//                            .tolist() of every code
+//   bnerv_huffman_code_lengths  HuffmanCodec.from_data(...).get_code_table() bit sizes, train_nerv_all.py:596-599
+//                            (dahuffman 0.4.1's heap construction incl. its EOF leaf) - host code, <= 4096 symbols
+//
+// Arithmetic is the reference's, operation by operation, in round-to-nearest f32 intrinsics that nvcc never contracts
+// into FMAs, so codes, tables and reconstructions are bit-identical to the torch CPU result.  All kernels are one-pass
+// HBM-bound sweeps; the whole job of a 15 M parameter model is a few hundred launches of a few microseconds.
+#include <algorithm>
+#include <vector>
+#include "common.cuh"
+
+namespace bnerv {
+
+static constexpr int PTQ_ERR_BLOCKS = 592;            // 148 SMs x 4 resident blocks of 256 threads
+static constexpr long long PTQ_TARGET_THREADS = 148LL * 2048;
+static constexpr int PTQ_BLOCK_MODE_BELOW = 1024;     // fewer groups than this: one block per (group, split)
+
+// A candidate's view of the tensor: element (o, a, i) lives at (o*A + a)*inner + i and belongs to group o*inner + i
+// (axis candidates: A = t.shape[axis]; whole tensor: outer = inner = 1, A = numel).
+struct PtqView {
+    unsigned outer, A, inner;
+};
+
+struct PtqCandSet {
+    int n;
+    PtqView view[BNERV_PTQ_MAX_CAND];
+    long long table_off[BNERV_PTQ_MAX_CAND];
+    long long groups[BNERV_PTQ_MAX_CAND];
+};
+
+static int splits_for(long long G, long long A) {
+    if (G >= PTQ_BLOCK_MODE_BELOW) return static_cast<int>(std::min<long long>(A, (PTQ_TARGET_THREADS + G - 1) / G));
+    const long long want = std::max<long long>(1, (PTQ_ERR_BLOCKS + G - 1) / G);
+    return static_cast<int>(std::max<long long>(1, std::min<long long>((A + 2047) / 2048, want)));
+}
+
+__device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
+
+// ---- min / max over the reduced axis --------------------------------------------------------------------------
+__global__ void ptq_minmax_thread_kernel(const float* __restrict__ t, PtqView v, int S, float2* __restrict__ partial) {
+    const unsigned G = v.outer * v.inner;
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const unsigned sp = blockIdx.y;
+    const unsigned a0 = static_cast<unsigned>(static_cast<unsigned long long>(v.A) * sp / S);
+    const unsigned a1 = static_cast<unsigned>(static_cast<unsigned long long>(v.A) * (sp + 1) / S);
+    const unsigned o = g / v.inner, i = g - o * v.inner;
+    const float* p = t + (static_cast<size_t>(o) * v.A) * v.inner + i;
+    float mn = INFINITY, mx = -INFINITY;
+    for (unsigned a = a0; a < a1; ++a) {
+        const float x = __ldg(p + static_cast<size_t>(a) * v.inner);
+        mn = fminf(mn, x);
+        mx = fmaxf(mx, x);
+    }
+    partial[static_cast<size_t>(g) * S + sp] = make_float2(mn, mx);
+}
+
+__global__ void ptq_minmax_block_kernel(const float* __restrict__ t, PtqView v, int S, float2* __restrict__ partial) {
+    const unsigned g = blockIdx.x, sp = blockIdx.y;
+    const unsigned a0 = static_cast<unsigned>(static_cast<unsigned long long>(v.A) * sp / S);
+    const unsigned a1 = static_cast<unsigned>(static_cast<unsigned long long>(v.A) * (sp + 1) / S);
+    const unsigned o = g / v.inner, i = g - o * v.inner;
+    const float* p = t + (static_cast<size_t>(o) * v.A) * v.inner + i;
+    float mn = INFINITY, mx = -INFINITY;
+    for (unsigned a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
+        const float x = __ldg(p + static_cast<size_t>(a) * v.inner);
+        mn = fminf(mn, x);
+        mx = fmaxf(mx, x);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    __shared__ float smn[8], smx[8];
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (unsigned w = 1; w < blockDim.x / 32; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+        partial[static_cast<size_t>(g) * S + sp] = make_float2(mn, mx);
+    }
+}
+
+// scale = (max - min) / (2^bits - 1) in f32 (hnerv_utils.py:106,111); per-axis tables are then stored as f16 (:113)
+__global__ void ptq_table_kernel(const float2* __restrict__ partial, unsigned G, int S, float levels, int as_f16,
+                                 float* __restrict__ table) {
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int s = 0; s < S; ++s) {
+        const float2 p = partial[static_cast<size_t>(g) * S + s];
+        mn = fminf(mn, p.x);
+        mx = fmaxf(mx, p.y);
+    }
+    float scale = __fdiv_rn(__fsub_rn(mx, mn), levels);
+    if (as_f16) { mn = round_f16(mn); scale = round_f16(scale); }
+    table[g] = mn;
+    table[G + g] = scale;
+}
+
+// quant = clamp(round((t - min) / scale), 0, levels); new_t = min + scale * quant   (hnerv_utils.py:120-121)
+__device__ __forceinline__ float ptq_reconstruct(float x, float tmin, float scale, float levels, float& q) {
+    q = fminf(fmaxf(rintf(__fdiv_rn(__fsub_rn(x, tmin), scale)), 0.0f), levels);
+    return __fadd_rn(tmin, __fmul_rn(scale, q));
+}
+
+__device__ __forceinline__ unsigned ptq_group_of(unsigned idx, const PtqView& v) {
+    if (v.inner == 1) return idx / v.A;                 // whole tensor (outer 1 -> 0) or last axis
+    const unsigned span = v.A * v.inner;
+    const unsigned o = idx / span, rem = idx - o * span;
+    return o * v.inner + rem % v.inner;
+}
+
+// mean |t - new_t| of one candidate, stage 1: fixed grid, fixed per-thread order, one f64 partial per block
+__global__ void __launch_bounds__(256) ptq_error_kernel(const float* __restrict__ t, unsigned n, PtqView v,
+                                                        const float* __restrict__ table, float levels,
+                                                        double* __restrict__ partial) {
+    const unsigned G = v.outer * v.inner;
+    double acc = 0.0;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const unsigned g = ptq_group_of(idx, v);
+        const float x = __ldg(t + idx);
+        float q;
+        const float nt = ptq_reconstruct(x, __ldg(table + g), __ldg(table + G + g), levels, q);
+        acc += static_cast<double>(fabsf(__fsub_rn(x, nt)));
+    }
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    __shared__ double sw[8];
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) acc += sw[w];
+        partial[blockIdx.x] = acc;
+    }
+}
+
+__global__ void ptq_error_final_kernel(const double* __restrict__ partial, int nb, unsigned n, double* __restrict__ err_out) {
+    __shared__ double s[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nb; i += 256) acc += partial[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if (static_cast<int>(threadIdx.x) < d) s[threadIdx.x] += s[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *err_out = s[0] / static_cast<double>(n);
+}
+
+// best = first candidate with the smallest error (min(err_t_list) + list.index, hnerv_utils.py:127-128), then the
+// codes and the reconstruction of that candidate
+__global__ void __launch_bounds__(256) ptq_apply_kernel(const float* __restrict__ t, unsigned n, PtqCandSet cs,
+                                                        const float* __restrict__ tables, const double* __restrict__ err,
+                                                        float levels, uint8_t* __restrict__ quant, float* __restrict__ new_t,
+                                                        int* __restrict__ best_out) {
+    int best = 0;
+    for (int c = 1; c < cs.n; ++c)
+        if (err[c] < err[best]) best = c;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *best_out = best;
+    PtqView v = cs.view[0];
+    long long off = cs.table_off[0];
+    for (int c = 1; c < cs.n; ++c)
+        if (c == best) { v = cs.view[c]; off = cs.table_off[c]; }
+    const unsigned G = v.outer * v.inner;
+    const float* table = tables + off;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const unsigned g = ptq_group_of(idx, v);
+        float q;
+        const float nt = ptq_reconstruct(__ldg(t + idx), __ldg(table + g), __ldg(table + G + g), levels, q);
+        quant[idx] = static_cast<uint8_t>(q);
+        if (new_t) new_t[idx] = nt;
+    }
+}
+
+// ---- histogram of uint8 codes ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) histogram_u8_kernel(const uint8_t* __restrict__ codes, size_t n,
+                                                           unsigned long long* __restrict__ counts) {
+    __shared__ unsigned h[8][256];                      // one sub-histogram per warp: peaked code distributions
+    for (int k = threadIdx.x; k < 8 * 256; k += 256) (&h[0][0])[k] = 0;
+    __syncthreads();
+    unsigned* mine = h[threadIdx.x >> 5];
+    const size_t misalign = (4 - (reinterpret_cast<uintptr_t>(codes) & 3)) & 3;
+    const size_t head = n < misalign ? n : misalign;
+    const size_t words = (n - head) / 4;
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x, nthr = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const unsigned* body = reinterpret_cast<const unsigned*>(codes + head);
+    for (size_t w = tid; w < words; w += nthr) {
+        const unsigned x = __ldg(body + w);
+        atomicAdd(mine + (x & 255u), 1u);
+        atomicAdd(mine + ((x >> 8) & 255u), 1u);
+        atomicAdd(mine + ((x >> 16) & 255u), 1u);
+        atomicAdd(mine + (x >> 24), 1u);
+    }
+    if (tid < head) atomicAdd(mine + codes[tid], 1u);
+    const size_t tail0 = head + words * 4;
+    if (tid < n - tail0) atomicAdd(mine + codes[tail0 + tid], 1u);
+    __syncthreads();
+    unsigned total = 0;
+    for (int w = 0; w < 8; ++w) total += h[w][threadIdx.x];
+    if (total) atomicAdd(counts + threadIdx.x, static_cast<unsigned long long>(total));
+}
+
+static int ptq_make_plan(const int64_t* shape, int ndim, bnerv_ptq_plan* plan, PtqCandSet* cs, long long* numel) {
+    if (!shape) return set_error(BNERV_E_BADARG, "ptq: null shape");
+    if (ndim < 0 || ndim > BNERV_PTQ_MAX_CAND - 1) return set_error(BNERV_E_UNSUPPORTED, "ptq: %d dimensions (at most %d)", ndim, BNERV_PTQ_MAX_CAND - 1);
+    long long n = 1;
+    for (int d = 0; d < ndim; ++d) {
+        if (shape[d] <= 0) return set_error(BNERV_E_BADARG, "ptq: non-positive extent");
+        n *= shape[d];
+        if (n >= (1LL << 31)) return set_error(BNERV_E_UNSUPPORTED, "ptq: tensors of 2^31 elements or more");
+    }
+    bnerv_ptq_plan p{};
+    PtqCandSet c{};
+    p.axis[0] = -1; p.groups[0] = 1; p.table_offset[0] = 0;
+    c.view[0] = PtqView{1u, static_cast<unsigned>(n), 1u};
+    int nc = 1;
+    long long off = 2, gmax = 1;
+    for (int d = 0; d < ndim; ++d) {
+        const long long G = n / shape[d];
+        // t_min.nelement() / t.nelement() < 0.02 (hnerv_utils.py:110), evaluated like Python: a double division
+        if (!(static_cast<double>(G) / static_cast<double>(n) < 0.02)) continue;
+        long long inner = 1;
+        for (int e = d + 1; e < ndim; ++e) inner *= shape[e];
+        p.axis[nc] = d; p.groups[nc] = G; p.table_offset[nc] = off;
+        c.view[nc] = PtqView{static_cast<unsigned>(G / inner), static_cast<unsigned>(shape[d]), static_cast<unsigned>(inner)};
+        off += 2 * G;
+        gmax = std::max(gmax, G);
+        ++nc;
+    }
+    p.n_cand = nc;
+    p.table_floats = off;
+    p.scratch_doubles = PTQ_ERR_BLOCKS + gmax + PTQ_TARGET_THREADS + PTQ_ERR_BLOCKS;
+    c.n = nc;
+    for (int k = 0; k < nc; ++k) { c.table_off[k] = p.table_offset[k]; c.groups[k] = p.groups[k]; }
+    if (plan) *plan = p;
+    if (cs) *cs = c;
+    if (numel) *numel = n;
+    return 0;
+}
+
+}  // namespace bnerv
+
+using namespace bnerv;
+
+extern "C" int bnerv_ptq_plan_tensor(const int64_t* shape, int ndim, bnerv_ptq_plan* plan) {
+    if (!plan) return set_error(BNERV_E_BADARG, "ptq_plan_tensor: null plan");
+    return ptq_make_plan(shape, ndim, plan, nullptr, nullptr);
+}
+
+extern "C" int bnerv_ptq_quant_tensor(const float* t, const int64_t* shape, int ndim, int bits, uint8_t* quant, float* new_t,
+                                      float* tables, double* err, int32_t* best, double* scratch, void* stream) {
+    if (!t || !quant || !tables || !err || !best || !scratch) return set_error(BNERV_E_BADARG, "ptq_quant_tensor: null pointer");
+    if (bits < 1 || bits > 8) return set_error(BNERV_E_UNSUPPORTED, "ptq_quant_tensor: %d bits (codes are uint8: 1..8)", bits);
+    bnerv_ptq_plan plan;
+    PtqCandSet cs;
+    long long n = 0;
+    if (int rc = ptq_make_plan(shape, ndim, &plan, &cs, &n)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float levels = static_cast<float>((1 << bits) - 1);
+    double* err_partial = scratch;
+    float2* mm_partial = reinterpret_cast<float2*>(scratch + PTQ_ERR_BLOCKS);
+    const int err_blocks = static_cast<int>(std::min<long long>(PTQ_ERR_BLOCKS, (n + 255) / 256));
+    for (int c = 0; c < cs.n; ++c) {
+        const PtqView v = cs.view[c];
+        const long long G = cs.groups[c];
+        const int S = splits_for(G, v.A);
+        if (G >= PTQ_BLOCK_MODE_BELOW) {
+            dim3 grid(static_cast<unsigned>((G + 255) / 256), S);
+            ptq_minmax_thread_kernel<<<grid, 256, 0, st>>>(t, v, S, mm_partial);
+        } else {
+            dim3 grid(static_cast<unsigned>(G), S);
+            ptq_minmax_block_kernel<<<grid, 256, 0, st>>>(t, v, S, mm_partial);
+        }
+        if (int rc = check_launch("ptq_minmax_kernel")) return rc;
+        ptq_table_kernel<<<static_cast<unsigned>((G + 255) / 256), 256, 0, st>>>(mm_partial, static_cast<unsigned>(G), S, levels, c > 0,
+                                                                                  tables + cs.table_off[c]);
+        if (int rc = check_launch("ptq_table_kernel")) return rc;
+        ptq_error_kernel<<<err_blocks, 256, 0, st>>>(t, static_cast<unsigned>(n), v, tables + cs.table_off[c], levels, err_partial);
+        if (int rc = check_launch("ptq_error_kernel")) return rc;
+        ptq_error_final_kernel<<<1, 256, 0, st>>>(err_partial, err_blocks, static_cast<unsigned>(n), err + c);
+        if (int rc = check_launch("ptq_error_final_kernel")) return rc;
+    }
+    ptq_apply_kernel<<<err_blocks, 256, 0, st>>>(t, static_cast<unsigned>(n), cs, tables, err, levels, quant, new_t, best);
+    return check_launch("ptq_apply_kernel");
+}
+
+extern "C" int bnerv_histogram_u8(const uint8_t* codes, size_t n, uint64_t* counts256, void* stream) {
+    if (!codes || !counts256) return set_error(BNERV_E_BADARG, "histogram_u8: null pointer");
+    if (n == 0) return 0;
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>(PTQ_ERR_BLOCKS, (n / 4 + 255) / 256 + 1));
+    histogram_u8_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(codes, n, reinterpret_cast<unsigned long long*>(counts256));
+    return check_launch("histogram_u8_kernel");
+}
+
+// dahuffman 0.4.1, HuffmanCodec.from_frequencies: heap of (frequency, [leaves...]) tuples plus one EOF leaf of frequency
+// 1; Python orders equal frequencies by the leaf lists, whose first elements always differ (the leaf sets of two live
+// nodes are disjoint), so the order key is (frequency, first leaf's symbol) with EOF below every symbol; a merged node
+// starts with the leaves of the smaller operand.  A strict total order fixes the pop sequence whatever the heap shape.
+extern "C" int bnerv_huffman_code_lengths(const uint64_t* counts, int n_symbols, int32_t* lengths) {
+    if (!counts || !lengths) return set_error(BNERV_E_BADARG, "huffman_code_lengths: null pointer");
+    if (n_symbols <= 0 || n_symbols > 4096) return set_error(BNERV_E_UNSUPPORTED, "huffman_code_lengths: %d symbols (1..4096)", n_symbols);
+    struct Node { uint64_t freq; int first; int left, right; };
+    std::vector<Node> nodes;
+    std::vector<int> live;
+    nodes.push_back(Node{1, -1, -1, -1});               // EOF
+    live.push_back(0);
+    for (int s = 0; s < n_symbols; ++s) {
+        lengths[s] = 0;
+        if (counts[s]) { nodes.push_back(Node{counts[s], s, -1, -1}); live.push_back(static_cast<int>(nodes.size()) - 1); }
+    }
+    if (live.size() < 2) return set_error(BNERV_E_BADARG, "huffman_code_lengths: every count is zero");
+    auto less = [&](int a, int b) {
+        return nodes[a].freq != nodes[b].freq ? nodes[a].freq < nodes[b].freq : nodes[a].first < nodes[b].first;
+    };
+    auto pop_min = [&]() {
+        size_t k = 0;
+        for (size_t i = 1; i < live.size(); ++i) if (less(live[i], live[k])) k = i;
+        const int id = live[k];
+        live[k] = live.back();
+        live.pop_back();
+        return id;
+    };
+    while (live.size() > 1) {
+        const int a = pop_min(), b = pop_min();
+        nodes.push_back(Node{nodes[a].freq + nodes[b].freq, nodes[a].first, a, b});
+        live.push_back(static_cast<int>(nodes.size()) - 1);
+    }
+    std::vector<std::pair<int, int>> stack{{live[0], 0}};
+    while (!stack.empty()) {
+        const auto [id, depth] = stack.back();
+        stack.pop_back();
+        if (nodes[id].left < 0) { if (nodes[id].first >= 0) lengths[nodes[id].first] = depth; continue; }
+        stack.push_back({nodes[id].left, depth + 1});
+        stack.push_back({nodes[id].right, depth + 1});
+    }
+    return 0;
+}

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define BNERV_ABI_VERSION 2
+#define BNERV_ABI_VERSION 3
 
 /* error codes (negative) */
 #define BNERV_E_BADARG      (-1)   /* null pointer / non-positive size / misaligned pointer          */
@@ -256,6 +256,48 @@ int bnerv_ssim_stats(const float* x, const float* y, int planes, int H, int W, f
 int bnerv_ssim_grad(const float* x, const float* y, int planes, int H, int W, float C1, float C2, const float* gw,
                     float* scratch, int accumulate, float* dx, void* stream);
 size_t bnerv_ssim_scratch_floats(int planes, int H, int W);
+
+/* ------------------------------------------------------------------------------------------------
+ * Post-training quantisation + Huffman bit accounting (the on-disk format either side of the
+ * decoder).  Replaces quant_tensor (hnerv_utils.py:101-134) as called for every decoder tensor by quant_model
+ * (train_nerv_all.py:620-641) and for the frame embeddings (:542), and the statistics half of the Huffman stage
+ * (train_nerv_all.py:581-607: .tolist() of every code, np.unique, dahuffman's HuffmanCodec.from_data).
+ *
+ * quant_tensor tries one (min, scale) pair for the whole tensor (kept in f32) and, for every axis whose reduced table is
+ * < 2 % of the tensor (extent > 50), one pair per slice along that axis (stored as f16), and keeps the candidate with the
+ * smallest mean |t - dequant| (the first one on ties).  bnerv_ptq_plan_tensor (host only, no CUDA call) lists the
+ * candidates of a shape and where their tables go; bnerv_ptq_quant_tensor runs them all and selects on the device:
+ *   t       : f32, contiguous, `shape[0..ndim)`, ndim <= 4, fewer than 2^31 elements, finite values
+ *   quant   : u8 [numel]  codes of the best candidate        new_t : f32 [numel] its reconstruction, or NULL
+ *   tables  : f32 [plan.table_floats]; candidate c owns [table_offset[c], +groups[c]) = min, the next groups[c] = scale
+ *             (per-axis values already rounded to f16, held in f32); group index = flat index of the keepdim table
+ *   err     : f64 [BNERV_PTQ_MAX_CAND] mean |t - new_t| per candidate;  best : i32 [1] winning candidate index
+ *   scratch : f64 [plan.scratch_doubles]
+ * Every arithmetic step is the reference's in round-to-nearest f32 (true division as torch's CPU kernels do; torch's CUDA
+ * kernel multiplies by 1/(2^bits-1) when dividing by a scalar, which can move a whole-tensor scale by 1 ulp), so codes,
+ * tables and reconstruction are bit-identical to the CPU reference; the candidate errors are summed in f64 in a fixed
+ * order (the reference: f32 pairwise), which can only matter for exact near-ties between candidates. */
+#define BNERV_PTQ_MAX_CAND 5
+typedef struct bnerv_ptq_plan {
+    int32_t n_cand;                           /* 1 + number of eligible axes                                  */
+    int32_t axis[BNERV_PTQ_MAX_CAND];         /* -1: whole tensor; else the axis min/max reduce over          */
+    int64_t groups[BNERV_PTQ_MAX_CAND];       /* entries of the candidate's min table (= of its scale table)  */
+    int64_t table_offset[BNERV_PTQ_MAX_CAND]; /* float offset of [min table | scale table] inside `tables`    */
+    int64_t table_floats;                     /* floats the caller provides for `tables`                      */
+    int64_t scratch_doubles;                  /* doubles the caller provides for `scratch`                    */
+} bnerv_ptq_plan;
+int bnerv_ptq_plan_tensor(const int64_t* shape, int ndim, bnerv_ptq_plan* plan);
+int bnerv_ptq_quant_tensor(const float* t, const int64_t* shape, int ndim, int bits, uint8_t* quant, float* new_t,
+                           float* tables, double* err, int32_t* best, double* scratch, void* stream);
+/* counts256[v] += number of codes equal to v (u64 [256], caller-zeroed before the first tensor of a model). */
+int bnerv_histogram_u8(const uint8_t* codes, size_t n, uint64_t* counts256, void* stream);
+/* HOST function (no CUDA call): Huffman code length in bits of every symbol with a non-zero count, 0 for the others,
+ * as dahuffman==0.4.1's HuffmanCodec.from_data assigns them - an EOF leaf of frequency 1 joins the alphabet and equal
+ * frequencies are ordered by (first leaf's symbol), EOF first.  The package is not vendored by the reference: its
+ * published algorithm is restated (parity unpinned for the tie-breaking: every Huffman tree has the same total cost
+ * INCLUDING the EOF leaf, but which equally frequent symbols end up beside that leaf decides a few bits of the sum over
+ * the real symbols the reference reports). */
+int bnerv_huffman_code_lengths(const uint64_t* counts, int n_symbols, int32_t* lengths);
 
 /* Sizes (in elements) of the buffers the caller must provide. */
 size_t bnerv_c8_numel(int B, int C, int H, int W);                 /* __half elements            */
