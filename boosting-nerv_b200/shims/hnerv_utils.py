@@ -5,7 +5,8 @@ call `loss_fn(pred, target, args.loss)` (train_nerv_all.py:344).  Putting THIS d
 PYTHONPATH makes that import resolve here: the module executes the reference's own `hnerv_utils.py` (the next one on
 sys.path) in its namespace - datasets, metrics, logging helpers, everything - and then replaces `loss_fn` by
 `bnerv_b200.losses.loss_fn` (same signature and loss_type names; SSIM / MS-SSIM terms on csrc/loss_ops.cu) for CUDA
-tensors.  CPU tensors keep the reference's own implementation.
+tensors.  CPU tensors keep the reference's own implementation.  `quant_tensor` (the post-training quantiser evaluate() and
+quant_model() call, train_nerv_all.py:542,634) is routed to `bnerv_b200.ptq.quant_tensor` the same way (bit-identical).
 
     PYTHONPATH=/path/to/repo/boosting-nerv_b200/shims:/path/to/repo/boosting-nerv_b200:$PYTHONPATH python train_nerv_all.py ...
 """
@@ -37,3 +38,13 @@ def loss_fn(pred, target, loss_type="L2", batch_average=True):
         from bnerv_b200.losses import loss_fn as _native
         return _native(pred, target, loss_type, batch_average)
     return _reference_loss_fn(pred, target, loss_type, batch_average)
+
+
+_reference_quant_tensor = _ref.quant_tensor      # hnerv_utils.py:101
+
+
+def quant_tensor(t, bits=8):
+    if t.is_cuda and t.dtype.is_floating_point and t.element_size() == 4 and 1 <= bits <= 8:
+        from bnerv_b200.ptq import quant_tensor as _native
+        return _native(t, bits)
+    return _reference_quant_tensor(t, bits)

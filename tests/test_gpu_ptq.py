@@ -136,3 +136,28 @@ def test_quant_model_huffman_bits_and_quantised_decode():
     assert _capi.launch_count() - n0 >= 10
     ref, _ = orc.hnerv_boost_decode(want_sd, orc.cfg_from_args(a), want_de[:2], g["t"])
     assert max_rel(img.cpu(), ref) < 1e-3
+
+
+def test_hnerv_utils_shim_routes_cuda_quant_tensor_to_the_device_kernels(tmp_path):
+    import importlib
+    import os
+    import sys
+    from conftest import ROOT
+    from bnerv_b200 import _capi
+    (tmp_path / "hnerv_utils.py").write_text("def loss_fn(*a, **k):\n    return 'reference'\n\ndef quant_tensor(t, bits=8):\n    return ('reference', bits)\n")
+    old_path, old_mod = list(sys.path), sys.modules.pop("hnerv_utils", None)
+    try:
+        sys.path[:0] = [os.path.join(ROOT, "boosting-nerv_b200", "shims"), str(tmp_path)]
+        mod = importlib.import_module("hnerv_utils")
+        t = torch.randn(96, 24, 3, 3, generator=torch.Generator().manual_seed(2))
+        n0 = _capi.launch_count()
+        q, new_t = mod.quant_tensor(t.cuda(), 8)
+        assert _capi.launch_count() > n0
+        want_q, want_new = po.quant_tensor(t, 8)
+        _same(q, new_t, want_q, want_new)
+        assert mod.quant_tensor(t, 8) == ("reference", 8)               # CPU tensors stay with the reference code
+    finally:
+        sys.path[:] = old_path
+        sys.modules.pop("hnerv_utils", None)
+        if old_mod is not None:
+            sys.modules["hnerv_utils"] = old_mod

@@ -136,7 +136,7 @@ def test_hnerv_utils_shim_re_exports_the_reference_module_and_overrides_loss_fn(
     from conftest import ROOT
     fake = tmp_path / "hnerv_utils.py"
     fake.write_text("MARK = 41\n\ndef loss_fn(pred, target, loss_type='L2', batch_average=True):\n    return ('reference', loss_type)\n\n"
-                    "def psnr_fn_single(a, b):\n    return 'psnr'\n")
+                    "def psnr_fn_single(a, b):\n    return 'psnr'\n\ndef quant_tensor(t, bits=8):\n    return ('reference', bits)\n")
     shim_dir = os.path.join(ROOT, "boosting-nerv_b200", "shims")
     old_path, old_mod = list(sys.path), sys.modules.pop("hnerv_utils", None)
     try:
@@ -145,6 +145,7 @@ def test_hnerv_utils_shim_re_exports_the_reference_module_and_overrides_loss_fn(
         assert mod.MARK == 41 and mod.psnr_fn_single(0, 0) == "psnr"
         assert mod.loss_fn(torch.zeros(1), torch.zeros(1), "L1") == ("reference", "L1")       # CPU tensors: reference code
         assert mod.loss_fn is not mod._reference_loss_fn
+        assert mod.quant_tensor(torch.zeros(4), 6) == ("reference", 6)                          # CPU tensors: reference code
     finally:
         sys.path[:] = old_path
         sys.modules.pop("hnerv_utils", None)
