@@ -23,7 +23,8 @@ EXPORTS = [
     "bnerv_pack_head_weight", "bnerv_head_conv3", "bnerv_nerv_block_fwd", "bnerv_head_conv1",
     "bnerv_ssim_stats", "bnerv_ssim_grad", "bnerv_ssim_scratch_floats",
     # post-training quantisation + Huffman statistics (ABI version 3)
-    "bnerv_ptq_plan_tensor", "bnerv_ptq_quant_tensor", "bnerv_histogram_u8", "bnerv_huffman_code_lengths",
+    "bnerv_ptq_plan_tensor", "bnerv_ptq_quant_tensor", "bnerv_ptq_dequant_tensor", "bnerv_histogram_u8",
+    "bnerv_huffman_code_lengths",
 ]
 
 
@@ -76,6 +77,7 @@ def _load():
     lib.bnerv_ssim_scratch_floats.restype = ctypes.c_size_t
     lib.bnerv_ptq_plan_tensor.argtypes = [vp, i, ctypes.POINTER(PtqPlan)]
     lib.bnerv_ptq_quant_tensor.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp]
+    lib.bnerv_ptq_dequant_tensor.argtypes = [vp, vp, i, i, vp, vp, i, vp, vp]
     lib.bnerv_histogram_u8.argtypes = [vp, ctypes.c_size_t, vp, vp]
     lib.bnerv_huffman_code_lengths.argtypes = [vp, i, vp]
     lib.bnerv_conv_fused_ex.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -77,6 +77,45 @@ def dequant_tensor(quant_t):
     return tmin.expand_as(q) + scale.expand_as(q) * q
 
 
+def reconstruct_tensor(quant_t):
+    """Stored form ({'quant': uint8, 'min', 'scale'} as quant_tensor returns it) -> the f32 tensor quant_model loads into the
+    quantised model (train_nerv_all.py:634-638), bit-identical to quant_tensor's second return value."""
+    q, tmin, scale = quant_t["quant"], quant_t["min"], quant_t["scale"]
+    _need_cuda(q, tmin, scale)
+    require_current_device(q.device)
+    if q.dtype != torch.uint8 or tmin.dtype != scale.dtype or tmin.shape != scale.shape:
+        raise TypeError("reconstruct_tensor: expected uint8 codes and min / scale tables of one dtype and shape")
+    shape = tuple(q.shape)
+    if tmin.dim() == 0:
+        axis = -1                                   # whole-tensor candidate
+    else:                                           # keepdim table of the one reduced axis (extent > 50, hnerv_utils.py:110)
+        red = [d for d, (a, b) in enumerate(zip(tmin.shape, shape)) if a == 1 and b != 1]
+        if tmin.dim() != len(shape) or len(red) != 1 or any(a != b for d, (a, b) in enumerate(zip(tmin.shape, shape)) if d != red[0]):
+            raise ValueError(f"reconstruct_tensor: tables of shape {tuple(tmin.shape)} are not a keepdim reduction of {shape}")
+        axis = red[0]
+    if tmin.dtype not in (torch.float16, torch.float32):
+        raise TypeError(f"reconstruct_tensor: tables must be float16 or float32, got {tmin.dtype}")
+    arr = (ctypes.c_int64 * max(1, len(shape)))(*shape)
+    out = torch.empty(shape, dtype=torch.float32, device=q.device)
+    q, tmin, scale = q.contiguous(), tmin.contiguous(), scale.contiguous()
+    check("bnerv_ptq_dequant_tensor",
+          lib.bnerv_ptq_dequant_tensor(ptr(q), arr, len(shape), axis, ptr(tmin), ptr(scale), int(tmin.dtype == torch.float16), ptr(out), _stream()))
+    return out
+
+
+def load_quant_ckt(model, quant_ckt):
+    """Decode side of quant_model: fill `model`'s non-encoder tensors from the stored codes + tables (strict on keys)."""
+    sd = model.state_dict()
+    missing = [k for k in sd if "encoder" not in k and k not in quant_ckt]
+    extra = [k for k in quant_ckt if k not in sd]
+    if missing or extra:
+        raise KeyError(f"load_quant_ckt: missing {missing[:3]}, unexpected {extra[:3]}")
+    with torch.no_grad():
+        for k, qt in quant_ckt.items():
+            sd[k].copy_(reconstruct_tensor(qt))
+    return model
+
+
 def quant_state_dict(state_dict, bits):
     """quant_tensor over every non-encoder tensor of a state_dict (the loop of train_nerv_all.py:630-636), all launches
     issued before the single read-back of the winning candidate indices.

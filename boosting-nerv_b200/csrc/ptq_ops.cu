@@ -178,6 +178,19 @@ __global__ void __launch_bounds__(256) ptq_apply_kernel(const float* __restrict_
     }
 }
 
+// new_t = min + scale * quant from the stored form (u8 codes + f32 scalar pair or f16 keepdim tables): the decode side of the
+// format, bit-identical to the reconstruction quant_tensor returned (and quant_model loads, train_nerv_all.py:634-638)
+template <typename T>
+__global__ void __launch_bounds__(256) ptq_dequant_kernel(const uint8_t* __restrict__ quant, unsigned n, PtqView v,
+                                                          const T* __restrict__ tmin, const T* __restrict__ scale,
+                                                          float* __restrict__ out) {
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const unsigned g = ptq_group_of(idx, v);
+        const float m = static_cast<float>(tmin[g]), sc = static_cast<float>(scale[g]);
+        out[idx] = __fadd_rn(m, __fmul_rn(sc, static_cast<float>(quant[idx])));
+    }
+}
+
 // ---- histogram of uint8 codes ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) histogram_u8_kernel(const uint8_t* __restrict__ codes, size_t n,
                                                            unsigned long long* __restrict__ counts) {
@@ -288,6 +301,30 @@ extern "C" int bnerv_ptq_quant_tensor(const float* t, const int64_t* shape, int 
     }
     ptq_apply_kernel<<<err_blocks, 256, 0, st>>>(t, static_cast<unsigned>(n), cs, tables, err, levels, quant, new_t, best);
     return check_launch("ptq_apply_kernel");
+}
+
+extern "C" int bnerv_ptq_dequant_tensor(const uint8_t* quant, const int64_t* shape, int ndim, int axis, const void* tmin,
+                                        const void* scale, int tables_f16, float* out, void* stream) {
+    if (!quant || !tmin || !scale || !out) return set_error(BNERV_E_BADARG, "ptq_dequant_tensor: null pointer");
+    bnerv_ptq_plan plan;
+    long long n = 0;
+    if (int rc = ptq_make_plan(shape, ndim, &plan, nullptr, &n)) return rc;
+    if (axis < -1 || axis >= ndim) return set_error(BNERV_E_BADARG, "ptq_dequant_tensor: axis %d of %d dimensions", axis, ndim);
+    PtqView v{1u, static_cast<unsigned>(n), 1u};
+    if (axis >= 0) {
+        long long inner = 1;
+        for (int e = axis + 1; e < ndim; ++e) inner *= shape[e];
+        v = PtqView{static_cast<unsigned>(n / shape[axis] / inner), static_cast<unsigned>(shape[axis]), static_cast<unsigned>(inner)};
+    }
+    const int blocks = static_cast<int>(std::min<long long>(PTQ_ERR_BLOCKS, (n + 255) / 256));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (tables_f16)
+        ptq_dequant_kernel<__half><<<blocks, 256, 0, st>>>(quant, static_cast<unsigned>(n), v, static_cast<const __half*>(tmin),
+                                                          static_cast<const __half*>(scale), out);
+    else
+        ptq_dequant_kernel<float><<<blocks, 256, 0, st>>>(quant, static_cast<unsigned>(n), v, static_cast<const float*>(tmin),
+                                                         static_cast<const float*>(scale), out);
+    return check_launch("ptq_dequant_kernel");
 }
 
 extern "C" int bnerv_histogram_u8(const uint8_t* codes, size_t n, uint64_t* counts256, void* stream) {

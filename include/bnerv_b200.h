@@ -289,6 +289,13 @@ typedef struct bnerv_ptq_plan {
 int bnerv_ptq_plan_tensor(const int64_t* shape, int ndim, bnerv_ptq_plan* plan);
 int bnerv_ptq_quant_tensor(const float* t, const int64_t* shape, int ndim, int bits, uint8_t* quant, float* new_t,
                            float* tables, double* err, int32_t* best, double* scratch, void* stream);
+/* Decode side of the same format: out = min + scale * quant in f32 from the stored u8 codes and the winning candidate's
+ * tables (axis = -1: one f32 pair, tables_f16 = 0; axis >= 0: f16 keepdim tables over that axis, tables_f16 = 1) -
+ * bit-identical to the `new_t` bnerv_ptq_quant_tensor produced, i.e. to what quant_model loads into the quantised model
+ * (train_nerv_all.py:634-638).  (hnerv_utils.dequant_tensor, :185-188, is unused by the reference and evaluates the same
+ * expression in f16 when the tables are f16.) */
+int bnerv_ptq_dequant_tensor(const uint8_t* quant, const int64_t* shape, int ndim, int axis, const void* tmin,
+                             const void* scale, int tables_f16, float* out, void* stream);
 /* counts256[v] += number of codes equal to v (u64 [256], caller-zeroed before the first tensor of a model). */
 int bnerv_histogram_u8(const uint8_t* codes, size_t n, uint64_t* counts256, void* stream);
 /* HOST function (no CUDA call): Huffman code length in bits of every symbol with a non-zero count, 0 for the others,

@@ -34,6 +34,7 @@ def test_quant_tensor_is_bit_identical_to_the_reference_goldens(name):
     assert _capi.launch_count() - n0 >= 5
     want = {k: torch.from_numpy(g[k]) for k in ("quant", "min", "scale")}
     _same(q, new_t, want, torch.from_numpy(g["new_t"]))
+    assert torch.equal(ptq.reconstruct_tensor(q).cpu(), torch.from_numpy(g["new_t"]))      # decode side: stored form -> new_t
     d = ptq.dequant_tensor(q)
     assert d.dtype == torch.from_numpy(g["dequant"]).dtype
     if d.dtype == torch.float32:                 # f16 tables: the reference's dequant_tensor is f16 arithmetic, device-dependent rounding
@@ -62,6 +63,7 @@ def test_quant_tensor_matches_oracle_at_model_sizes(shape, bits, kind):
     want_q, want_new = po.quant_tensor(t, bits)
     q, new_t = ptq.quant_tensor(t.cuda(), bits)
     _same(q, new_t, want_q, want_new)
+    assert torch.equal(ptq.reconstruct_tensor(q), new_t)
 
 
 def test_constant_tensor_is_reconstructed_exactly():
@@ -119,6 +121,12 @@ def test_quant_model_huffman_bits_and_quantised_decode():
     for k in quant_ckt:
         _same(quant_ckt[k], qsd[k], want_ckt[k], want_sd[k])
     assert ptq.quant_model(m, types.SimpleNamespace(quant_model_bit=-1))[1] is None
+    # decode side of the format: a fresh model filled from the stored codes + tables equals the quantised model bit for bit
+    fresh = ptq.load_quant_ckt(HNeRV_Boost(a).eval().cuda(), quant_ckt)
+    fsd = fresh.state_dict()
+    assert all(torch.equal(fsd[k], qsd[k]) for k in quant_ckt)
+    with pytest.raises(KeyError):
+        ptq.load_quant_ckt(fresh, {k: v for k, v in list(quant_ckt.items())[1:]})
 
     emb = torch.rand(64, 16, 2, 4, generator=torch.Generator().manual_seed(5))
     q_emb, deq_emb = ptq.quant_tensor(emb.cuda(), 6)

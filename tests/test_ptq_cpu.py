@@ -71,6 +71,7 @@ def test_plan_lists_the_reference_candidates():
     assert _capi.lib.bnerv_ptq_quant_tensor(one, arr, 1, 9, one, None, one, one, one, one, None) == -2      # > 8 bits: codes are uint8
     assert _capi.lib.bnerv_ptq_quant_tensor(None, arr, 1, 8, one, None, one, one, one, one, None) == -1
     assert _capi.lib.bnerv_histogram_u8(None, 4, one, None) == -1
+    assert _capi.lib.bnerv_ptq_dequant_tensor(one, arr, 1, 1, one, one, 1, one, None) == -1 and b"axis" in _capi.lib.bnerv_last_error()
     assert _capi.lib.bnerv_launch_count() == 0
 
 

@@ -65,8 +65,17 @@ def main():
 
     t_nat, (ckt, qe) = wall(native)
     t_ref, (ckt_r, qe_r) = wall(reference)
-    same = all(torch.equal(ckt[k]["quant"], ckt_r[k]["quant"]) for k in ckt) and torch.equal(qe["quant"], qe_r["quant"])
-    print(f"quantise decoder (8 bit) + embeddings (6 bit): native {t_nat:.2f} ms, torch ops {t_ref:.2f} ms, codes identical: {same}")
+    print(f"quantise decoder (8 bit) + embeddings (6 bit): native {t_nat:.2f} ms, torch ops on this GPU {t_ref:.2f} ms")
+    # torch's CUDA kernel divides by the Python scalar 2^bits-1 as a multiplication by its f32 reciprocal, torch's CPU kernel (the
+    # goldens, the oracle, this library) as a true division: scales can differ by 1 ulp, so a few codes on rounding boundaries move
+    pairs = [(ckt[k], ckt_r[k]) for k in ckt] + [(qe, qe_r)]
+    diff = sum(int((a["quant"] != b["quant"]).sum()) for a, b in pairs)
+    worst = max(int((a["quant"].int() - b["quant"].int()).abs().max()) for a, b in pairs)
+    ident = sum(torch.equal(a["quant"], b["quant"]) for a, b in pairs)
+    print(f"vs torch-on-GPU codes: {ident}/{len(pairs)} tensors identical, {diff} of {n_par + emb.numel()} codes differ, by at most {worst} level "
+          f"(scalar division as reciprocal multiply on CUDA; bit-exactness vs the CPU reference is what tests/test_gpu_ptq.py gates)")
+    t_dec, _ = wall(lambda: [ptq.reconstruct_tensor(v) for v in ckt.values()])
+    print(f"decode side (codes + tables -> f32 weights, {len(ckt)} tensors): {t_dec:.2f} ms")
 
     t_bits, bits = wall(lambda: ptq.huffman_bits(ckt, qe))
 
