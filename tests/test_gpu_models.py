@@ -160,10 +160,11 @@ def test_full_resolution_properties_hnerv_1080p():
     assert max_rel(img[:, :, :96, :216].cpu(), emu[:, :, :96, :216]) < 2e-4
 
 
-@pytest.mark.parametrize("name", ["hnerv_l", "enerv_m", "nerv_s", "nerv_xs_640", "nerv_s_640"])
+@pytest.mark.parametrize("name", ["hnerv_l", "enerv_m", "nerv_s", "nerv_xs_640", "nerv_s_640", "hnerv_m", "hnerv_bunny", "nerv_xs"])
 def test_benchmarked_presets_full_frame_against_oracle(name):
     """The configurations bench.py measures (BASELINE.json configs 2-4: full width, full resolution, random-init
-    weights under manual_seed(1)) decoded natively vs the CPU oracle on the same frame: 1e-3 gate + PSNR."""
+    weights under manual_seed(1)) and the other shipped presets (10M HNeRV, the Bunny HNeRV, NeRV-XS at 720p) decoded
+    natively vs the CPU oracle on the same frame: 1e-3 gate + PSNR."""
     import bench
     from bnerv_b200 import preset
     model, a = bench.build_model(name)
