@@ -35,3 +35,6 @@ def test_b200_arm_json_line():
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and "traffic" in r
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == "frames/s" and c["sample"]
+    q = d["ptq"]                     # extra: PTQ + Huffman accounting + quantised decode on the native kernels
+    assert "error" not in q and 0 < q["bits_per_param"] <= 9 and q["total_bpp"] > 0 and q["quantised_decode_frames_per_s"] > 0
+    assert q["psnr_quantised_vs_unquantised_db"] > 25
