@@ -25,6 +25,8 @@ EXPORTS = [
     # post-training quantisation + Huffman statistics (ABI version 3)
     "bnerv_ptq_plan_tensor", "bnerv_ptq_quant_tensor", "bnerv_ptq_dequant_tensor", "bnerv_histogram_u8",
     "bnerv_huffman_code_lengths",
+    # ConvNeXt encoder forward
+    "bnerv_convnext_stage_fwd", "bnerv_convnext_stage_work_floats", "bnerv_nhwc_to_nchw",
 ]
 
 
@@ -51,6 +53,18 @@ class PtqPlan(ctypes.Structure):
                 ("scratch_doubles", ctypes.c_int64)]
 
 
+class ConvNextBlock(ctypes.Structure):
+    """struct bnerv_convnext_block"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("dw_w", "dw_b", "ln_w", "ln_b", "pw1_w", "pw1_b", "pw2_w", "pw2_b", "gamma")]
+
+
+class ConvNextStage(ctypes.Structure):
+    """struct bnerv_convnext_stage"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("ln_in_w", "ln_in_b", "down_w", "down_b", "ln_out_w", "ln_out_b")] + \
+               [("blocks", ctypes.POINTER(ConvNextBlock)), ("n_blocks", ctypes.c_int32), ("Cin", ctypes.c_int32),
+                ("Cout", ctypes.c_int32), ("s", ctypes.c_int32)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -75,6 +89,10 @@ def _load():
     lib.bnerv_ssim_grad.argtypes = [vp, vp, i, i, i, f, f, vp, vp, i, vp, vp]
     lib.bnerv_ssim_scratch_floats.argtypes = [i, i, i]
     lib.bnerv_ssim_scratch_floats.restype = ctypes.c_size_t
+    lib.bnerv_convnext_stage_fwd.argtypes = [ctypes.POINTER(ConvNextStage), vp, i, i, i, i, vp, vp, vp]
+    lib.bnerv_convnext_stage_work_floats.argtypes = [i, i, i, i, i]
+    lib.bnerv_convnext_stage_work_floats.restype = ctypes.c_size_t
+    lib.bnerv_nhwc_to_nchw.argtypes = [vp, i, i, i, i, vp, vp]
     lib.bnerv_ptq_plan_tensor.argtypes = [vp, i, ctypes.POINTER(PtqPlan)]
     lib.bnerv_ptq_quant_tensor.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp]
     lib.bnerv_ptq_dequant_tensor.argtypes = [vp, vp, i, i, vp, vp, i, vp, vp]

@@ -307,8 +307,16 @@ class HNeRV_Boost(_BoostBase):
         n_enc = sum(p.data.nelement() for p in self.encoder.parameters())
         return (n_all - n_enc) / 1e6
 
+    def _encode(self, frame):
+        """ConvNeXt encoder (model_hnerv.py:189): the native f32 forward under the decode path's dispatch rule (no autograd,
+        CUDA tensors, backend 'b200'; CPU tensors raise), the torch module when training or with backend 'torch'."""
+        if self._use_engine(frame):
+            from .encoder import convnext_forward
+            return convnext_forward(self.encoder, frame)
+        return self.encoder(frame)
+
     def forward_encoder(self, input):
-        return self.encoder(input)
+        return self._encode(input)
 
     def forward_embed_quant(self, img_embed, entropy_model=None):
         code, quant, img_embed = self.embed_quantizer(img_embed)
@@ -340,14 +348,14 @@ class HNeRV_Boost(_BoostBase):
         return img, outs, self._finish(t0)
 
     def forward(self, input, input_embed=None, entropy_model=None, pre_img=None, post_img=None, norm_idx=None):
-        img_embed = input_embed if input_embed is not None else self.encoder(input)
+        img_embed = input_embed if input_embed is not None else self._encode(input)
         if self.embed_quantizer is not None:
             self.embed_quantizer.init_data(img_embed)
             code_e, quant_e, img_embed = self.embed_quantizer(img_embed)
             if entropy_model is not None:
                 self.bitrate_e_dict.update(entropy_model.cal_bitrate(code_e, quant_e, self.training))
         if pre_img is not None and post_img is not None:
-            img_embed = 0.5 * (self.encoder(pre_img) + self.encoder(post_img))
+            img_embed = 0.5 * (self._encode(pre_img) + self._encode(post_img))
         return self.forward_decoder(img_embed, norm_idx)
 
 

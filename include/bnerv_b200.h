@@ -306,6 +306,32 @@ int bnerv_histogram_u8(const uint8_t* codes, size_t n, uint64_t* counts256, void
  * the real symbols the reference reports). */
 int bnerv_huffman_code_lengths(const uint64_t* counts, int n_symbols, int32_t* lengths);
 
+/* ------------------------------------------------------------------------------------------------
+ * ConvNeXt encoder of HNeRV_Boost, forward only (encoder half): one stage of
+ * ConvNeXt.forward (model_blocks.py:314-320) per call -
+ *     [LayerNorm channels_first] -> Conv2d(Cin, Cout, kernel s, stride s) -> [LayerNorm channels_first (stage 0)]
+ *     -> n_blocks x Block.forward (model_blocks.py:246-260): x + gamma * pwconv2(GELU(pwconv1(LayerNorm(dwconv7x7(x)))))
+ * as HNeRV_Boost.forward_encoder (model_hnerv.py:230-234) runs it per frame in evaluate() and when a sequence's
+ * embeddings are extracted.  f32 CUDA-core arithmetic with exact erf (the embedding feeds the whole decoder; gate 1e-5
+ * against the reference's f32 result); all LayerNorms use eps = 1e-6 like the reference.  Training keeps the torch module.
+ *   weights : the module's own f32 parameter storage, no packing (down_w [Cout][Cin][s][s], dw_w [C][1][7][7],
+ *             pw1_w [4C][C], pw2_w [C][4C], gamma [C]; ln_in_* / ln_out_* NULL where the stage has no such LayerNorm)
+ *   x       : the frame, NCHW f32 (x_is_nchw = 1, stage 0) or the previous stage's channels-last output [B][Hin][Win][Cin]
+ *   y_nhwc  : [B][Hin/s][Win/s][Cout] f32 (channels-last; bnerv_nhwc_to_nchw converts the last stage's output)
+ *   work    : f32 [bnerv_convnext_stage_work_floats(B, Hin, Win, s, Cout)] */
+typedef struct bnerv_convnext_block {
+    const float *dw_w, *dw_b, *ln_w, *ln_b, *pw1_w, *pw1_b, *pw2_w, *pw2_b, *gamma;
+} bnerv_convnext_block;
+typedef struct bnerv_convnext_stage {
+    const float *ln_in_w, *ln_in_b, *down_w, *down_b, *ln_out_w, *ln_out_b;
+    const bnerv_convnext_block* blocks;       /* HOST array of n_blocks entries (device pointers inside) */
+    int32_t n_blocks, Cin, Cout, s;
+} bnerv_convnext_stage;
+int    bnerv_convnext_stage_fwd(const bnerv_convnext_stage* stage, const float* x, int x_is_nchw, int B, int Hin, int Win,
+                                float* y_nhwc, float* work, void* stream);
+size_t bnerv_convnext_stage_work_floats(int B, int Hin, int Win, int s, int Cout);
+int    bnerv_nhwc_to_nchw(const float* x_nhwc, int B, int H, int W, int C, float* y_nchw, void* stream);
+
 /* Sizes (in elements) of the buffers the caller must provide. */
 size_t bnerv_c8_numel(int B, int C, int H, int W);                 /* __half elements            */
 size_t bnerv_packed_weight_numel(int Cout, int Cin, int k, int s); /* __half elements            */
