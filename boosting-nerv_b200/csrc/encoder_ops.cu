@@ -10,7 +10,7 @@
 // decoder's work.  Layout between kernels: channels-last f32 [B][H][W][C] (LayerNorm and the point-wise MLP are per-pixel
 // reductions over C); the patch conv gathers its A operand straight from the NCHW frame (stage 0) or the previous NHWC
 // map (with the preceding LayerNorm applied on the fly from per-pixel statistics), so no im2col buffer exists.
-// One templated 64x64x16 register-tiled SGEMM serves the patch conv and both point-wise layers.
+// One templated register-tiled SGEMM (128x64x16 or 64x64x16 block tiles) serves the patch conv and both point-wise layers.
 #include <algorithm>
 #include "common.cuh"
 
@@ -54,6 +54,11 @@ __global__ void __launch_bounds__(256) enc_ln_inplace_kernel(float* __restrict__
 }
 
 // ---- depthwise 7x7, padding 3, channels-last (Block.dwconv, model_blocks.py:236) ---------------------------------
+// A thread owns a strip of DW_TW output pixels of one row and one channel: each of the 7 input rows is loaded once
+// (DW_TW + 6 values) and reused by the 7 column taps from registers - 12 loads per output instead of 49.  Neighbouring
+// threads are neighbouring channels, so every load / store is a contiguous run of C floats.
+constexpr int DW_TW = 8;
+
 __global__ void __launch_bounds__(256) enc_dwconv7_kernel(const float* __restrict__ x, int B, int H, int W, int C,
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           float* __restrict__ y) {
@@ -63,27 +68,42 @@ __global__ void __launch_bounds__(256) enc_dwconv7_kernel(const float* __restric
         wt[t * C + c] = __ldg(w + k);
     }
     __syncthreads();
-    const size_t total = static_cast<size_t>(B) * H * W * C;
+    const int strips = (W + DW_TW - 1) / DW_TW;
+    const size_t total = static_cast<size_t>(B) * H * strips * C;
     for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int c = static_cast<int>(idx % C);
-        const size_t p = idx / C;
-        const int wq = static_cast<int>(p % W);
-        const int hq = static_cast<int>((p / W) % H);
-        const size_t b = p / (static_cast<size_t>(W) * H);
-        float acc = __ldg(bias + c);
+        size_t q = idx / C;
+        const int w0 = static_cast<int>(q % strips) * DW_TW;
+        q /= strips;
+        const int hq = static_cast<int>(q % H);
+        const size_t b = q / H;
+        float acc[DW_TW];
+        const float bv = __ldg(bias + c);
+#pragma unroll
+        for (int o = 0; o < DW_TW; ++o) acc[o] = bv;
 #pragma unroll
         for (int r = 0; r < 7; ++r) {
             const int hh = hq + r - 3;
             if (hh < 0 || hh >= H) continue;
+            const float* row = x + ((b * H + hh) * W) * C + c;
+            float v[DW_TW + 6];
+#pragma unroll
+            for (int t = 0; t < DW_TW + 6; ++t) {
+                const int ww = w0 - 3 + t;
+                v[t] = (ww >= 0 && ww < W) ? __ldg(row + static_cast<size_t>(ww) * C) : 0.0f;
+            }
 #pragma unroll
             for (int s = 0; s < 7; ++s) {
-                const int ww = wq + s - 3;
-                if (ww < 0 || ww >= W) continue;
-                acc = fmaf(__ldg(x + ((b * H + hh) * W + ww) * C + c), wt[(r * 7 + s) * C + c], acc);
+                const float wgt = wt[(r * 7 + s) * C + c];
+#pragma unroll
+                for (int o = 0; o < DW_TW; ++o) acc[o] = fmaf(v[o + s], wgt, acc[o]);
             }
         }
-        y[idx] = acc;
+        float* out = y + ((b * H + hq) * W) * C + c;
+#pragma unroll
+        for (int o = 0; o < DW_TW; ++o)
+            if (w0 + o < W) out[static_cast<size_t>(w0 + o) * C] = acc[o];
     }
 }
 
@@ -104,7 +124,7 @@ struct EncGemm {
     int Cin, H, W, s, Ho, Wo, nchw;    // PATCH geometry
 };
 
-constexpr int EG_BM = 64, EG_BN = 64, EG_BK = 16;
+constexpr int EG_BN = 64, EG_BK = 16;       // block tile: (16 * TM) rows x 64 columns x 16 k; 16 x 16 threads, TM x 4 outputs each
 
 template <int AMODE>
 __device__ __forceinline__ float enc_load_a(const EncGemm& g, int p, int k) {
@@ -125,38 +145,49 @@ __device__ __forceinline__ float enc_load_a(const EncGemm& g, int p, int k) {
     }
 }
 
-template <int AMODE, int EPI>
+template <int AMODE, int EPI, int TM>
 __global__ void __launch_bounds__(256) enc_gemm_kernel(EncGemm g) {
-    __shared__ __align__(16) float As[EG_BK][EG_BM + 4];
+    constexpr int BM = 16 * TM;
+    __shared__ __align__(16) float As[EG_BK][BM + 4];
     __shared__ __align__(16) float Bs[EG_BK][EG_BN + 4];
     const int tid = threadIdx.x;
-    const int m0 = blockIdx.x * EG_BM, n0 = blockIdx.y * EG_BN;
-    const int tm = (tid >> 4) * 4, tn = (tid & 15) * 4;        // 16 x 16 threads, 4 x 4 outputs each
-    float acc[4][4] = {};
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * EG_BN;
+    const int tm = (tid >> 4) * TM, tn = (tid & 15) * 4;
+    float acc[TM][4] = {};
     for (int k0 = 0; k0 < g.K; k0 += EG_BK) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {                           // 64 x 16 elements of A and of W per k-chunk, 4 each per thread
+        for (int r = 0; r < BM / 16; ++r) {                     // BM x 16 elements of A: consecutive threads walk k
             const int e = tid + r * 256;
-            const int kk = e & 15, mm = e >> 4;                 // consecutive threads walk k: contiguous for ROWS and for W
+            const int kk = e & 15, mm = e >> 4;
             As[kk][mm] = enc_load_a<AMODE>(g, m0 + mm, k0 + kk);
-            const int n = n0 + mm, k = k0 + kk;
-            Bs[kk][mm] = (n < g.N && k < g.K) ? __ldg(g.w + static_cast<size_t>(n) * g.K + k) : 0.0f;
+        }
+#pragma unroll
+        for (int r = 0; r < EG_BN / 16; ++r) {                  // 64 x 16 elements of W
+            const int e = tid + r * 256;
+            const int kk = e & 15, nn = e >> 4;
+            const int n = n0 + nn, k = k0 + kk;
+            Bs[kk][nn] = (n < g.N && k < g.K) ? __ldg(g.w + static_cast<size_t>(n) * g.K + k) : 0.0f;
         }
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < EG_BK; ++kk) {
-            const float4 av = *reinterpret_cast<const float4*>(&As[kk][tm]);
-            const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tn]);
-            const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+            float a4[TM];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < TM; i += 4) {
+                const float4 av = *reinterpret_cast<const float4*>(&As[kk][tm + i]);
+                a4[i] = av.x; a4[i + 1] = av.y; a4[i + 2] = av.z; a4[i + 3] = av.w;
+            }
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tn]);
+            const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TM; ++i) {
         const int p = m0 + tm + i;
         if (p >= g.M) continue;
 #pragma unroll
@@ -185,8 +216,14 @@ __global__ void __launch_bounds__(256) enc_nhwc_to_nchw_kernel(const float* __re
 
 template <int AMODE, int EPI>
 static int enc_launch_gemm(const EncGemm& g, cudaStream_t st, const char* what) {
-    dim3 grid((g.M + EG_BM - 1) / EG_BM, (g.N + EG_BN - 1) / EG_BN);
-    enc_gemm_kernel<AMODE, EPI><<<grid, 256, 0, st>>>(g);
+    const unsigned nt = (g.N + EG_BN - 1) / EG_BN;
+    if (static_cast<size_t>((g.M + 127) / 128) * nt >= 2 * 148) {       // enough 128-row tiles for two waves: the wider micro-tile
+        dim3 grid((g.M + 127) / 128, nt);
+        enc_gemm_kernel<AMODE, EPI, 8><<<grid, 256, 0, st>>>(g);
+    } else {
+        dim3 grid((g.M + 63) / 64, nt);
+        enc_gemm_kernel<AMODE, EPI, 4><<<grid, 256, 0, st>>>(g);
+    }
     return check_launch(what);
 }
 
@@ -244,7 +281,7 @@ extern "C" int bnerv_convnext_stage_fwd(const bnerv_convnext_stage* sg, const fl
         const bnerv_convnext_block& blk = sg->blocks[bi];
         if (!blk.dw_w || !blk.dw_b || !blk.ln_w || !blk.ln_b || !blk.pw1_w || !blk.pw1_b || !blk.pw2_w || !blk.pw2_b || !blk.gamma)
             return set_error(BNERV_E_BADARG, "convnext_stage_fwd: null weight in block %d", bi);
-        enc_dwconv7_kernel<<<enc_blocks(pout * C, 256), 256, 49 * C * sizeof(float), st>>>(y_nhwc, B, Ho, Wo, C, blk.dw_w, blk.dw_b, dmap);
+        enc_dwconv7_kernel<<<enc_blocks(static_cast<size_t>(B) * Ho * ((Wo + DW_TW - 1) / DW_TW) * C, 256), 256, 49 * C * sizeof(float), st>>>(y_nhwc, B, Ho, Wo, C, blk.dw_w, blk.dw_b, dmap);
         if (int rc = check_launch("enc_dwconv7_kernel")) return rc;
         enc_ln_stats_kernel<<<enc_blocks(pout * 32, 256), 256, 0, st>>>(dmap, pout, C, eps, stats_blk);
         if (int rc = check_launch("enc_ln_stats_kernel")) return rc;
