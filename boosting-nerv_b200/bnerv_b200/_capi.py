@@ -123,10 +123,9 @@ def _load():
     lib.bnerv_packed_weight_numel.restype = ctypes.c_size_t
     lib.bnerv_packed_bias_numel.argtypes = [i, i]
     lib.bnerv_packed_bias_numel.restype = ctypes.c_size_t
-    for name in EXPORTS:
-        fn = getattr(lib, name)
-        if fn.restype is ctypes.c_int and name != "bnerv_abi_version":
-            pass
+    missing = [name for name in EXPORTS if not hasattr(lib, name)]
+    if missing:
+        raise ImportError(f"{LIB_PATH} is stale: missing {missing} (re-run `python boosting-nerv_b200/build.py`)")
     return lib
 
 
