@@ -13,9 +13,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-def test_encoder_matches_reference_golden_through_forward_encoder():
+@pytest.mark.parametrize("gold", ["hnerv_tiny.npz", "hnerv_tiny_trained.npz"])
+def test_encoder_matches_reference_golden_through_forward_encoder(gold):
     from bnerv_b200 import _capi
-    sd, g = load_golden("hnerv_tiny.npz")
+    sd, g = load_golden(gold)
     m = HNeRV_Boost(tiny_args("HNeRV_Boost")).eval()
     m.load_state_dict(sd)
     m = m.cuda()

@@ -20,7 +20,8 @@ def _build(model, args=None):
     return m.eval(), a
 
 
-@pytest.mark.parametrize("model,gold", [("NeRV_Boost", "nerv_tiny.npz"), ("ENeRV_Boost", "enerv_tiny.npz"), ("HNeRV_Boost", "hnerv_tiny.npz")])
+@pytest.mark.parametrize("model,gold", [("NeRV_Boost", "nerv_tiny.npz"), ("ENeRV_Boost", "enerv_tiny.npz"), ("HNeRV_Boost", "hnerv_tiny.npz"),
+                                        ("HNeRV_Boost", "hnerv_tiny_trained.npz")])
 def test_model_matches_reference_golden(model, gold):
     from bnerv_b200 import _capi
     sd, g = load_golden(gold)
@@ -42,6 +43,22 @@ def test_model_matches_reference_golden(model, gold):
     assert len(outs) == sum(k.startswith("out") for k in g)
     for i, o in enumerate(outs):
         assert max_rel(o.cpu(), g[f"out{i}"]) < REL, i
+
+
+def test_reference_trained_model_psnr_against_ground_truth_within_0p01_db():
+    """north_star: PSNR within 0.01 dB of the reference.  The golden holds a reference-TRAINED tiny HNeRV_Boost (25 dB on its
+    synthetic frames) with the reference's own outputs: frame -> native encoder -> native decoder must land on the same PSNR."""
+    sd, g = load_golden("hnerv_tiny_trained.npz")
+    m, _ = _build("HNeRV_Boost")
+    m.load_state_dict(sd)
+    m = m.cuda()
+    with torch.no_grad():
+        img, lst, _ = m(g["frame"].cuda(), norm_idx=g["t"].cuda())
+    assert max_rel(lst[0].cpu(), g["enc"]) < 1e-5                               # embedding from the native f32 encoder
+    assert max_rel(img.cpu(), g["img_full"]) < REL
+    for b in range(img.shape[0]):
+        ours, ref = orc.psnr(img[b:b + 1].cpu(), g["frame"][b:b + 1]), orc.psnr(g["img_full"][b:b + 1], g["frame"][b:b + 1])
+        assert ref > 20.0 and abs(ours - ref) < 0.01, (ours, ref)
 
 
 def test_default_list_semantics_element0():

@@ -41,6 +41,18 @@ def test_hnerv_boost_decoder_matches_reference():
         assert max_rel(o, g[f"out{i}"]) < TOL, i
 
 
+def test_hnerv_boost_decoder_matches_reference_on_trained_weights():
+    """tests/golden/make_golden_trained.py: the reference trained for 1200 steps (25 dB) - pre-sin magnitudes and the
+    encoder's layer scale are no longer the initialisation's."""
+    sd, g = load_golden("hnerv_tiny_trained.npz")
+    img, outs = orc.hnerv_boost_decode(sd, _cfg("HNeRV_Boost"), g["emb"], g["t"])
+    assert max_rel(img, g["img"]) < TOL and max_rel(img, g["img_full"]) < TOL
+    for i, o in enumerate(outs):
+        assert max_rel(o, g[f"out{i}"]) < TOL, i
+    assert orc.psnr(g["img"], g["frame"]) > 20.0                 # it did learn the frames
+    assert max(float(v.abs().max()) for k, v in sd.items() if k.endswith("gamma")) > 0.05
+
+
 def test_f64_oracle_close_to_f32_reference():
     sd, g = load_golden("hnerv_tiny.npz")
     img64, _ = orc.hnerv_boost_decode(sd, _cfg("HNeRV_Boost"), g["emb"], g["t"], dtype=torch.float64)
