@@ -18,7 +18,8 @@ def _build(model):
 
 
 @pytest.mark.parametrize("model,gold", [("NeRV_Boost", "nerv_tiny.npz"), ("ENeRV_Boost", "enerv_tiny.npz"), ("HNeRV_Boost", "hnerv_tiny.npz"),
-                                        ("HNeRV_Boost", "hnerv_tiny_trained.npz")])
+                                        ("HNeRV_Boost", "hnerv_tiny_trained.npz"), ("NeRV_Boost", "nerv_tiny_trained.npz"),
+                                        ("ENeRV_Boost", "enerv_tiny_trained.npz")])
 def test_state_dict_layout_and_torch_wiring(model, gold):
     sd, g = load_golden(gold)
     m = _build(model).eval()

@@ -63,6 +63,24 @@ def test_hnerv_boost_decoder_matches_reference_on_trained_weights():
     assert max(float(v.abs().max()) for k, v in sd.items() if k.endswith("gamma")) > 0.05
 
 
+@pytest.mark.parametrize("model,gold,worst_lo,worst_hi", [("NeRV_Boost", "nerv_tiny_trained.npz", 3e-4, 1.5e-3),
+                                                          ("ENeRV_Boost", "enerv_tiny_trained.npz", 7e-4, 3e-3)])
+def test_nerv_and_enerv_match_reference_on_trained_weights(model, gold, worst_lo, worst_hi):
+    sd, g = load_golden(gold)
+    img, outs = orc.forward(model, sd, _cfg(model), g["t"])
+    assert max_rel(img, g["img"]) < TOL and orc.psnr(g["img"], g["frame"]) > 25.0
+    for i, o in enumerate(outs):
+        assert max_rel(o, g[f"out{i}"]) < 5e-6, i
+    orc.EMULATE = torch.float16                                   # f16-operand prediction: image inside the 1e-3 gate
+    try:
+        emu_img, emu_outs = orc.forward(model, sd, _cfg(model), g["t"])
+    finally:
+        orc.EMULATE = None
+    assert max_rel(emu_img, g["img"]) < 1e-3
+    assert abs(orc.psnr(emu_img, g["frame"]) - orc.psnr(g["img"], g["frame"])) < 0.01
+    assert worst_lo < max(max_rel(o, g[f"out{i}"]) for i, o in enumerate(emu_outs)) < worst_hi
+
+
 def test_f64_oracle_close_to_f32_reference():
     sd, g = load_golden("hnerv_tiny.npz")
     img64, _ = orc.hnerv_boost_decode(sd, _cfg("HNeRV_Boost"), g["emb"], g["t"], dtype=torch.float64)
