@@ -63,3 +63,15 @@ def load_block_golden():
 def max_rel(a, b):
     """max |a-b| / max|b| — the 'relative fp32' metric used for the 1e-3 gate."""
     return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-12)).item()
+
+
+def check_trained_golden_outputs(img, outs, g, psnr_fn):
+    """Gates shared by the reference-TRAINED goldens (CPU: the oracle's f16-operand emulation; GPU: the device decode).
+    Intermediate maps within 5e-3 of the f32 reference (measured on the device: <= 3.1e-3 HNeRV, 1.6e-3 E-NeRV, 8.9e-4 NeRV,
+    profiles/r01_v8_trained_golden_report.txt) and PSNR against the frames the model was trained on within 0.01 dB of the
+    reference's (north_star; measured <= 0.002 dB)."""
+    vs_ref = [max_rel(o.cpu(), g[f"out{i}"]) for i, o in enumerate(outs)]
+    assert len(vs_ref) == sum(k.startswith("out") for k in g) and max(vs_ref) < 5e-3, vs_ref
+    ours, ref = psnr_fn(img.cpu(), g["frame"]), psnr_fn(g["img"], g["frame"])
+    assert ref > 20.0 and abs(ours - ref) < 0.01, (ours, ref)
+    return vs_ref
