@@ -9,6 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libbnerv_b200.so")
 
+E_BADARG, E_UNSUPPORTED, E_NODRIVER = -1, -2, -3
 ACT_NONE, ACT_SIN, ACT_GELU, ACT_RELU, ACT_TANH01 = 0, 1, 2, 3, 4
 ACT_CODES = {"none": ACT_NONE, "sin": ACT_SIN, "gelu": ACT_GELU, "relu": ACT_RELU, "tanh01": ACT_TANH01}
 
@@ -27,6 +28,8 @@ EXPORTS = [
     "bnerv_huffman_code_lengths",
     # ConvNeXt encoder forward
     "bnerv_convnext_stage_fwd", "bnerv_convnext_stage_work_floats", "bnerv_nhwc_to_nchw",
+    # one kernel per NeRVBlock for the narrow stages (ABI version 4)
+    "bnerv_nerv_block_fused", "bnerv_resblock_fused", "bnerv_debug_set_buffer",
 ]
 
 
@@ -84,6 +87,9 @@ def _load():
     lib.bnerv_pack_head_weight.argtypes = [vp, i, i, vp, vp]
     lib.bnerv_head_conv3.argtypes = [vp, i, i, i, i, vp, vp, i, i, vp, vp]
     lib.bnerv_nerv_block_fwd.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.bnerv_nerv_block_fused.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
+    lib.bnerv_resblock_fused.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, i, vp, vp, vp, vp]
+    lib.bnerv_debug_set_buffer.argtypes = [vp, i]
     lib.bnerv_head_conv1.argtypes = [vp, i, i, i, i, vp, vp, i, i, vp, vp]
     lib.bnerv_ssim_stats.argtypes = [vp, vp, i, i, i, f, f, vp, vp]
     lib.bnerv_ssim_grad.argtypes = [vp, vp, i, i, i, f, f, vp, vp, i, vp, vp]

@@ -109,6 +109,14 @@ class _BlockPlan:
                 raise Unsupported("SFT inner activation other than relu")
         self.cout = self.up.cout
         self.scale = (self.pre.s if self.pre else 1) * self.up.s
+        # One kernel per block for the narrow stages (bnerv_nerv_block_fused); when only the up-conv is too wide / has a
+        # PixelShuffle factor the fused kernel does not take, the ResBlock_SFT half alone is one kernel (bnerv_resblock_fused).
+        cp, cin_p = ops.round_up(self.cout, 16), ops.round_up(self.up.cin, 16)
+        self.fuse = None
+        if cp <= 48 and not os.environ.get("BNERV_NO_BLOCK_FUSION"):
+            whole = (self.up.k == 3 and self.up.s in (1, 2) and cin_p <= 64 and self.up.s ** 2 * cp <= 256
+                     and not os.environ.get("BNERV_NO_UP_FUSION"))
+            self.fuse = "block" if whole else "res"
 
 
 def _sft_tensors(sft):
@@ -126,6 +134,7 @@ class _Captured:
 
 class DecoderEngine:
     use_graph = True
+    fuse_blocks = True          # narrow NeRVBlocks as one kernel each (False: always three fused-conv launches)
 
     def __init__(self, model):
         self.model = model
@@ -301,13 +310,22 @@ class DecoderEngine:
                 ops.conv_fused(cur, blk.pre.packed(), cin, H, W, act="none", out_pre=mid)
                 cur, cin, H, W = mid, blk.pre.cout, H * blk.pre.s, W * blk.pre.s
             Ho, Wo = H * blk.up.s, W * blk.up.s
-            x0 = view(ws["x0"], blk.cout, Ho, Wo)
-            u = view(ws["u"], blk.cout, Ho, Wo)
-            ops.conv_fused(cur, blk.up.packed(), cin, H, W, act=blk.act, g1p=g0, beta=b0, out_pre=x0, out_aff=u)
-            wbuf = view(ws["w"], blk.cout, Ho, Wo)
-            ops.conv_fused(u, blk.c0.packed(), blk.cout, Ho, Wo, act=blk.inner_act, g1p=g1, beta=b1, out_aff=wbuf)
             out = view(nxt_buf, blk.cout, Ho, Wo)
-            ops.conv_fused(wbuf, blk.c1.packed(), blk.cout, Ho, Wo, act="none", resid=x0, out_pre=out)
+            done = None
+            if blk.fuse == "block" and self.fuse_blocks:
+                done = ops.nerv_block_fused(cur, blk.up.packed(), blk.c0.packed(), blk.c1.packed(), cin, H, W, blk.act,
+                                            blk.inner_act, g0, b0, g1, b1, out=out)
+            if done is None:
+                x0 = view(ws["x0"], blk.cout, Ho, Wo)
+                u = view(ws["u"], blk.cout, Ho, Wo)
+                ops.conv_fused(cur, blk.up.packed(), cin, H, W, act=blk.act, g1p=g0, beta=b0, out_pre=x0, out_aff=u)
+                if blk.fuse is not None and self.fuse_blocks:
+                    done = ops.resblock_fused(u, x0, blk.c0.packed(), blk.c1.packed(), blk.cout, Ho, Wo, blk.inner_act, g1, b1,
+                                              out=out)
+                if done is None:
+                    wbuf = view(ws["w"], blk.cout, Ho, Wo)
+                    ops.conv_fused(u, blk.c0.packed(), blk.cout, Ho, Wo, act=blk.inner_act, g1p=g1, beta=b1, out_aff=wbuf)
+                    ops.conv_fused(wbuf, blk.c1.packed(), blk.cout, Ho, Wo, act="none", resid=x0, out_pre=out)
             if keep is True or (keep == "first" and bi == 0):
                 outs.append(ops.c8_to_nchw(out, blk.cout))
             cur, cin, H, W = out, blk.cout, Ho, Wo

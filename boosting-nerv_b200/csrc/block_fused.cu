@@ -1,0 +1,795 @@
+// One kernel per NeRVBlock for the NARROW stages (C <= 48): up-conv (+PixelShuffle +sin) -> TAT affine -> conv3x3 -> GELU ->
+// TAT affine -> conv3x3 -> + x0, with every intermediate map (x0, u, w) resident in shared memory / TMEM.
+// Replaces NeRVBlock.forward (model_blocks.py:34-46) = UpConv (:213-220) + Sin (:129-134) + ResBlock_SFT (:83-89) with its
+// two SFTLayer affines (:101-105) by ONE launch that reads the block's input once and writes its output once.
+//
+// Why a second kernel next to conv_tc.cu: at <= 48 channels a conv launch is bound by its fixed costs and by the HBM round
+// trips of x0 / u / w (NeRV-S: 25 launches of ~13 us against an HBM floor of 29 us per frame); the weights of all three convs
+// are a few KB, so they stay resident and a CTA walks "regions" of the output map:
+//
+//   region R = Rh x Rw output pixels (multiples of 16 x 8 = one UMMA row block: 16 image rows x 8 px), output tile O = R
+//   shrunk by 2 px.  All three stages run over the SAME blocks of R; what shrinks is the part of R that is valid:
+//     up   : x0, u on all of R        (input tile = R + 1 px halo, TMA, zero-filled outside the image = conv padding)
+//     c0   : w = gelu(conv(u))*g1p+b1 valid on R - 1 px   (the border ring is computed from stale margins and never used)
+//     c1   : out = x0 + conv(w)       valid on R - 2 px = O
+//   Tile buffer T ((Rh+2) x (Rw+2) px, C8 f16, the UMMA A operand layout [group][row][px][16 B]) is reused IN PLACE:
+//   input (s = 1) -> u -> w, because a stage's epilogue starts only after ALL of its MMAs completed (tcgen05.commit).
+//   x0 of the O pixels waits in a second buffer for the residual.  Out-of-image pixels of u / w are written as exact zeros
+//   (the reference applies the affine BEFORE the next conv's zero padding, model_blocks.py:105 then :86).
+//
+// MMA: tcgen05.mma.cta_group::1 kind::f16, M = 128 (one row block), N = Cp (s*s*Cp for the up-conv), K = 16 per (tap, k step);
+// same descriptors as conv_tc.cu (no-swizzle K-major; tap (r, sx) = start-address offset into the halo tile).  Each stage's
+// blocks are committed in up to 4 groups so that the epilogue of group i overlaps the MMAs of group i+1; two CTAs per SM
+// (when shared memory allows) overlap one CTA's MMA phase with the other's epilogue phase.
+//
+// The arithmetic is the 3-launch path's, operation by operation (same accumulation order, same epilogue functions, f16
+// rounding of x0 / u / w at the same places), so bnerv_nerv_block_fused is expected to be BIT-IDENTICAL to
+// bnerv_nerv_block_fwd - that is what tests/test_gpu_block_fused.py checks.
+#include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include "common.cuh"
+
+namespace bnerv {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();          // conv_tc.cu
+
+constexpr int BF_EPI_THREADS = 256;           // 8 epilogue warps: TMEM lane quarter = warp & 3, two warps per quarter
+constexpr int BF_THREADS   = BF_EPI_THREADS + 32;   // + warp 8: TMA + MMA issue (one elected lane)
+constexpr int BF_REPS      = BF_EPI_THREADS / 128;
+constexpr int BF_GROUPS    = 4;               // a stage's row blocks are committed in 4 groups (block order) to 4 barriers
+constexpr int BF_MAX_CP    = 64;
+constexpr int BF_MAX_NUP   = 256;
+constexpr int BF_SMEM_MAX  = 227 * 1024;
+
+struct BfCst {                                // staged in shared memory
+    float b_up[BF_MAX_NUP];
+    float b_c0[BF_MAX_CP], b_c1[BF_MAX_CP];
+    float g0p[BF_MAX_CP], beta0[BF_MAX_CP], g1p[BF_MAX_CP], beta1[BF_MAX_CP];
+};
+
+struct BlockFusedArgs {
+    int B, H, W, s, Ho, Wo;
+    int has_up;                  // 0: x is u (conv0's input, already affine-transformed), resid is x0
+    int act_up, act_inner;
+    int cin_groups, ksteps_in;   // up-conv input channels / 8, / 16
+    int C, cgroups, ksteps;      // block channels: Cp / 8, Cp / 16
+    int cp;
+    int n_up;                    // s*s*Cp
+    int Rh, Rw, Oh, Ow;
+    int nby, nbx;                // row blocks of R
+    int iby, ibx;                // row blocks of the up stage's input-resolution region (== nby, nbx for s = 1)
+    int tiles_x, tiles_y, n_regions;
+    int t_pitch, t_rows, t_group_b;
+    int in_pitch, in_rows, in_group_b;
+    int in_is_t;                 // the TMA input lands in T (s == 1 or no up stage)
+    int in_ksteps;               // k steps of the TMA input (ksteps_in or ksteps)
+    uint32_t off_wup, off_wc0, off_wc1, off_t, off_in, off_x0, off_cst, off_bar;
+    int tmem_cols;
+    const __half *w_up, *w_c0, *w_c1;
+    const float *b_up, *b_c0, *b_c1, *g0p, *beta0, *g1p, *beta1;
+    const __half* resid;
+    __half* out;
+    int phase_delay_ns;          // start offset (clock cycles) of the second CTA on an SM (anti-phase, see the kernel)
+    long long* dbg;              // optional timestamps (bnerv_debug_set_buffer): [cta][region < 4][12] clock64 stamps
+    int dbg_ctas;
+};
+
+#define BF_STAMP(k) do { if (a.dbg && threadIdx.x == 0 && static_cast<int>(blockIdx.x) < a.dbg_ctas && dbg_reg < 4) \
+        a.dbg[(static_cast<size_t>(blockIdx.x) * 4 + dbg_reg) * 12 + (k)] = clock64(); } while (0)
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// packed global weights [tap][G][Np][8 halves] -> shared [kc][tap][g2][Np][8 halves] (G = 2*kc + g2): the B operand of
+// K step kc, tap t is one contiguous [2 groups][Np][16 B] slab (K-major no-swizzle: LBO = Np*16, SBO = 128).
+__device__ __forceinline__ void stage_weights(uint8_t* dst, const __half* src, int taps, int groups, int np) {
+    const int total = taps * groups * np;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int idx = threadIdx.x; idx < total; idx += BF_THREADS) {
+        const int n = idx % np;
+        const int rest = idx / np;
+        const int G = rest % groups, tap = rest / groups;
+        d4[(((G >> 1) * taps + tap) * 2 + (G & 1)) * np + n] = __ldg(s4 + idx);
+    }
+}
+
+// tcgen05.mma with the descriptors given as (lo, hi) 32-bit halves: only the 14-bit start-address field of `lo` changes
+// between the MMAs of a stage, so the issuing thread does one 32-bit add per operand instead of 64-bit or/shift chains
+// (a single thread's dependent integer chain, ~45 cycles per MMA, was what bounded the first version of this kernel).
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// One stage's MMAs: nby x nbx row blocks (16 rows x 8 px) of the tile at a_base, all 9 taps, `ksteps` K steps, N columns
+// per block at TMEM column b*N; block group g = [g*nb/4, (g+1)*nb/4) is committed to bar0 + 8*g (an empty group commits
+// too, so all four barriers complete once per stage).  One thread issues.
+__device__ __forceinline__ void issue_stage(uint32_t tmem_base, uint32_t a_base, int pitch, int group_b, int nby, int nbx,
+                                            int ksteps, uint32_t w_base, int N, uint32_t bar0) {
+    const uint32_t idesc = umma_idesc_f16(128, N);
+    const uint64_t a_d = umma_desc_hi_noswz(static_cast<uint32_t>(group_b), static_cast<uint32_t>(pitch) * 16u);
+    const uint64_t b_d = umma_desc_hi_noswz(static_cast<uint32_t>(N) * 16u, 128u);
+    const uint32_t a_hi = static_cast<uint32_t>(a_d >> 32), b_hi = static_cast<uint32_t>(b_d >> 32);
+    const uint32_t a_lo0 = static_cast<uint32_t>(a_d) | ((a_base & 0x3FFFFu) >> 4);
+    const uint32_t b_lo0 = static_cast<uint32_t>(b_d) | ((w_base & 0x3FFFFu) >> 4);
+    const uint32_t ks16 = static_cast<uint32_t>(2 * group_b) >> 4;    // one K step of A = 2 channel groups
+    const uint32_t tap16 = static_cast<uint32_t>(2 * N);              // one tap of B, in 16-byte units
+    const uint32_t p1 = static_cast<uint32_t>(pitch), p2 = 2u * p1;
+    const int nb = nby * nbx;
+    int b = 0, by = 0, bx = 0;
+    uint32_t d = tmem_base;
+#pragma unroll 1
+    for (int g = 0; g < BF_GROUPS; ++g) {
+        const int b_end = (g + 1) * nb / BF_GROUPS;
+#pragma unroll 1
+        for (; b < b_end; ++b) {
+            uint32_t al = a_lo0 + static_cast<uint32_t>(by * 16 * pitch + bx * 8);
+            uint32_t bl = b_lo0;
+#pragma unroll 1
+            for (int kc = 0; kc < ksteps; ++kc) {
+                umma_f16_lohi(d, al,          a_hi, bl,             b_hi, idesc, kc > 0 ? 1u : 0u);
+                umma_f16_lohi(d, al + 1,      a_hi, bl + tap16,     b_hi, idesc, 1u);
+                umma_f16_lohi(d, al + 2,      a_hi, bl + 2 * tap16, b_hi, idesc, 1u);
+                umma_f16_lohi(d, al + p1,     a_hi, bl + 3 * tap16, b_hi, idesc, 1u);
+                umma_f16_lohi(d, al + p1 + 1, a_hi, bl + 4 * tap16, b_hi, idesc, 1u);
+                umma_f16_lohi(d, al + p1 + 2, a_hi, bl + 5 * tap16, b_hi, idesc, 1u);
+                umma_f16_lohi(d, al + p2,     a_hi, bl + 6 * tap16, b_hi, idesc, 1u);
+                umma_f16_lohi(d, al + p2 + 1, a_hi, bl + 7 * tap16, b_hi, idesc, 1u);
+                umma_f16_lohi(d, al + p2 + 2, a_hi, bl + 8 * tap16, b_hi, idesc, 1u);
+                al += ks16;
+                bl += 9 * tap16;
+            }
+            d += static_cast<uint32_t>(N);
+            if (++bx == nbx) { bx = 0; ++by; }
+        }
+        umma_commit(bar0 + 8 * g);
+    }
+}
+
+__device__ __forceinline__ uint4 pack8f(const float2* x) {
+    uint4 o;
+    o.x = pack_h2_satfinite(x[0]); o.y = pack_h2_satfinite(x[1]);
+    o.z = pack_h2_satfinite(x[2]); o.w = pack_h2_satfinite(x[3]);
+    return o;
+}
+
+template <int ACT>
+__device__ __forceinline__ float2 bf_act2(float2 x, int act) {
+    if (ACT >= 0) return act2<ACT>(x);
+    switch (act) {
+        case BNERV_ACT_SIN:    return sin2(x);
+        case BNERV_ACT_GELU:   return gelu2(x);
+        case BNERV_ACT_RELU:   return act2<BNERV_ACT_RELU>(x);
+        case BNERV_ACT_TANH01: return tanh01_2(x);
+        default:               return x;
+    }
+}
+
+// x = v + bias for one 16-column accumulator group (bias: 16 floats in shared memory); v is dead afterwards, so the
+// caller can re-issue tcgen05.ld into it for the next item while the activation math of this one runs
+__device__ __forceinline__ void bias_add16(const uint32_t* v, const float* bias, float2* x) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float4 bs = *reinterpret_cast<const float4*>(bias + 4 * p);
+        x[2 * p]     = add2(make_float2(__uint_as_float(v[4 * p]),     __uint_as_float(v[4 * p + 1])), make_float2(bs.x, bs.y));
+        x[2 * p + 1] = add2(make_float2(__uint_as_float(v[4 * p + 2]), __uint_as_float(v[4 * p + 3])), make_float2(bs.z, bs.w));
+    }
+}
+
+// y = x * g + e for 8 channels (4 float2) with g / e from shared memory
+__device__ __forceinline__ void affine8(const float2* x, const float* g, const float* e, float2* y) {
+    const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+    const float4 e0 = *reinterpret_cast<const float4*>(e), e1 = *reinterpret_cast<const float4*>(e + 4);
+    y[0] = fma2(x[0], make_float2(g0.x, g0.y), make_float2(e0.x, e0.y));
+    y[1] = fma2(x[1], make_float2(g0.z, g0.w), make_float2(e0.z, e0.w));
+    y[2] = fma2(x[2], make_float2(g1.x, g1.y), make_float2(e1.x, e1.y));
+    y[3] = fma2(x[3], make_float2(g1.z, g1.w), make_float2(e1.z, e1.w));
+}
+
+struct Region { int b, oy0, ox0; };           // batch index, origin of the output tile O
+
+__device__ __forceinline__ Region decode_region(const BlockFusedArgs& a, int r) {
+    Region g;
+    const int tx = r % a.tiles_x;
+    const int rest = r / a.tiles_x;
+    const int ty = rest % a.tiles_y;
+    g.b = rest / a.tiles_y;
+    g.oy0 = ty * a.Oh;
+    g.ox0 = tx * a.Ow;
+    return g;
+}
+
+__device__ __forceinline__ int floor_div(int x, int d) { return (x >= 0) ? x / d : -((-x + d - 1) / d); }
+
+// TMA load of a region's input tile (1 px halo) - one box of 2 channel groups per K step.
+__device__ __forceinline__ void issue_input(const BlockFusedArgs& a, const CUtensorMap* tm, uint32_t dst, uint32_t bar, const Region& g) {
+    const int iy0 = floor_div(g.oy0 - 2, a.s), ix0 = floor_div(g.ox0 - 2, a.s);
+    mbar_expect_tx(bar, static_cast<uint32_t>(a.in_ksteps * 2 * a.in_group_b));
+    const int groups = a.has_up ? a.cin_groups : a.cgroups;
+    for (int kc = 0; kc < a.in_ksteps; ++kc)
+        tma_load_3d(dst + kc * 2 * a.in_group_b, tm, bar, 2 * (ix0 - 1), iy0 - 1, g.b * groups + 2 * kc);
+}
+
+template <int ACT_UP, int ACT_IN>
+__global__ void __launch_bounds__(BF_THREADS, 2)
+block_fused_kernel(const __grid_constant__ CUtensorMap tmIn, const BlockFusedArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const bool is_issuer = (warp == BF_EPI_THREADS / 32);
+    const int q = warp & 3, rep = (warp >> 2) & 1;
+    const int m = q * 32 + lane;                      // row of a row block == TMEM lane
+    const int my = m >> 3, mx = m & 7;
+
+    BfCst* cst = reinterpret_cast<BfCst*>(smem + a.off_cst);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.off_bar);       // [0] input, [1..4] MMA commit groups
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + BF_GROUPS);
+    const uint32_t in_bar = smem_u32(bars), mma_bar0 = smem_u32(bars + 1);
+    const uint32_t t_base = smem_u32(smem + a.off_t);
+    const uint32_t in_base = a.in_is_t ? t_base : smem_u32(smem + a.off_in);
+    uint8_t* t_ptr = smem + a.off_t;
+    uint8_t* x0_ptr = smem + a.off_x0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(in_bar, 1);
+        for (int g = 0; g < BF_GROUPS; ++g) mbar_init(mma_bar0 + 8 * g, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmIn);
+    }
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), static_cast<uint32_t>(a.tmem_cols));
+    // resident weights and biases (never written by a kernel that precedes this one in the stream: before the PDL wait)
+    stage_weights(smem + a.off_wc0, a.w_c0, 9, a.cgroups, a.cp);
+    stage_weights(smem + a.off_wc1, a.w_c1, 9, a.cgroups, a.cp);
+    if (a.has_up) {
+        stage_weights(smem + a.off_wup, a.w_up, 9, a.cin_groups, a.n_up);
+        for (int i = threadIdx.x; i < a.n_up; i += BF_THREADS) cst->b_up[i] = __ldg(a.b_up + i);
+    }
+    for (int i = threadIdx.x; i < a.cp; i += BF_THREADS) {
+        cst->b_c0[i] = __ldg(a.b_c0 + i);
+        cst->b_c1[i] = __ldg(a.b_c1 + i);
+    }
+    // the tile margins are read by the MMAs of border blocks (results unused): keep them finite
+    {
+        const int t_chunks = (a.in_is_t && a.has_up && a.cin_groups > a.cgroups ? a.cin_groups : a.cgroups) * a.t_group_b / 16;
+        uint4* t4 = reinterpret_cast<uint4*>(t_ptr);
+        for (int i = threadIdx.x; i < t_chunks; i += BF_THREADS) t4[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+    pdl_wait();                       // activations / TAT tables come from earlier kernels
+    pdl_launch_dependents();
+
+    // Two CTAs share an SM and would otherwise run in lockstep - both in their MMA phase (tensor pipe: shared-memory operand
+    // reads), then both in their epilogue phase (MUFU / TMEM reads) - so that nothing overlaps (measured: 27 k cycles per
+    // region pair = the SUM of the per-resource times).  The CTA that got the upper half of TMEM starts half a region late.
+    if (a.phase_delay_ns > 0 && (tmem_base & 0xFFFFu) != 0) {
+        long long t0 = clock64();
+        while (clock64() - t0 < a.phase_delay_ns) __nanosleep(200);
+    }
+
+    int r = blockIdx.x;
+    uint32_t in_phase = 0, mma_par = 0;               // all four commit barriers complete once per stage: one parity
+    const int nb = a.nby * a.nbx;                     // row blocks of R
+    const int inb = a.iby * a.ibx;
+    const int next_stride = gridDim.x;
+    int dbg_reg = -1;
+
+    if (is_issuer) {
+        // ============================ warp 8: TMA loads + MMA issue (one elected lane) ============================
+        const uint32_t wup_s = smem_u32(smem + a.off_wup), wc0_s = smem_u32(smem + a.off_wc0), wc1_s = smem_u32(smem + a.off_wc1);
+        auto wait_stage_mmas = [&]() {
+            for (int g = 0; g < BF_GROUPS; ++g) mbar_wait(mma_bar0 + 8 * g, mma_par);
+        };
+        if (r < a.n_regions && elect_one()) issue_input(a, &tmIn, in_base, in_bar, decode_region(a, r));
+        __syncwarp();
+        int cur_b = -1;
+        for (; r < a.n_regions; r += next_stride) {
+            ++dbg_reg;
+            const int next = r + next_stride;
+            const int rb = decode_region(a, r).b;
+            if (rb != cur_b) { cur_b = rb; __syncthreads(); __syncthreads(); }      // the epilogue warps restage the TAT tables
+            if (a.has_up) {
+                mbar_wait(in_bar, in_phase);
+                in_phase ^= 1;
+                tc_fence_after();
+                if (elect_one())
+                    issue_stage(tmem_base, in_base, a.in_pitch, a.in_group_b, a.iby, a.ibx, a.ksteps_in, wup_s, a.n_up, mma_bar0);
+                __syncwarp();
+                if (!a.in_is_t) {             // a separate input buffer is free as soon as the up-conv's MMAs have read it
+                    wait_stage_mmas();
+                    if (next < a.n_regions && elect_one()) issue_input(a, &tmIn, in_base, in_bar, decode_region(a, next));
+                    __syncwarp();
+                }
+                mma_par ^= 1u;
+                __syncthreads();              // (A) u complete in T
+                tc_fence_after();
+            }
+            if (!a.has_up) { mbar_wait(in_bar, in_phase); in_phase ^= 1; tc_fence_after(); }
+            if (elect_one())
+                issue_stage(tmem_base, t_base, a.t_pitch, a.t_group_b, a.nby, a.nbx, a.ksteps, wc0_s, a.cp, mma_bar0);
+            __syncwarp();
+            mma_par ^= 1u;
+            __syncthreads();                  // (B) w complete in T
+            tc_fence_after();
+            if (elect_one())
+                issue_stage(tmem_base, t_base, a.t_pitch, a.t_group_b, a.nby, a.nbx, a.ksteps, wc1_s, a.cp, mma_bar0);
+            __syncwarp();
+            if (a.in_is_t) {                  // every MMA that reads T has completed: the next region's input may land in it
+                wait_stage_mmas();
+                if (next < a.n_regions && elect_one()) issue_input(a, &tmIn, in_base, in_bar, decode_region(a, next));
+                __syncwarp();
+            }
+            mma_par ^= 1u;
+            __syncthreads();                  // (C) accumulators and x0 buffer free
+            tc_fence_after();
+        }
+    } else {
+        // ============================ warps 0..7: epilogues ============================
+        uint32_t waited = 0;                          // commit groups this thread has already waited for in the current stage
+        auto wait_grp = [&](int g) {
+            if (!((waited >> g) & 1u)) { mbar_wait(mma_bar0 + 8 * g, mma_par); waited |= 1u << g; }
+        };
+        auto wait_all = [&]() {
+#pragma unroll
+            for (int g = 0; g < BF_GROUPS; ++g) wait_grp(g);
+            tc_fence_after();
+        };
+        auto stage_done = [&]() { wait_all(); mma_par ^= 1u; waited = 0; };
+        const int n16 = a.cp >> 4;                    // 16-column groups per block (c0 / c1)
+        const int n16_up = a.n_up >> 4;
+        const size_t plane = static_cast<size_t>(a.Ho) * a.Wo * 8;
+        int cur_b = -1;
+
+        for (; r < a.n_regions; r += next_stride) {
+            ++dbg_reg;
+            const Region rg = decode_region(a, r);
+            const int ry0 = rg.oy0 - 2, rx0 = rg.ox0 - 2;     // origin of R in the output map
+            if (rg.b != cur_b) {                               // TAT tables of this frame (block-uniform branch)
+                cur_b = rg.b;
+                __syncthreads();
+                for (int i = threadIdx.x; i < a.cp; i += BF_EPI_THREADS) {
+                    if (a.has_up) {
+                        cst->g0p[i] = __ldg(a.g0p + static_cast<size_t>(rg.b) * a.cp + i);
+                        cst->beta0[i] = __ldg(a.beta0 + static_cast<size_t>(rg.b) * a.cp + i);
+                    }
+                    cst->g1p[i] = __ldg(a.g1p + static_cast<size_t>(rg.b) * a.cp + i);
+                    cst->beta1[i] = __ldg(a.beta1 + static_cast<size_t>(rg.b) * a.cp + i);
+                }
+                __syncthreads();
+            }
+            BF_STAMP(0);
+            if (a.dbg && threadIdx.x == 0 && static_cast<int>(blockIdx.x) < a.dbg_ctas && dbg_reg < 4) {
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                a.dbg[(static_cast<size_t>(blockIdx.x) * 4 + dbg_reg) * 12 + 11] = smid;
+                unsigned long long gt;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                a.dbg[(static_cast<size_t>(blockIdx.x) * 4 + dbg_reg) * 12 + 10] = static_cast<long long>(gt);
+            }
+
+            // ============================= up stage: x0 = act(PS(conv(x))), u = x0*g0p + beta0 =============================
+            if (a.has_up) {
+                // in place (s = 1: u overwrites the input tile): no store before EVERY MMA of the stage has read its operands
+                if (a.in_is_t) wait_all();
+                BF_STAMP(1);
+                const int n_items = inb * n16_up;
+                uint32_t v[16];
+                int idx = rep;
+                if (idx < n_items) {
+                    const int b = idx / n16_up;
+                    wait_grp(((b + 1) * BF_GROUPS - 1) / inb);
+                    tc_fence_after();
+                    tmem_ld16(tmem_lane + static_cast<uint32_t>(b * a.n_up + (idx - b * n16_up) * 16), v);
+                }
+                for (; idx < n_items; idx += BF_REPS) {
+                    const int b = idx / n16_up, g16 = idx - b * n16_up;
+                    tmem_ld_wait();
+                    float2 x[8];
+                    bias_add16(v, cst->b_up + g16 * 16, x);
+                    {                                                    // next item's accumulators: in flight during the math below
+                        const int nidx = idx + BF_REPS;
+                        if (nidx < n_items) {
+                            const int nb_ = nidx / n16_up;
+                            wait_grp(((nb_ + 1) * BF_GROUPS - 1) / inb);
+                            tc_fence_after();
+                            tmem_ld16(tmem_lane + static_cast<uint32_t>(nb_ * a.n_up + (nidx - nb_ * n16_up) * 16), v);
+                        }
+                    }
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) x[p] = bf_act2<ACT_UP>(x[p], a.act_up);
+                    const int by = b / a.ibx, bx = b - by * a.ibx;
+                    const int py = by * 16 + my, px = bx * 8 + mx;        // pixel of the input-resolution region
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        int G, ry, rx;                                    // channel group, pixel relative to R
+                        if (a.s == 1) { G = 2 * g16 + hh; ry = py; rx = px; }
+                        else {                                            // s == 2: packed row order [i][c/8][j][c%8]
+                            const int i = g16 / a.cgroups;
+                            G = g16 - i * a.cgroups;
+                            ry = 2 * py + i; rx = 2 * px + hh;
+                        }
+                        const int oy = ry0 + ry, ox = rx0 + rx;
+                        const bool inside = (oy >= 0) && (oy < a.Ho) && (ox >= 0) && (ox < a.Wo);
+                        float2 y[4];
+                        affine8(x + 4 * hh, cst->g0p + 8 * G, cst->beta0 + 8 * G, y);
+                        uint4 uo = pack8f(y);
+                        if (!inside) uo = make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4*>(t_ptr + static_cast<size_t>(G) * a.t_group_b + ((ry + 1) * a.t_pitch + rx + 1) * 16) = uo;
+                        const int qy = ry - 2, qx = rx - 2;
+                        if (qy >= 0 && qy < a.Oh && qx >= 0 && qx < a.Ow)
+                            *reinterpret_cast<uint4*>(x0_ptr + (static_cast<size_t>(G * a.Oh + qy) * a.Ow + qx) * 16) = pack8f(x + 4 * hh);
+                    }
+                }
+                stage_done();
+                BF_STAMP(2);
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncthreads();              // (A)
+                tc_fence_after();
+                BF_STAMP(3);
+            }
+
+            // ============================= c0 stage: w = act_inner(conv3(u))*g1p + beta1 =============================
+            {
+                // w overwrites u in place: a block's epilogue must not store while a neighbouring block's MMAs still read u
+                wait_all();
+                BF_STAMP(5);
+                const int n_items = nb * n16;
+                uint32_t v[16];
+                int idx = rep;
+                if (idx < n_items) {
+                    const int b = idx / n16;
+                    tmem_ld16(tmem_lane + static_cast<uint32_t>(b * a.cp + (idx - b * n16) * 16), v);
+                }
+                for (; idx < n_items; idx += BF_REPS) {
+                    const int b = idx / n16, g16 = idx - b * n16;
+                    tmem_ld_wait();
+                    float2 x[8];
+                    bias_add16(v, cst->b_c0 + g16 * 16, x);
+                    {
+                        const int nidx = idx + BF_REPS;
+                        if (nidx < n_items) {
+                            const int nb_ = nidx / n16;
+                            tmem_ld16(tmem_lane + static_cast<uint32_t>(nb_ * a.cp + (nidx - nb_ * n16) * 16), v);
+                        }
+                    }
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) x[p] = bf_act2<ACT_IN>(x[p], a.act_inner);
+                    const int by = b / a.nbx, bx = b - by * a.nbx;
+                    const int ry = by * 16 + my, rx = bx * 8 + mx;
+                    const int oy = ry0 + ry, ox = rx0 + rx;
+                    const bool inside = (oy >= 0) && (oy < a.Ho) && (ox >= 0) && (ox < a.Wo);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int G = 2 * g16 + hh;
+                        float2 y[4];
+                        affine8(x + 4 * hh, cst->g1p + 8 * G, cst->beta1 + 8 * G, y);
+                        uint4 wo = pack8f(y);
+                        if (!inside) wo = make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4*>(t_ptr + static_cast<size_t>(G) * a.t_group_b + ((ry + 1) * a.t_pitch + rx + 1) * 16) = wo;
+                    }
+                }
+                stage_done();
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncthreads();              // (B)
+                tc_fence_after();
+                BF_STAMP(6);
+            }
+
+            // ============================= c1 stage: out = x0 + conv3(w) =============================
+            {
+                const int n_items = nb * n16;
+                uint32_t v[16];
+                int idx = rep;
+                if (idx < n_items) {
+                    const int b = idx / n16;
+                    wait_grp(((b + 1) * BF_GROUPS - 1) / nb);
+                    tc_fence_after();
+                    tmem_ld16(tmem_lane + static_cast<uint32_t>(b * a.cp + (idx - b * n16) * 16), v);
+                }
+                for (; idx < n_items; idx += BF_REPS) {
+                    const int b = idx / n16, g16 = idx - b * n16;
+                    const int by = b / a.nbx, bx = b - by * a.nbx;
+                    const int ry = by * 16 + my, rx = bx * 8 + mx;
+                    const int qy = ry - 2, qx = rx - 2;
+                    const int oy = ry0 + ry, ox = rx0 + rx;
+                    const bool valid = (qy >= 0) && (qy < a.Oh) && (qx >= 0) && (qx < a.Ow) && (oy < a.Ho) && (ox < a.Wo);
+                    const size_t goff = ((static_cast<size_t>(rg.b) * a.cgroups + 2 * g16) * a.Ho + oy) * static_cast<size_t>(a.Wo) * 8 +
+                                        static_cast<size_t>(ox) * 8;
+                    uint4 rr[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+                    if (valid) {
+                        if (a.has_up) {
+                            rr[0] = *reinterpret_cast<const uint4*>(x0_ptr + (static_cast<size_t>((2 * g16) * a.Oh + qy) * a.Ow + qx) * 16);
+                            rr[1] = *reinterpret_cast<const uint4*>(x0_ptr + (static_cast<size_t>((2 * g16 + 1) * a.Oh + qy) * a.Ow + qx) * 16);
+                        } else {
+                            rr[0] = __ldg(reinterpret_cast<const uint4*>(a.resid + goff));
+                            rr[1] = __ldg(reinterpret_cast<const uint4*>(a.resid + goff + plane));
+                        }
+                    }
+                    tmem_ld_wait();
+                    float2 x[8];
+                    bias_add16(v, cst->b_c1 + g16 * 16, x);
+                    {
+                        const int nidx = idx + BF_REPS;
+                        if (nidx < n_items) {
+                            const int nb_ = nidx / n16;
+                            wait_grp(((nb_ + 1) * BF_GROUPS - 1) / nb);
+                            tc_fence_after();
+                            tmem_ld16(tmem_lane + static_cast<uint32_t>(nb_ * a.cp + (nidx - nb_ * n16) * 16), v);
+                        }
+                    }
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        x[4 * hh + 0] = add2(x[4 * hh + 0], unpack_h2(rr[hh].x)); x[4 * hh + 1] = add2(x[4 * hh + 1], unpack_h2(rr[hh].y));
+                        x[4 * hh + 2] = add2(x[4 * hh + 2], unpack_h2(rr[hh].z)); x[4 * hh + 3] = add2(x[4 * hh + 3], unpack_h2(rr[hh].w));
+                    }
+                    if (valid) {
+                        *reinterpret_cast<uint4*>(a.out + goff) = pack8f(x);
+                        *reinterpret_cast<uint4*>(a.out + goff + plane) = pack8f(x + 4);
+                    }
+                }
+                stage_done();
+                BF_STAMP(8);
+                tc_fence_before();
+                __syncthreads();              // (C) TMEM accumulators and the x0 buffer are free for the next region
+                tc_fence_after();
+                BF_STAMP(9);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, static_cast<uint32_t>(a.tmem_cols));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int bf_make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_b,
+                       uint64_t stride2_b, uint32_t b0, uint32_t b1, uint32_t b2) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return set_error(BNERV_E_NODRIVER, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_b, stride2_b};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(static_cast<int>(r), "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+    return 0;
+}
+
+static uint32_t align_up_u32(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+
+struct BfPlan { BlockFusedArgs a; size_t smem; int ctas_per_sm; };
+
+// Fills geometry + shared-memory layout for region (Rh, Rw); returns false when it does not fit one SM.
+static bool bf_plan(BlockFusedArgs& a, int Rh, int Rw, size_t& smem_bytes, int& tmem_cols) {
+    a.Rh = Rh; a.Rw = Rw; a.Oh = Rh - 4; a.Ow = Rw - 4;
+    a.nby = Rh / 16; a.nbx = Rw / 8;
+    if (a.has_up && a.s == 2) { a.iby = Rh / 32; a.ibx = Rw / 16; } else { a.iby = a.nby; a.ibx = a.nbx; }
+    a.tiles_x = (a.Wo + a.Ow - 1) / a.Ow;
+    a.tiles_y = (a.Ho + a.Oh - 1) / a.Oh;
+    const long long regions = 1LL * a.B * a.tiles_x * a.tiles_y;
+    if (regions > 0x3fffffffLL) return false;
+    a.n_regions = static_cast<int>(regions);
+    a.t_pitch = Rw + 2; a.t_rows = Rh + 2; a.t_group_b = a.t_rows * a.t_pitch * 16;
+    a.in_is_t = (!a.has_up || a.s == 1) ? 1 : 0;
+    if (a.in_is_t) { a.in_pitch = a.t_pitch; a.in_rows = a.t_rows; }
+    else { a.in_pitch = a.ibx * 8 + 2; a.in_rows = a.iby * 16 + 2; }
+    a.in_group_b = a.in_rows * a.in_pitch * 16;
+    a.in_ksteps = a.has_up ? a.ksteps_in : a.ksteps;
+    if (2 * a.in_pitch > 256 || a.in_rows > 256) return false;
+    const int t_groups = (a.in_is_t && a.has_up && a.cin_groups > a.cgroups) ? a.cin_groups : a.cgroups;
+    uint32_t off = 0;
+    a.off_wc0 = off; off += 9u * a.cp * a.cp * 2u;
+    a.off_wc1 = off; off += 9u * a.cp * a.cp * 2u;
+    a.off_wup = off; if (a.has_up) off += 9u * (a.cin_groups * 8) * a.n_up * 2u;
+    off = align_up_u32(off, 1024);
+    a.off_t = off; off += static_cast<uint32_t>(t_groups) * a.t_group_b;
+    off = align_up_u32(off, 1024);
+    a.off_in = off; if (!a.in_is_t) off += static_cast<uint32_t>(a.cin_groups) * a.in_group_b;
+    off = align_up_u32(off, 128);
+    a.off_x0 = off; if (a.has_up) off += static_cast<uint32_t>(a.cgroups) * a.Oh * a.Ow * 16u;
+    off = align_up_u32(off, 16);
+    a.off_cst = off; off += static_cast<uint32_t>(sizeof(BfCst));
+    off = align_up_u32(off, 16);
+    a.off_bar = off; off += (1 + BF_GROUPS) * 8 + 16;
+    smem_bytes = off;
+    int cols = a.nby * a.nbx * a.cp;
+    if (a.has_up) { const int c2 = a.iby * a.ibx * a.n_up; if (c2 > cols) cols = c2; }
+    if (cols > 512) return false;
+    tmem_cols = 32;
+    while (tmem_cols < cols) tmem_cols *= 2;
+    // descriptor fields: LBO / SBO are 14-bit counts of 16 bytes
+    if ((a.t_group_b >> 4) > 0x3FFF || (a.in_group_b >> 4) > 0x3FFF) return false;
+    return smem_bytes <= static_cast<size_t>(BF_SMEM_MAX);
+}
+
+static int g_bf_sms = 0;
+static long long* g_bf_dbg = nullptr;
+static int g_bf_dbg_ctas = 0;
+
+static int bf_launch(const void* x, BlockFusedArgs& a, cudaStream_t stream) {
+    if (g_bf_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_bf_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_bf_sms <= 0) g_bf_sms = 148;
+    }
+    // Region choice: among the shapes that fit, minimise (waves of regions over the grid) x (pixels a region computes),
+    // preferring two CTAs per SM (one CTA's MMA phase overlaps the other's epilogue phase).
+    static const int forced_rh = getenv("BNERV_BF_RH") ? atoi(getenv("BNERV_BF_RH")) : 0;
+    static const int forced_rw = getenv("BNERV_BF_RW") ? atoi(getenv("BNERV_BF_RW")) : 0;
+    const int rh_step = (a.has_up && a.s == 2) ? 32 : 16, rw_step = (a.has_up && a.s == 2) ? 16 : 8;
+    double best_cost = 0.0;
+    int best_rh = 0, best_rw = 0, best_cps = 1, best_cols = 0;
+    size_t best_smem = 0;
+    for (int rh = rh_step; rh <= 64; rh += rh_step) {
+        for (int rw = rw_step; rw <= 64; rw += rw_step) {
+            if (forced_rh && (rh != forced_rh || rw != forced_rw)) continue;
+            BlockFusedArgs t = a;
+            size_t smem = 0;
+            int cols = 0;
+            if (!bf_plan(t, rh, rw, smem, cols)) continue;
+            int cps = 1;
+            if (2 * (smem + 1024) <= static_cast<size_t>(228 * 1024) && 2 * cols <= 512) cps = 2;
+            const long long slots = 1LL * g_bf_sms * cps;
+            const long long waves = (t.n_regions + slots - 1) / slots;
+            // per-SM time ~ regions an SM processes x region work; one CTA per SM loses the MMA/epilogue overlap
+            double cost = static_cast<double>(waves) * cps * rh * rw * (cps == 2 ? 1.0 : 1.35);
+            cost += 1e-7 * static_cast<double>(t.n_regions) * rh * rw;       // ties: less halo over-compute
+            if (best_rh == 0 || cost < best_cost) {
+                best_cost = cost; best_rh = rh; best_rw = rw; best_cps = cps; best_cols = cols; best_smem = smem;
+            }
+        }
+    }
+    if (best_rh == 0) return set_error(BNERV_E_UNSUPPORTED, "nerv_block_fused: no region shape fits (C = %d, Cin groups = %d, s = %d)",
+                                       a.C, a.cin_groups, a.s);
+    size_t smem = 0;
+    int cols = 0;
+    bf_plan(a, best_rh, best_rw, smem, cols);
+    a.tmem_cols = best_cols;
+    (void)best_smem;
+
+    a.dbg = g_bf_dbg; a.dbg_ctas = g_bf_dbg_ctas;
+    {
+        // anti-phase offset ~ half a region: ~3 stages x (MMA + epilogue) / 2, estimated from the region size (cycles)
+        static const int forced_delay = getenv("BNERV_BF_DELAY") ? atoi(getenv("BNERV_BF_DELAY")) : -1;
+        const int est = 6 * a.nby * a.nbx * a.ksteps * 9 * 16;      // ~ half of 3 stages x blocks x 9*ksteps MMAs x ~32 cycles
+        a.phase_delay_ns = best_cps == 2 ? (forced_delay >= 0 ? forced_delay : est) : 0;
+    }
+    CUtensorMap tm;
+    const int in_groups = a.has_up ? a.cin_groups : a.cgroups;
+    const int inH = a.has_up ? a.H : a.Ho, inW = a.has_up ? a.W : a.Wo;
+    int rc = bf_make_map(&tm, x, 2ull * inW, inH, 1ull * a.B * in_groups, 16ull * inW, 16ull * inW * inH,
+                         2 * a.in_pitch, a.in_rows, 2);
+    if (rc) return rc;
+
+    using KernelFn = void (*)(const CUtensorMap, const BlockFusedArgs);
+    KernelFn fn = block_fused_kernel<-1, -1>;
+    int slot = 0;
+    if (a.act_up == BNERV_ACT_SIN && a.act_inner == BNERV_ACT_GELU) { fn = block_fused_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU>; slot = 1; }
+    static bool attr_set[2][32] = {};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (!attr_set[slot][cur_dev & 31]) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_MAX);
+        if (e != cudaSuccess) return set_error(static_cast<int>(e), "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+        cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_set[slot][cur_dev & 31] = true;
+    }
+    const long long slots = 1LL * g_bf_sms * best_cps;
+    static const bool verbose = getenv("BNERV_BF_VERBOSE") != nullptr;
+    if (verbose)
+        fprintf(stderr, "block_fused: C=%d cin_groups=%d s=%d has_up=%d %dx%d -> region %dx%d, %d regions, %d CTAs/SM, smem %zu B, "
+                "TMEM cols %d\n", a.C, a.cin_groups, a.s, a.has_up, a.Ho, a.Wo, a.Rh, a.Rw, a.n_regions, best_cps, smem, a.tmem_cols);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(a.n_regions < slots ? a.n_regions : slots));
+    cfg.blockDim = dim3(BF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("BNERV_NO_PDL") != nullptr;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, tm, a);
+    if (e != cudaSuccess) {
+        count_launch();
+        return set_error(static_cast<int>(e), "block_fused_kernel launch: %s", cudaGetErrorString(e));
+    }
+    return check_launch("block_fused_kernel");
+}
+
+}  // namespace bnerv
+
+using namespace bnerv;
+
+// Bring-up instrumentation (not part of the product ABI's data path): when set, thread 0 of the first `n_ctas` CTAs of the
+// following fused-block launches records clock64 stamps of its first 4 regions into buf[n_ctas][4][12] (10 phase stamps, slot 11
+// = SM id).  Pass NULL to switch off.
+extern "C" int bnerv_debug_set_buffer(void* buf, int n_ctas) {
+    bnerv::g_bf_dbg = static_cast<long long*>(buf);
+    bnerv::g_bf_dbg_ctas = buf ? n_ctas : 0;
+    return 0;
+}
+
+extern "C" int bnerv_nerv_block_fused(const void* x, int B, int Cin, int H, int W, const void* w_up, const float* b_up, int k_up,
+                                      int s, int act_up, const void* w_c0, const float* b_c0, const void* w_c1, const float* b_c1,
+                                      int C, int act_inner, const float* g0p, const float* beta0, const float* g1p,
+                                      const float* beta1, void* out, void* stream) {
+    if (!x || !w_up || !b_up || !w_c0 || !b_c0 || !w_c1 || !b_c1 || !out) return set_error(BNERV_E_BADARG, "nerv_block_fused: null pointer");
+    if (!g0p || !beta0 || !g1p || !beta1) return set_error(BNERV_E_BADARG, "nerv_block_fused: the four TAT tables are required");
+    if (B <= 0 || Cin <= 0 || C <= 0 || H <= 0 || W <= 0) return set_error(BNERV_E_BADARG, "nerv_block_fused: non-positive size");
+    if (k_up != 3) return set_error(BNERV_E_UNSUPPORTED, "nerv_block_fused: up-conv kernel size %d (only 3)", k_up);
+    if (s != 1 && s != 2) return set_error(BNERV_E_UNSUPPORTED, "nerv_block_fused: PixelShuffle factor %d (only 1 and 2)", s);
+    const int cp = round_up(C, 16), cin_p = round_up(Cin, 16);
+    if (cp > 48 || cin_p > 64) return set_error(BNERV_E_UNSUPPORTED, "nerv_block_fused: C = %d / Cin = %d outside the narrow range", C, Cin);
+    if (s * s * cp > BF_MAX_NUP) return set_error(BNERV_E_UNSUPPORTED, "nerv_block_fused: up-conv N = %d", s * s * cp);
+    if (act_up < BNERV_ACT_NONE || act_up > BNERV_ACT_TANH01 || act_inner < BNERV_ACT_NONE || act_inner > BNERV_ACT_TANH01)
+        return set_error(BNERV_E_UNSUPPORTED, "nerv_block_fused: activation code");
+    const uintptr_t align_or = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_up) | reinterpret_cast<uintptr_t>(w_c0) |
+                               reinterpret_cast<uintptr_t>(w_c1) | reinterpret_cast<uintptr_t>(out);
+    if (align_or & 15) return set_error(BNERV_E_BADARG, "nerv_block_fused: pointers must be 16-byte aligned");
+    BlockFusedArgs a{};
+    a.B = B; a.H = H; a.W = W; a.s = s; a.Ho = H * s; a.Wo = W * s;
+    a.has_up = 1; a.act_up = act_up; a.act_inner = act_inner;
+    a.cin_groups = cin_p / 8; a.ksteps_in = cin_p / 16;
+    a.C = C; a.cp = cp; a.cgroups = cp / 8; a.ksteps = cp / 16;
+    a.n_up = s * s * cp;
+    a.w_up = static_cast<const __half*>(w_up); a.w_c0 = static_cast<const __half*>(w_c0); a.w_c1 = static_cast<const __half*>(w_c1);
+    a.b_up = b_up; a.b_c0 = b_c0; a.b_c1 = b_c1;
+    a.g0p = g0p; a.beta0 = beta0; a.g1p = g1p; a.beta1 = beta1;
+    a.resid = nullptr;
+    a.out = static_cast<__half*>(out);
+    return bf_launch(x, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bnerv_resblock_fused(const void* u, const void* x0, int B, int C, int H, int W, const void* w_c0, const float* b_c0,
+                                    const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1,
+                                    void* out, void* stream) {
+    if (!u || !x0 || !w_c0 || !b_c0 || !w_c1 || !b_c1 || !g1p || !beta1 || !out) return set_error(BNERV_E_BADARG, "resblock_fused: null pointer");
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return set_error(BNERV_E_BADARG, "resblock_fused: non-positive size");
+    const int cp = round_up(C, 16);
+    if (cp > 48) return set_error(BNERV_E_UNSUPPORTED, "resblock_fused: C = %d outside the narrow range", C);
+    if (act_inner < BNERV_ACT_NONE || act_inner > BNERV_ACT_TANH01) return set_error(BNERV_E_UNSUPPORTED, "resblock_fused: activation code");
+    const uintptr_t align_or = reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(w_c0) |
+                               reinterpret_cast<uintptr_t>(w_c1) | reinterpret_cast<uintptr_t>(out);
+    if (align_or & 15) return set_error(BNERV_E_BADARG, "resblock_fused: pointers must be 16-byte aligned");
+    BlockFusedArgs a{};
+    a.B = B; a.H = H; a.W = W; a.s = 1; a.Ho = H; a.Wo = W;
+    a.has_up = 0; a.act_up = BNERV_ACT_NONE; a.act_inner = act_inner;
+    a.C = C; a.cp = cp; a.cgroups = cp / 8; a.ksteps = cp / 16;
+    a.cin_groups = a.cgroups; a.ksteps_in = a.ksteps;
+    a.n_up = cp;
+    a.w_c0 = static_cast<const __half*>(w_c0); a.w_c1 = static_cast<const __half*>(w_c1);
+    a.b_c0 = b_c0; a.b_c1 = b_c1;
+    a.g1p = g1p; a.beta1 = beta1;
+    a.resid = static_cast<const __half*>(x0);
+    a.out = static_cast<__half*>(out);
+    return bf_launch(u, a, static_cast<cudaStream_t>(stream));
+}

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define BNERV_ABI_VERSION 3
+#define BNERV_ABI_VERSION 4
 
 /* error codes (negative) */
 #define BNERV_E_BADARG      (-1)   /* null pointer / non-positive size / misaligned pointer          */
@@ -120,6 +120,28 @@ int bnerv_nerv_block_fwd(const void* x, int B, int Cin, int H, int W, const void
                          int s, int act_up, const void* w_c0, const float* b_c0, const void* w_c1, const float* b_c1,
                          int C, int act_inner, const float* g0p, const float* beta0, const float* g1p,
                          const float* beta1, void* x0, void* u, void* wmap, void* out, void* stream);
+
+/* ONE kernel per NeRVBlock for the narrow stages (C <= 48 channels; north_star: "each NeRVBlock is a single fused kernel that
+ * stages the small per-stage feature map in shared memory"): same contract and the same arithmetic, operation by operation,
+ * as bnerv_nerv_block_fwd (bit-identical results), but x0, u and w never leave the SM - a CTA keeps the weights of all three
+ * convs resident and walks regions of the output map; the region's tile is rewritten in place (input -> u -> w) between the
+ * three tcgen05 stages, x0 waits in shared memory for the residual.  One read of x, one write of out.
+ *   Supported: k_up = 3, s in {1, 2}, round_up(C,16) <= 48, round_up(Cin,16) <= 64, s*s*round_up(C,16) <= 256; anything else
+ *   returns BNERV_E_UNSUPPORTED (nothing launched) and the caller uses bnerv_nerv_block_fwd. */
+int bnerv_nerv_block_fused(const void* x, int B, int Cin, int H, int W, const void* w_up, const float* b_up, int k_up,
+                           int s, int act_up, const void* w_c0, const float* b_c0, const void* w_c1, const float* b_c1,
+                           int C, int act_inner, const float* g0p, const float* beta0, const float* g1p,
+                           const float* beta1, void* out, void* stream);
+/* The ResBlock_SFT half alone (model_blocks.py:83-89) for blocks whose up-conv is too wide to fuse (PixelShuffle 3 / 5, wide
+ * inputs): u = x0*g0p + beta0 and x0 come from a bnerv_conv_fused launch;  out = x0 + conv3(act_inner(conv3(u))*g1p + beta1).
+ * u, x0, out: C8 f16 [B][C_p/8][H][W][8]; round_up(C,16) <= 48. */
+int bnerv_resblock_fused(const void* u, const void* x0, int B, int C, int H, int W, const void* w_c0, const float* b_c0,
+                         const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1,
+                         void* out, void* stream);
+
+/* Bring-up instrumentation for the fused-block kernel: device buffer of n_ctas*4*12 int64 receiving clock64 phase stamps of
+ * the first 4 regions of the first n_ctas CTAs of subsequent launches (slot 11 = SM id); NULL switches it off. */
+int bnerv_debug_set_buffer(void* buf, int n_ctas);
 
 /* The 3x3 head conv to <= 3 channels (HNeRV_Boost.head_layer, model_hnerv.py:214,273) + OutImg (model_blocks.py:57-63)
  * in its own form: out[p,c] = act(b[c] + sum_tap P[p+tap][(tap,c)]) with P = X . Wp ONE 1x1 tensor-core contraction to

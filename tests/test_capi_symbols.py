@@ -23,7 +23,7 @@ def test_header_symbols_are_exported():
 def test_sizes_and_argument_errors_without_a_gpu():
     from bnerv_b200 import _capi
     lib = _capi.lib
-    assert lib.bnerv_abi_version() == 3
+    assert lib.bnerv_abi_version() == 4
     assert lib.bnerv_c8_numel(2, 135, 4, 5) == 2 * 144 * 20
     assert lib.bnerv_packed_weight_numel(135, 162, 3, 2) == 9 * 176 * 4 * 144
     assert lib.bnerv_packed_bias_numel(112, 2) == 448

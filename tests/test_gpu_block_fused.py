@@ -1,0 +1,128 @@
+"""GPU: the one-kernel NeRVBlock (bnerv_nerv_block_fused / bnerv_resblock_fused, csrc/block_fused.cu) against the
+three-launch form (bnerv_nerv_block_fwd) it replaces, and against the reference block goldens.
+
+The fused kernel performs the same arithmetic operation by operation (same K order of the tensor-core accumulation, same
+epilogue functions, f16 rounding of x0 / u / w at the same places), so the gate is BIT-EXACT equality with the three-launch
+path - whose parity with the reference (model_blocks.py:34-46, 83-89, 101-105) is pinned by the block goldens and the
+model tests.  Shapes cover every narrow stage of the benchmarked presets (12, 15, 21, 30, 43 channels; PixelShuffle 1 and 2;
+Cin != C), ragged sizes that are not multiples of the region / row-block sizes, a map smaller than one region and B > 1."""
+import pytest
+import torch
+
+from conftest import load_block_golden, max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from bnerv_b200 import ops as o
+    return o
+
+
+def make_block(ops, B, cin, C, H, W, s, seed=0, k_up=3):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dev = "cuda"
+    rn = lambda *shape: torch.randn(*shape, device=dev, generator=g)
+    x = rn(B, cin, H, W)
+    w_up = rn(C * s * s, cin, k_up, k_up) / (cin * k_up * k_up) ** 0.5 * 2.0
+    b_up = rn(C * s * s) * 0.3
+    w_c0, b_c0 = rn(C, C, 3, 3) / (C * 9) ** 0.5 * 2.0, rn(C) * 0.3
+    w_c1, b_c1 = rn(C, C, 3, 3) / (C * 9) ** 0.5, rn(C) * 0.1
+    cp = ops.round_up(C, 16)
+    tabs = []
+    for i in range(4):
+        t = torch.zeros(B, cp, device=dev)
+        t[:, :C] = (1.0 if i % 2 == 0 else 0.0) + 0.3 * rn(B, C)
+        tabs.append(t)
+    return (ops.nchw_to_c8(x), ops.PackedConv(w_up, b_up, s), ops.PackedConv(w_c0, b_c0, 1), ops.PackedConv(w_c1, b_c1, 1), tabs)
+
+
+CASES = [  # B, cin, C, H, W, s
+    (1, 12, 12, 64, 96, 1),       # NeRV-S / XS s = 1 stage
+    (1, 12, 12, 45, 80, 2),       # NeRV up stage: 12 -> 48 + PixelShuffle(2)
+    (1, 30, 15, 45, 80, 2),       # NeRV-S layers.1: Cin_p = 32 -> Cp = 16
+    (1, 15, 12, 33, 47, 2),       # ragged: odd sizes
+    (2, 12, 12, 37, 51, 1),       # B > 1, ragged
+    (1, 12, 12, 7, 9, 1),         # smaller than one region
+    (1, 21, 21, 56, 72, 1),       # E-NeRV-M 1080p stage width (Cp = 32)
+    (1, 43, 21, 30, 44, 2),       # E-NeRV-M layers.6
+    (1, 43, 43, 40, 56, 1),       # E-NeRV-M 540p stage width (Cp = 48)
+    (3, 15, 15, 20, 28, 1),       # NeRV-XS fc_dim stage
+    (1, 12, 12, 180, 320, 2),     # many regions per CTA
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "B%d_%dto%d_%dx%d_s%d" % c)
+def test_fused_block_is_bit_identical_to_three_launches(ops, case):
+    B, cin, C, H, W, s = case
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, *case)
+    ref, _ = ops.nerv_block_fwd(x, up, c0, c1, cin, H, W, "sin", "gelu", g0, b0, g1, b1)
+    out = ops.nerv_block_fused(x, up, c0, c1, cin, H, W, "sin", "gelu", g0, b0, g1, b1)
+    assert out is not None, "shape unexpectedly outside the fused kernel's range"
+    torch.cuda.synchronize()
+    if not torch.equal(out, ref):
+        d = (out.float() - ref.float()).abs()
+        bad = d > 0
+        idx = bad.nonzero()[:8].tolist()
+        raise AssertionError(f"{int(bad.sum())} of {bad.numel()} values differ, max |diff| {d.max().item():.3e} "
+                             f"(max |ref| {ref.float().abs().max().item():.3e}); first [b, group, y, x, c]: {idx}")
+
+
+@pytest.mark.parametrize("case", [(1, 12, 12, 64, 96, 1), (2, 30, 30, 45, 80, 1), (1, 43, 43, 37, 53, 1), (1, 21, 21, 7, 5, 1)],
+                         ids=lambda c: "B%d_C%d_%dx%d" % (c[0], c[2], c[3], c[4]))
+def test_fused_resblock_is_bit_identical_to_two_launches(ops, case):
+    B, _, C, H, W, _ = case
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, B, C, C, H, W, 1)
+    dev = x.device
+    mk = lambda: torch.empty(ops.c8_shape(B, C, H, W), dtype=torch.float16, device=dev)
+    x0, u, wmap, ref = mk(), mk(), mk(), mk()
+    ops.conv_fused(x, up, C, H, W, act="sin", g1p=g0, beta=b0, out_pre=x0, out_aff=u)
+    ops.conv_fused(u, c0, C, H, W, act="gelu", g1p=g1, beta=b1, out_aff=wmap)
+    ops.conv_fused(wmap, c1, C, H, W, act="none", resid=x0, out_pre=ref)
+    out = ops.resblock_fused(u, x0, c0, c1, C, H, W, "gelu", g1, b1)
+    assert out is not None
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref), f"max |diff| {(out.float() - ref.float()).abs().max().item():.3e}"
+
+
+def test_fused_block_generic_activations_and_unsupported_shapes(ops):
+    # run-time activation codes (the generic instantiation): relu / none
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 12, 12, 40, 48, 1)
+    ref, _ = ops.nerv_block_fwd(x, up, c0, c1, 12, 40, 48, "relu", "relu", g0, b0, g1, b1)
+    out = ops.nerv_block_fused(x, up, c0, c1, 12, 40, 48, "relu", "relu", g0, b0, g1, b1)
+    assert torch.equal(out, ref)
+    # outside the range: nothing is launched, the wrapper reports None and the caller takes the three-launch path
+    from bnerv_b200 import _capi
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 12, 12, 9, 16, 3)           # PixelShuffle(3)
+    n0 = _capi.launch_count()
+    assert ops.nerv_block_fused(x, up, c0, c1, 12, 9, 16, "sin", "gelu", g0, b0, g1, b1) is None
+    x64 = make_block(ops, 1, 64, 64, 16, 16, 1)                                     # 64 channels
+    n1 = _capi.launch_count()
+    assert ops.nerv_block_fused(x64[0], x64[1], x64[2], x64[3], 64, 16, 16, "sin", "gelu", *x64[4]) is None
+    assert _capi.launch_count() == n1 and n1 > n0
+
+
+@pytest.mark.parametrize("name", ["s1_k3", "s2_k3"])
+def test_fused_block_against_reference_block_golden(ops, name):
+    """The narrow reference block goldens (tests/golden/blocks.npz, minted from the unmodified NeRVBlock,
+    model_blocks.py:34-46) through the one-kernel form: 1e-3 (north_star) and bit-identity with the three launches."""
+    c = load_block_golden()[name]
+    sd = {k[3:]: torch.from_numpy(v).cuda() for k, v in c.items() if k.startswith("sd/")}
+    ngf, new_ngf, ks, s, H, W, B = [int(v) for v in c["meta"]]
+    x, e = torch.from_numpy(c["x"]).cuda(), torch.from_numpy(c["e"]).cuda()
+    layers = []
+    for sft in ("sft0", "sft1"):
+        layers.append(tuple(sd[f"sft_block.{sft}.SFT_{br}_conv{i}.{p}"].reshape(-1, 32).contiguous() if p == "weight"
+                            else sd[f"sft_block.{sft}.SFT_{br}_conv{i}.{p}"]
+                            for br in ("scale", "shift") for i in (0, 1) for p in ("weight", "bias")))
+    tab = ops.SftTable(layers, B, x.device)
+    tab.run(e.flatten(1))
+    up = ops.PackedConv(sd["conv.upconv.0.weight"], sd["conv.upconv.0.bias"], s)
+    c0 = ops.PackedConv(sd["sft_block.conv0.weight"], sd["sft_block.conv0.bias"], 1)
+    c1 = ops.PackedConv(sd["sft_block.conv1.weight"], sd["sft_block.conv1.bias"], 1)
+    args = (ops.nchw_to_c8(x), up, c0, c1, ngf, H, W, "sin", "gelu", tab.g1p[0], tab.beta[0], tab.g1p[1], tab.beta[1])
+    out = ops.nerv_block_fused(*args)
+    assert out is not None
+    assert max_rel(ops.c8_to_nchw(out, new_ngf).cpu(), torch.from_numpy(c["y"])) < 1e-3
+    assert torch.equal(out, ops.nerv_block_fwd(*args)[0])
