@@ -109,14 +109,21 @@ class _BlockPlan:
                 raise Unsupported("SFT inner activation other than relu")
         self.cout = self.up.cout
         self.scale = (self.pre.s if self.pre else 1) * self.up.s
-        # One kernel per block for the narrow stages (bnerv_nerv_block_fused); when only the up-conv is too wide / has a
-        # PixelShuffle factor the fused kernel does not take, the ResBlock_SFT half alone is one kernel (bnerv_resblock_fused).
+        # One kernel per block for the narrow stages.  <= 16 channels: the row-streaming form (bnerv_nerv_block_stream, A operand
+        # in tensor memory); when only the up-conv is outside it (PixelShuffle, wide input) the ResBlock_SFT half alone is one
+        # kernel (bnerv_resblock_stream).  The region-tiled form (bnerv_nerv_block_fused, <= 48 channels) is correct but not
+        # faster than three launches above 16 channels (profiles/r02_block_fused_ss_vs_three_launches.txt): BNERV_BLOCK_FORM=tile
+        # selects it for comparison, BNERV_NO_BLOCK_FUSION=1 switches every fused form off.
         cp, cin_p = ops.round_up(self.cout, 16), ops.round_up(self.up.cin, 16)
         self.fuse = None
-        if cp <= 48 and not os.environ.get("BNERV_NO_BLOCK_FUSION"):
-            whole = (self.up.k == 3 and self.up.s in (1, 2) and cin_p <= 64 and self.up.s ** 2 * cp <= 256
-                     and not os.environ.get("BNERV_NO_UP_FUSION"))
-            self.fuse = "block" if whole else "res"
+        form = os.environ.get("BNERV_BLOCK_FORM", "stream")
+        if not os.environ.get("BNERV_NO_BLOCK_FUSION"):
+            if form == "tile" and cp <= 48:
+                whole = self.up.k == 3 and self.up.s in (1, 2) and cin_p <= 64 and self.up.s ** 2 * cp <= 256
+                self.fuse = ("tile", "block" if whole else "res")
+            elif form == "stream" and cp <= 16:
+                whole = self.up.k == 3 and self.up.s == 1 and cin_p <= 16
+                self.fuse = ("stream", "block" if whole else "res")
 
 
 def _sft_tensors(sft):
@@ -312,16 +319,17 @@ class DecoderEngine:
             Ho, Wo = H * blk.up.s, W * blk.up.s
             out = view(nxt_buf, blk.cout, Ho, Wo)
             done = None
-            if blk.fuse == "block" and self.fuse_blocks:
+            fuse = blk.fuse if self.fuse_blocks else None
+            if fuse is not None and fuse[1] == "block":
                 done = ops.nerv_block_fused(cur, blk.up.packed(), blk.c0.packed(), blk.c1.packed(), cin, H, W, blk.act,
-                                            blk.inner_act, g0, b0, g1, b1, out=out)
+                                            blk.inner_act, g0, b0, g1, b1, out=out, form=fuse[0])
             if done is None:
                 x0 = view(ws["x0"], blk.cout, Ho, Wo)
                 u = view(ws["u"], blk.cout, Ho, Wo)
                 ops.conv_fused(cur, blk.up.packed(), cin, H, W, act=blk.act, g1p=g0, beta=b0, out_pre=x0, out_aff=u)
-                if blk.fuse is not None and self.fuse_blocks:
+                if fuse is not None:
                     done = ops.resblock_fused(u, x0, blk.c0.packed(), blk.c1.packed(), blk.cout, Ho, Wo, blk.inner_act, g1, b1,
-                                              out=out)
+                                              out=out, form=fuse[0])
                 if done is None:
                     wbuf = view(ws["w"], blk.cout, Ho, Wo)
                     ops.conv_fused(u, blk.c0.packed(), blk.cout, Ho, Wo, act=blk.inner_act, g1p=g1, beta=b1, out_aff=wbuf)

@@ -406,9 +406,10 @@ def nerv_block_fwd(x_c8, up, c0, c1, cin, H, W, act_up, act_inner, g0p, beta0, g
     return out, x0
 
 
-def nerv_block_fused(x_c8, up, c0, c1, cin, H, W, act_up, act_inner, g0p, beta0, g1p, beta1, out=None):
-    """One NeRVBlock as ONE kernel (bnerv_nerv_block_fused; narrow stages only).  Returns out C8 f16, or None when the
-    shape is outside the fused kernel's range (BNERV_E_UNSUPPORTED: nothing was launched, use nerv_block_fwd / conv_fused)."""
+def nerv_block_fused(x_c8, up, c0, c1, cin, H, W, act_up, act_inner, g0p, beta0, g1p, beta1, out=None, form="tile"):
+    """One NeRVBlock as ONE kernel: form "tile" = bnerv_nerv_block_fused (region-tiled, <= 48 channels), "stream" =
+    bnerv_nerv_block_stream (row-streaming with the A operand in tensor memory, <= 16 channels).  Returns out C8 f16, or
+    None when the shape is outside that kernel's range (BNERV_E_UNSUPPORTED: nothing was launched)."""
     _need_cuda(x_c8)
     B = x_c8.shape[0]
     C, s = up.cout, up.s
@@ -417,12 +418,12 @@ def nerv_block_fused(x_c8, up, c0, c1, cin, H, W, act_up, act_inner, g0p, beta0,
     if TIMING is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = lib.bnerv_nerv_block_fused(ptr(x_c8), B, cin, H, W, ptr(up.w), ptr(up.b), up.k, s, ACT_CODES[act_up], ptr(c0.w),
-                                    ptr(c0.b), ptr(c1.w), ptr(c1.b), C, ACT_CODES[act_inner], ptr(g0p), ptr(beta0), ptr(g1p),
-                                    ptr(beta1), ptr(out), _stream())
+    fn = lib.bnerv_nerv_block_stream if form == "stream" else lib.bnerv_nerv_block_fused
+    rc = fn(ptr(x_c8), B, cin, H, W, ptr(up.w), ptr(up.b), up.k, s, ACT_CODES[act_up], ptr(c0.w), ptr(c0.b), ptr(c1.w), ptr(c1.b),
+            C, ACT_CODES[act_inner], ptr(g0p), ptr(beta0), ptr(g1p), ptr(beta1), ptr(out), _stream())
     if rc == _capi.E_UNSUPPORTED:
         return None
-    check("bnerv_nerv_block_fused", rc)
+    check("bnerv_nerv_block_" + ("stream" if form == "stream" else "fused"), rc)
     if TIMING is not None:
         e1.record()
         fl = conv_flops(B, cin, C, up.k, s, H, W) + 2 * conv_flops(B, C, C, 3, 1, H * s, W * s)
@@ -430,8 +431,9 @@ def nerv_block_fused(x_c8, up, c0, c1, cin, H, W, act_up, act_inner, g0p, beta0,
     return out
 
 
-def resblock_fused(u_c8, x0_c8, c0, c1, C, H, W, act_inner, g1p, beta1, out=None):
-    """ResBlock_SFT as ONE kernel (bnerv_resblock_fused): out = x0 + conv3(act(conv3(u))*g1p + beta1).  None = unsupported."""
+def resblock_fused(u_c8, x0_c8, c0, c1, C, H, W, act_inner, g1p, beta1, out=None, form="tile"):
+    """ResBlock_SFT as ONE kernel (bnerv_resblock_fused / bnerv_resblock_stream): out = x0 + conv3(act(conv3(u))*g1p + beta1).
+    None = unsupported."""
     _need_cuda(u_c8, x0_c8)
     B = u_c8.shape[0]
     if out is None:
@@ -439,11 +441,12 @@ def resblock_fused(u_c8, x0_c8, c0, c1, C, H, W, act_inner, g1p, beta1, out=None
     if TIMING is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = lib.bnerv_resblock_fused(ptr(u_c8), ptr(x0_c8), B, C, H, W, ptr(c0.w), ptr(c0.b), ptr(c1.w), ptr(c1.b),
-                                  ACT_CODES[act_inner], ptr(g1p), ptr(beta1), ptr(out), _stream())
+    fn = lib.bnerv_resblock_stream if form == "stream" else lib.bnerv_resblock_fused
+    rc = fn(ptr(u_c8), ptr(x0_c8), B, C, H, W, ptr(c0.w), ptr(c0.b), ptr(c1.w), ptr(c1.b), ACT_CODES[act_inner], ptr(g1p),
+            ptr(beta1), ptr(out), _stream())
     if rc == _capi.E_UNSUPPORTED:
         return None
-    check("bnerv_resblock_fused", rc)
+    check("bnerv_resblock_" + ("stream" if form == "stream" else "fused"), rc)
     if TIMING is not None:
         e1.record()
         TIMING.append((2 * conv_flops(B, C, C, 3, 1, H, W), e0, e1, (C, C, 3, 1, H, W, "resblock")))

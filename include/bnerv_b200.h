@@ -139,6 +139,21 @@ int bnerv_resblock_fused(const void* u, const void* x0, int B, int C, int H, int
                          const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1,
                          void* out, void* stream);
 
+/* The same two contracts in ROW-STREAMING form for stages of at most 16 channels (all 12-channel stages of NeRV-Boost XS / S):
+ * a CTA streams the rows of a 128-column strip through up-conv -> conv0 -> conv1, and the A operand of every tcgen05.mma
+ * comes from TENSOR MEMORY - the threads that own a row's pixels write its "row-im2col" (3 horizontal taps x 16 channels)
+ * into TMEM once, the vertical taps select among the A rows of a ring - instead of being re-read from shared memory nine
+ * times (17.6 vs 50.4 cycles per N = 16 MMA, profiles/r02_ts_probe_umma_ts_vs_ss.txt).  Bit-identical to
+ * bnerv_nerv_block_fwd.  Supported: k_up = 3, s = 1, C <= 16, Cin <= 16 (bnerv_resblock_stream: C <= 16);
+ * anything else returns BNERV_E_UNSUPPORTED with nothing launched. */
+int bnerv_nerv_block_stream(const void* x, int B, int Cin, int H, int W, const void* w_up, const float* b_up, int k_up,
+                            int s, int act_up, const void* w_c0, const float* b_c0, const void* w_c1, const float* b_c1,
+                            int C, int act_inner, const float* g0p, const float* beta0, const float* g1p,
+                            const float* beta1, void* out, void* stream);
+int bnerv_resblock_stream(const void* u, const void* x0, int B, int C, int H, int W, const void* w_c0, const float* b_c0,
+                          const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1,
+                          void* out, void* stream);
+
 /* Bring-up instrumentation for the fused-block kernel: device buffer of n_ctas*4*12 int64 receiving clock64 phase stamps of
  * the first 4 regions of the first n_ctas CTAs of subsequent launches (slot 11 = SM id); NULL switches it off. */
 int bnerv_debug_set_buffer(void* buf, int n_ctas);

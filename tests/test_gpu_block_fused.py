@@ -69,6 +69,46 @@ def test_fused_block_is_bit_identical_to_three_launches(ops, case):
                              f"(max |ref| {ref.float().abs().max().item():.3e}); first [b, group, y, x, c]: {idx}")
 
 
+STREAM_CASES = [  # B, cin, C, H, W, s : the row-streaming form (<= 16 channels, no PixelShuffle)
+    (1, 12, 12, 64, 96, 1),
+    (1, 12, 12, 180, 320, 1),     # several strips (320 = 2 * 122 + 76) and row segments
+    (2, 12, 12, 37, 51, 1),       # B > 1, ragged
+    (1, 12, 12, 7, 9, 1),         # smaller than one strip / segment
+    (3, 15, 15, 20, 28, 1),       # NeRV-XS fc_dim stage
+    (1, 16, 16, 33, 123, 1),      # full 16 channels, one column more than a strip
+    (1, 12, 12, 360, 640, 1),     # one CTA per SM, long segments
+    (1, 9, 12, 50, 245, 1),       # Cin != C, W = 2 strips + 1
+]
+
+
+@pytest.mark.parametrize("case", STREAM_CASES, ids=lambda c: "B%d_%dto%d_%dx%d_s%d" % c)
+def test_stream_block_is_bit_identical_to_three_launches(ops, case):
+    B, cin, C, H, W, s = case
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, *case)
+    ref, _ = ops.nerv_block_fwd(x, up, c0, c1, cin, H, W, "sin", "gelu", g0, b0, g1, b1)
+    out = ops.nerv_block_fused(x, up, c0, c1, cin, H, W, "sin", "gelu", g0, b0, g1, b1, form="stream")
+    assert out is not None, "shape unexpectedly outside the streaming kernel's range"
+    torch.cuda.synchronize()
+    if not torch.equal(out, ref):
+        d = (out.float() - ref.float()).abs()
+        bad = d > 0
+        raise AssertionError(f"{int(bad.sum())} of {bad.numel()} values differ, max |diff| {d.max().item():.3e} "
+                             f"(max |ref| {ref.float().abs().max().item():.3e}); first [b, group, y, x, c]: {bad.nonzero()[:8].tolist()}")
+    # the ResBlock_SFT half alone, fed with the first launch's outputs
+    mk = lambda: torch.empty_like(ref)
+    x0, u = mk(), mk()
+    ops.conv_fused(x, up, cin, H, W, act="sin", g1p=g0, beta=b0, out_pre=x0, out_aff=u)
+    out2 = ops.resblock_fused(u, x0, c0, c1, C, H, W, "gelu", g1, b1, form="stream")
+    assert out2 is not None and torch.equal(out2, ref)
+
+
+def test_stream_block_refuses_what_it_does_not_implement(ops):
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 12, 12, 20, 24, 2)           # PixelShuffle(2)
+    assert ops.nerv_block_fused(x, up, c0, c1, 12, 20, 24, "sin", "gelu", g0, b0, g1, b1, form="stream") is None
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 21, 21, 20, 24, 1)           # 21 channels
+    assert ops.nerv_block_fused(x, up, c0, c1, 21, 20, 24, "sin", "gelu", g0, b0, g1, b1, form="stream") is None
+
+
 @pytest.mark.parametrize("case", [(1, 12, 12, 64, 96, 1), (2, 30, 30, 45, 80, 1), (1, 43, 43, 37, 53, 1), (1, 21, 21, 7, 5, 1)],
                          ids=lambda c: "B%d_C%d_%dx%d" % (c[0], c[2], c[3], c[4]))
 def test_fused_resblock_is_bit_identical_to_two_launches(ops, case):

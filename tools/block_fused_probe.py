@@ -32,6 +32,27 @@ def describe(out, ref, C):
     return msg
 
 
+def check_stream():
+    from test_gpu_block_fused import STREAM_CASES
+    for case in STREAM_CASES:
+        B, cin, C, H, W, s = case
+        x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, *case)
+        ref, x0 = ops.nerv_block_fwd(x, up, c0, c1, cin, H, W, "sin", "gelu", g0, b0, g1, b1)
+        mk = lambda: torch.empty_like(ref)
+        x0b, u = mk(), mk()
+        ops.conv_fused(x, up, cin, H, W, act="sin", g1p=g0, beta=b0, out_pre=x0b, out_aff=u)
+        for name, fn in (("resblock", lambda o: ops.resblock_fused(u, x0b, c0, c1, C, H, W, "gelu", g1, b1, out=o, form="stream")),
+                         ("block", lambda o: ops.nerv_block_fused(x, up, c0, c1, cin, H, W, "sin", "gelu", g0, b0, g1, b1, out=o, form="stream"))):
+            try:
+                out = torch.full_like(ref, float("nan"))
+                res = fn(out)
+                torch.cuda.synchronize()
+                print(f"stream {name} {case}: " + ("UNSUPPORTED" if res is None else describe(out, ref, C)), flush=True)
+            except Exception as ex:
+                print(f"stream {name} {case}: EXCEPTION {ex}", flush=True)
+                return
+
+
 def check():
     for case in CASES:
         B, cin, C, H, W, s = case
@@ -106,9 +127,23 @@ def timing():
         def fused():
             ops.nerv_block_fused(x, up, c0, c1, cin, H, W, "sin", "gelu", g0, b0, g1, b1, out=out)
 
+        def stream():
+            ops.nerv_block_fused(x, up, c0, c1, cin, H, W, "sin", "gelu", g0, b0, g1, b1, out=out, form="stream")
+
+        def up_stream():
+            ops.conv_fused(x, up, cin, H, W, act="sin", g1p=g0, beta=b0, out_pre=x0, out_aff=u)
+            ops.resblock_fused(u, x0, c0, c1, C, H * s, W * s, "gelu", g1, b1, out=out, form="stream")
+
         t3, tf = timed(three), timed(fused)
         bytes_io = 2.0 * B * (ops.round_up(cin, 16) * H * W + cp * H * s * W * s)
-        print(f"{str(case):36s} {t3:14.4f} {tf:10.4f} {t3 / tf:6.2f} {bytes_io / tf / 1e6:12.1f}", flush=True)
+        msg = f"{str(case):36s} {t3:14.4f} {tf:10.4f} {t3 / tf:6.2f} {bytes_io / tf / 1e6:12.1f}"
+        if cp == 16:
+            if s == 1 and cin <= 16:
+                ts = timed(stream)
+                msg += f" | stream {ts:.4f} ms ({t3 / ts:.2f}x, {bytes_io / ts / 1e6:.0f} GB/s)"
+            tu = timed(up_stream)
+            msg += f" | up + resblock-stream {tu:.4f} ms ({t3 / tu:.2f}x)"
+        print(msg, flush=True)
 
 
 def stamps(case, n_ctas=300, show=(0, 1, 148, 149, 295)):
@@ -141,6 +176,9 @@ def stamps(case, n_ctas=300, show=(0, 1, 148, 149, 295)):
 
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if "--stream-check" in sys.argv:
+        check_stream()
+        sys.exit(0)
     if "--time-only" not in sys.argv:
         check()
     if "--stamps" in sys.argv:
