@@ -122,7 +122,7 @@ class _BlockPlan:
                 whole = self.up.k == 3 and self.up.s in (1, 2) and cin_p <= 64 and self.up.s ** 2 * cp <= 256
                 self.fuse = ("tile", "block" if whole else "res")
             elif form == "stream" and cp <= 16:
-                whole = self.up.k == 3 and self.up.s == 1 and cin_p <= 16
+                whole = self.up.k == 3 and self.up.s in (1, 2) and cin_p <= 16
                 self.fuse = ("stream", "block" if whole else "res")
 
 

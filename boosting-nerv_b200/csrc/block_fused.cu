@@ -629,8 +629,8 @@ static bool bf_plan(BlockFusedArgs& a, int Rh, int Rw, size_t& smem_bytes, int& 
 }
 
 static int g_bf_sms = 0;
-static long long* g_bf_dbg = nullptr;
-static int g_bf_dbg_ctas = 0;
+long long* g_bf_dbg = nullptr;        // shared with block_stream.cu
+int g_bf_dbg_ctas = 0;
 
 static int bf_launch(const void* x, BlockFusedArgs& a, cudaStream_t stream) {
     if (g_bf_sms == 0) {

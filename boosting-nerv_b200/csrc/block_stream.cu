@@ -18,7 +18,8 @@
 //     WG middle  : epilogue of D_c0(h): w = gelu(.)*g1p + beta1 -> builds A_c1(h)
 //     WG back    : epilogue of D_c1(h): out = . + x0 -> global
 //     MMA warp   : one elected lane issues the 9 MMAs of every (stage, row) as its three A rows become ready
-// Rings in TMEM: 5 A rows x 24 columns and 3 accumulators x 16 columns per stage = 504 of 512 columns; every hand-off is
+// Rings in TMEM: 4 A rows x 24 columns and 4 accumulators x 16 columns per stage = 480 of 512 columns (powers of two:
+// slot = row & 3, no integer division in the loops); every hand-off is
 // an mbarrier (A full / A free, D full / D free, input full / free, x0 full / free).
 // Out-of-image pixels of u / w are written as exact zeros (the reference pads AFTER the affine, model_blocks.py:105,:86).
 //
@@ -37,42 +38,61 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();          // conv_tc.cu
 
-constexpr int BS_WGS = 2;                     // warpgroups per stage: warpgroup p takes the rows of parity p
-constexpr int BS_MMA_WARP = 3 * BS_WGS * 4;   // warps 0-7 front (2 WGs), 8-15 middle, 16-23 back, 24-26 MMA issue (one per stage), 27 TMA
+// Six epilogue warpgroups, split by the per-row cost of the stages: 3 front (A_up build + sin epilogue + A_c0 build), 2 middle
+// (GELU epilogue + A_c1 build), 1 back (residual + store).  Warpgroup p of a stage with n warpgroups takes rows j = p (mod n).
+constexpr int BS_WG_F = 3, BS_WG_M = 2, BS_WG_B = 1;
+constexpr int BS_WGS = 3;                     // exchange-row buffers are sized for the largest count
+constexpr int BS_MMA_WARP = (BS_WG_F + BS_WG_M + BS_WG_B) * 4;   // warps 0-23 epilogues, 24-26 MMA issue (one per stage), 27 TMA
 constexpr int BS_THREADS = (BS_MMA_WARP + 4) * 32;
-constexpr int BS_NA = 5;                      // A-row ring slots per stage (TMEM)
-constexpr int BS_ND = 3;                      // accumulator ring slots per stage (TMEM)
-constexpr int BS_NI = 6;                      // input-row ring slots (shared memory)
-constexpr int BS_NX = 16;                     // x0-row ring slots (shared memory)
+constexpr int BS_NA = 4;                      // A-row ring slots per stage (TMEM)
+constexpr int BS_NIK = 2;                     // input rows in flight per front warpgroup
+constexpr int BS_NI = BS_WG_F * BS_NIK;       // input-row slots (shared memory): row r -> slot (r % 3) * 2 + (r / 3) % 2, use (r / 3) / 2.
+// Every front warpgroup owns its slots, so it waits on EVERY use of them in order.  (A shared ring taken in turns is not safe
+// here: TMA loads complete out of order, a warpgroup could test a slot whose previous load - consumed by another warpgroup -
+// has not landed yet, and the parity test of an mbarrier cannot tell "one phase behind" from "done".)
+constexpr int BS_NX = 24;                     // x0-row ring slots (shared memory); the writer leads the reader by <= 18 rows
 constexpr int BS_VALID = 122;                 // valid output columns per strip: lanes [2, 124)
 constexpr int BS_ACOLS = 24;                  // TMEM columns of one A row: 3 horizontal taps x 16 channels x f16
 constexpr int BS_A_COL0 = 0;                  // A rings: stage S at S * NA * 24
-constexpr int BS_D_COL0 = 3 * BS_NA * BS_ACOLS;            // accumulator rings: stage S at D_COL0 + S * ND * 16
+constexpr int BS_D_COL0 = 3 * BS_NA * BS_ACOLS;            // accumulator rings follow the A rings
+// Accumulator rings.  s = 1: 4 slots x 16 columns per stage (288 .. 480).  PixelShuffle(2) form (S2): the up-conv runs on
+// INPUT rows with N = 4 sub-positions x 16 channels = 64 columns, 2 slots; conv0 4 x 16; conv1 2 x 16 (288 .. 512).
+template <bool S2> struct BsRing {
+    static constexpr int ND0 = S2 ? 2 : 4, ND1 = 4, ND2 = S2 ? 2 : 4;
+    static constexpr int DW0 = S2 ? 64 : 16;
+    static constexpr int D0 = BS_D_COL0, D1 = D0 + ND0 * DW0, D2 = D1 + ND1 * 16;
+    static_assert(D2 + ND2 * 16 <= 512, "TMEM columns");
+    __host__ __device__ static constexpr int nd(int S) { return S == 0 ? ND0 : (S == 1 ? ND1 : ND2); }
+    __host__ __device__ static constexpr int dcol(int S) { return S == 0 ? D0 : (S == 1 ? D1 : D2); }
+    __host__ __device__ static constexpr int dw(int S) { return S == 0 ? DW0 : 16; }
+};
 constexpr int BS_ROW_B = 2 * 128 * 16;        // one input row in shared memory: [2 groups][128 px][16 B]
 constexpr int BS_XROW_B = 2 * 130 * 16;       // one exchange row: [2 groups][130 px][16 B] (px 0 and 129 stay zero)
 
-struct BsCst { float b_up[16], b_c0[16], b_c1[16], g0p[16], beta0[16], g1p[16], beta1[16]; };
+struct BsCst { float b_up[64], b_c0[16], b_c1[16], g0p[16], beta0[16], g1p[16], beta1[16]; };
 
 struct BsBars {
     uint64_t in_full[BS_NI], in_empty[BS_NI];
     uint64_t a_full[3][BS_NA], a_empty[3][BS_NA];
-    uint64_t d_full[3][BS_ND], d_empty[3][BS_ND];
-    uint64_t x0_full[BS_NX], x0_empty[BS_NX];
+    uint64_t d_full[3][4], d_empty[3][4];
+    uint64_t tok[BS_WG_F];       // S2 form: "front warpgroup p has built its pair of A_c0 rows" (orders the builds, see the kernel)
     uint32_t tmem_slot, pad;
 };
 
 struct BsSmem {
-    uint8_t w[3][9 * 2 * 16 * 16];            // weights of up / c0 / c1: [tap][2 groups][16 rows][16 B]
+    uint8_t w_up[9 * 2 * 64 * 16];            // up-conv weights: [tap][2 groups][N = 16 or 64 rows][16 B]
+    uint8_t w_c[2][9 * 2 * 16 * 16];          // conv0 / conv1 weights: [tap][2 groups][16 rows][16 B]
     uint8_t in_ring[BS_NI][BS_ROW_B];
-    uint8_t u_ring[BS_WGS][2][BS_XROW_B];
-    uint8_t w_ring[BS_WGS][2][BS_XROW_B];
+    uint8_t u_ring[BS_WG_F][2][2][BS_XROW_B]; // per front warpgroup: double-buffered exchange rows (two rows per step in the S2 form)
+    uint8_t w_ring[BS_WG_M][2][BS_XROW_B];
     uint8_t x0_ring[BS_NX][BS_ROW_B];
     BsCst cst;
     BsBars bars;
 };
 
 struct BsArgs {
-    int B, H, W;
+    int B, H, W, C;              // H, W: the block's OUTPUT resolution (= input resolution x s)
+    int s;                       // PixelShuffle factor of the up-conv: 1 or 2
     int has_up;                  // 0: the TMA input is u (conv0's input), the residual x0 is read from `resid`
     int act_up, act_inner;
     int strips, segs, seg_rows;
@@ -80,7 +100,15 @@ struct BsArgs {
     const float *b_up, *b_c0, *b_c1, *g0p, *beta0, *g1p, *beta1;
     const __half* resid;
     __half* out;
+    long long* dbg;              // bring-up: CTA 0 records clock64 stamps [role < 9][iteration < 32][4] (bnerv_debug_set_buffer)
 };
+
+#define BS_STAMP(role, it, k) do { if (DBG && a.dbg && blockIdx.x == 0 && (threadIdx.x & 127) == 0 && (it) < 32) \
+        a.dbg[((role) * 32 + (it)) * 4 + (k)] = clock64(); } while (0)
+#define BS_STAMP1(role, it, k) do { if (DBG && a.dbg && blockIdx.x == 0 && lane == 0 && (it) < 32) \
+        a.dbg[((role) * 32 + (it)) * 4 + (k)] = clock64(); } while (0)
+
+extern long long* g_bf_dbg;
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& lo, const uint4& hi) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -135,22 +163,31 @@ __device__ __forceinline__ void bs_affine8(const float2* x, const float* g, cons
 }
 
 // packed global weights [tap][2 groups][16 rows][8 halves] are already the shared-memory form for one K step
-__device__ __forceinline__ void bs_stage_weights(uint8_t* dst, const __half* src) {
+__device__ __forceinline__ void bs_stage_weights(uint8_t* dst, const __half* src, int n_rows) {
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst);
-    for (int i = threadIdx.x; i < 9 * 2 * 16; i += BS_THREADS) d4[i] = __ldg(s4 + i);
+    for (int i = threadIdx.x; i < 9 * 2 * n_rows; i += BS_THREADS) d4[i] = __ldg(s4 + i);
 }
 
-template <int ACT_UP, int ACT_IN>
+// NP: float2 channel pairs that carry data (6 when C <= 12: the 4 pad channels are exact zeros through sin / GELU / ReLU and
+// are not evaluated); DBG: records BS_STAMPs.
+// S2: the up-conv carries PixelShuffle(2) - it runs on input rows (half resolution), see the front warpgroups.
+template <int ACT_UP, int ACT_IN, int NP, bool DBG, bool S2>
 __global__ void __launch_bounds__(BS_THREADS, 1)
 block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     BsSmem& sm = *reinterpret_cast<BsSmem*>(smem_raw);
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    const int wg = warp >> 2;                         // 0,1 front, 2,3 middle, 4,5 back, 6 = MMA / TMA warps
-    const int stage_of_wg = wg / BS_WGS;              // 0 front, 1 middle, 2 back
-    const int par = wg % BS_WGS;                      // row parity this warpgroup handles
+    const int wg = warp >> 2;                         // 0-2 front, 3-4 middle, 5 back, 6 = MMA / TMA warps
+    const int stage_of_wg = wg < BS_WG_F ? 0 : (wg < BS_WG_F + BS_WG_M ? 1 : 2);
+    const int par = stage_of_wg == 0 ? wg : (stage_of_wg == 1 ? wg - BS_WG_F : wg - BS_WG_F - BS_WG_M);   // row residue this warpgroup handles
+    // S2: two front warpgroups.  A warpgroup may only wait on ring slots whose EVERY use it sees or whose previous use is implied
+    // complete by its own previous row (mbarrier waits test a phase parity: "one use behind" and "done" look alike).  With
+    // the 2 accumulator slots TMEM leaves for the 64-column up-conv rows, a third warpgroup's first wait would be for the
+    // second use of a slot.  With two, each warpgroup owns one slot.
+    constexpr int NFRONT = S2 ? 2 : BS_WG_F;
+    const int nwg = stage_of_wg == 0 ? NFRONT : (stage_of_wg == 1 ? BS_WG_M : BS_WG_B);
     const int q = warp & 3;
     const int m = q * 32 + lane;                      // TMEM lane == column of the strip
 
@@ -165,36 +202,44 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
     const int col = sx0 + m;
     const bool col_in = (col >= 0) && (col < a.W);
 
+    using R = BsRing<S2>;
     const int S0 = a.has_up ? 0 : 1;                  // first stage that runs
-    // rows per stage: up y0-2 .. y1+1, c0 y0-1 .. y1, c1 y0 .. y1-1;  A rows per stage: two more than its output rows
-    const int n_out[3] = {rows + 4, rows + 2, rows};
-    const int n_in = a.has_up ? rows + 6 : rows + 4;  // TMA rows: A_up rows (x) or A_c0 rows (u)
-    const int in_row0 = a.has_up ? y0 - 3 : y0 - 2;
+    // rows per stage: up y0-2 .. y1+1, c0 y0-1 .. y1, c1 y0 .. y1-1;  A rows per stage: two more than its output rows.
+    // S2: the up stage counts INPUT rows: row hi yields output rows 2hi, 2hi+1; y0 is even, so the u rows y0-2 .. y1+1
+    // (A_c0 rows 0 .. rows+3) come from input rows (y0-2)/2 + jin, jin < n_jin.
+    const int n_ac0 = rows + 4;
+    const int n_jin = (n_ac0 + 1) / 2;
+    const int n_out[3] = {S2 ? n_jin : rows + 4, rows + 2, rows};
+    const int n_in = a.has_up ? n_out[0] + 2 : rows + 4;            // TMA rows: A_up rows (x) or A_c0 rows (u)
+    const int in_row0 = a.has_up ? (S2 ? (y0 - 2) / 2 - 1 : y0 - 3) : y0 - 2;
+    const int in_x0 = S2 ? sx0 / 2 - 1 : sx0 - 1;     // image column (input resolution) of pixel 0 of an input row in shared memory
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < BS_NI; ++i) { mbar_init(smem_u32(&sm.bars.in_full[i]), 1); mbar_init(smem_u32(&sm.bars.in_empty[i]), 4); }
         for (int s = 0; s < 3; ++s) {
             for (int i = 0; i < BS_NA; ++i) { mbar_init(smem_u32(&sm.bars.a_full[s][i]), 4); mbar_init(smem_u32(&sm.bars.a_empty[s][i]), 1); }
-            for (int i = 0; i < BS_ND; ++i) { mbar_init(smem_u32(&sm.bars.d_full[s][i]), 1); mbar_init(smem_u32(&sm.bars.d_empty[s][i]), 4); }
+            for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&sm.bars.d_full[s][i]), 1); mbar_init(smem_u32(&sm.bars.d_empty[s][i]), 4); }
         }
-        for (int i = 0; i < BS_NX; ++i) { mbar_init(smem_u32(&sm.bars.x0_full[i]), 4); mbar_init(smem_u32(&sm.bars.x0_empty[i]), 4); }
+        for (int i = 0; i < BS_WG_F; ++i) mbar_init(smem_u32(&sm.bars.tok[i]), 4);
         fence_mbar_init();
         tma_prefetch_desc(&tmIn);
     }
     if (warp == BS_MMA_WARP) tmem_alloc(smem_u32(&sm.bars.tmem_slot), 512);
-    if (a.has_up) bs_stage_weights(sm.w[0], a.w_up);
-    bs_stage_weights(sm.w[1], a.w_c0);
-    bs_stage_weights(sm.w[2], a.w_c1);
-    if (threadIdx.x < 16) {
+    if (a.has_up) bs_stage_weights(sm.w_up, a.w_up, R::DW0);
+    bs_stage_weights(sm.w_c[0], a.w_c0, 16);
+    bs_stage_weights(sm.w_c[1], a.w_c1, 16);
+    if (threadIdx.x < 64) {
         const int i = threadIdx.x;
-        sm.cst.b_up[i] = a.has_up ? __ldg(a.b_up + i) : 0.0f;
-        sm.cst.b_c0[i] = __ldg(a.b_c0 + i);
-        sm.cst.b_c1[i] = __ldg(a.b_c1 + i);
+        sm.cst.b_up[i] = (a.has_up && i < R::DW0) ? __ldg(a.b_up + i) : 0.0f;
+        if (i < 16) {
+            sm.cst.b_c0[i] = __ldg(a.b_c0 + i);
+            sm.cst.b_c1[i] = __ldg(a.b_c1 + i);
+        }
     }
-    for (int i = threadIdx.x; i < BS_WGS * 2 * BS_XROW_B / 16; i += BS_THREADS) {   // exchange rows: the edge pixels stay zero
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(sm.u_ring) / 16); i += BS_THREADS)      // exchange rows: the edge pixels stay zero
         reinterpret_cast<uint4*>(sm.u_ring)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(sm.w_ring) / 16); i += BS_THREADS)
         reinterpret_cast<uint4*>(sm.w_ring)[i] = make_uint4(0, 0, 0, 0);
-    }
     pdl_wait();                       // TAT tables / activations come from earlier kernels
     pdl_launch_dependents();
     if (threadIdx.x < 16) {
@@ -236,11 +281,12 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
     if (warp == BS_MMA_WARP + 3) {
         // =============================== TMA producer: input rows -> ring ===============================
         for (int i = 0; i < n_in; ++i) {
-            const int slot = i % BS_NI;
-            mbar_wait(smem_u32(&sm.bars.in_empty[slot]), ((i / BS_NI) & 1) ^ 1);
+            const int owner = i % NFRONT, seq = i / NFRONT;                // row i belongs to front warpgroup `owner`, its seq-th row
+            const int slot = owner * BS_NIK + (seq % BS_NIK);
+            mbar_wait(smem_u32(&sm.bars.in_empty[slot]), ((seq / BS_NIK) & 1) ^ 1);
             if (elect_one()) {
                 mbar_expect_tx(smem_u32(&sm.bars.in_full[slot]), BS_ROW_B);
-                tma_load_3d(smem_u32(sm.in_ring[slot]), &tmIn, smem_u32(&sm.bars.in_full[slot]), 2 * (sx0 - 1), in_row0 + i, fb * 2);
+                tma_load_3d(smem_u32(sm.in_ring[slot]), &tmIn, smem_u32(&sm.bars.in_full[slot]), 2 * in_x0, in_row0 + i, fb * 2);
             }
             __syncwarp();
         }
@@ -250,64 +296,148 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
         //  per (stage, row) even when they are already complete - 1400 cycles per row, which was the whole row period)
         const int S = warp - BS_MMA_WARP;
         if (S >= S0) {
-            const uint32_t idesc = umma_idesc_f16(128, 16);
-            const uint64_t b_d = umma_desc_hi_noswz(16u * 16u, 128u);
+            const int N = (S == 0) ? R::DW0 : 16;                       // accumulator columns of one row of this stage
+            const int nd = R::nd(S);
+            const uint32_t idesc = umma_idesc_f16(128, N);
+            const uint64_t b_d = umma_desc_hi_noswz(static_cast<uint32_t>(N) * 16u, 128u);
             const uint32_t b_hi = static_cast<uint32_t>(b_d >> 32);
-            const uint32_t b_lo = static_cast<uint32_t>(b_d) | ((smem_u32(sm.w[S]) & 0x3FFFFu) >> 4);
+            const uint32_t b_lo = static_cast<uint32_t>(b_d) | ((smem_u32(S == 0 ? sm.w_up : sm.w_c[S - 1]) & 0x3FFFFu) >> 4);
+            const uint32_t tap16 = static_cast<uint32_t>(2 * N);       // one tap of B in 16-byte units
+            const uint32_t d_base = tmem_base + R::dcol(S);
             const int n = n_out[S];
             int a_waited = 0;
             for (int j = 0; j < n; ++j) {
+                BS_STAMP1(6 + S, j, 0);
                 while (a_waited <= j + 2) {                             // A rows j, j+1, j+2 (image rows h-1, h, h+1)
                     mbar_wait(smem_u32(&sm.bars.a_full[S][a_waited % BS_NA]), (a_waited / BS_NA) & 1);
                     ++a_waited;
                 }
-                const int ds = j % BS_ND;
-                mbar_wait(smem_u32(&sm.bars.d_empty[S][ds]), ((j / BS_ND) & 1) ^ 1);
+                BS_STAMP1(6 + S, j, 1);
+                const int ds = j % nd;
+                mbar_wait(smem_u32(&sm.bars.d_empty[S][ds]), ((j / nd) & 1) ^ 1);
                 tc_fence_after();
+                BS_STAMP1(6 + S, j, 2);
                 if (elect_one()) {
-                    const uint32_t d = tmem_base + BS_D_COL0 + (S * BS_ND + ds) * 16;
+                    const uint32_t d = d_base + ds * N;
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
                         const uint32_t at = tmem_base + BS_A_COL0 + (S * BS_NA + (j + r) % BS_NA) * BS_ACOLS;
 #pragma unroll
                         for (int sx = 0; sx < 3; ++sx)
-                            umma_f16_ts(d, at + sx * 8, b_lo + (r * 3 + sx) * 32, b_hi, idesc, (r | sx) ? 1u : 0u);
+                            umma_f16_ts(d, at + sx * 8, b_lo + (r * 3 + sx) * tap16, b_hi, idesc, (r | sx) ? 1u : 0u);
                     }
                     umma_commit(smem_u32(&sm.bars.d_full[S][ds]));
                     umma_commit(smem_u32(&sm.bars.a_empty[S][j % BS_NA]));      // A row j has had its last reader
                 }
                 __syncwarp();
+                BS_STAMP1(6 + S, j, 3);
             }
         }
+    } else if (stage_of_wg == 0 && par >= NFRONT) {
+        // (S2 form: the third front warpgroup has no rows)
     } else if (stage_of_wg == 0) {
-        // =============================== front warpgroups (rows of parity `par`) ===============================
+        // =============================== front warpgroups (rows j = par mod nwg) ===============================
         if (!a.has_up) {
             // residual form: the input rows ARE u -> A_c0 rows
-            for (int i = par; i < n_in; i += BS_WGS) {
-                const int slot = i % BS_NI;
-                mbar_wait(smem_u32(&sm.bars.in_full[slot]), (i / BS_NI) & 1);
+            int seq = 0;
+            for (int i = par; i < n_in; i += nwg, ++seq) {
+                const int slot = par * BS_NIK + (seq % BS_NIK);
+                mbar_wait(smem_u32(&sm.bars.in_full[slot]), (seq / BS_NIK) & 1);
                 build_a(1, i, sm.in_ring[slot], 128, 0, 127);
                 if (lane == 0) mbar_arrive(smem_u32(&sm.bars.in_empty[slot]));
             }
-        } else {
+        } else if (S2) {
+            // ---------- PixelShuffle(2) up-conv: one step = one INPUT row hi = (y0-2)/2 + jin -> output rows 2hi, 2hi+1 ----------
+            // D_up(jin): lane l = input column sx0/2 + l (l < 64 carry data), 64 columns = packed rows n' = ((i*2 + G)*2 + j)*8 + c%8
+            // (bnerv_pack_conv_weight, s = 2): 16-column group i*2+G holds output row 2hi+i, channel group G, both output
+            // columns 2*(sx0/2 + l) + j.  The sin epilogue therefore runs on lanes 0..63 (warps 0, 1 of the warpgroup); all
+            // four warps build the two A_c0 rows afterwards.
             auto build_up = [&](int i) {
-                const int slot = i % BS_NI;
-                mbar_wait(smem_u32(&sm.bars.in_full[slot]), (i / BS_NI) & 1);
+                const int seq = i / NFRONT;
+                const int slot = par * BS_NIK + (seq % BS_NIK);
+                mbar_wait(smem_u32(&sm.bars.in_full[slot]), (seq / BS_NIK) & 1);
                 build_a(0, i, sm.in_ring[slot], 128, 0, 127);
                 if (lane == 0) mbar_arrive(smem_u32(&sm.bars.in_empty[slot]));
             };
-            // A_up rows of this parity run two of its rows ahead of the epilogue (MMA_up(j) reads A rows j, j+1, j+2)
             if (par < n_in) build_up(par);
-            if (par + BS_WGS < n_in) build_up(par + BS_WGS);
             int it = 0;
-            for (int j = par; j < n_out[0]; j += BS_WGS, ++it) {
-                if (j + 2 * BS_WGS < n_in) build_up(j + 2 * BS_WGS);
+            for (int j = par; j < n_out[0]; j += nwg, ++it) {
+                if (j + nwg < n_in) build_up(j + nwg);
+                const int ds = j % R::ND0;                               // == par: this warpgroup's own slot
+                mbar_wait(smem_u32(&sm.bars.d_full[0][ds]), (j / R::ND0) & 1);
+                tc_fence_after();
+                uint8_t* ubuf = sm.u_ring[par][it & 1][0];               // two exchange rows: + i * BS_XROW_B
+                if (m < 64) {
+#pragma unroll 1
+                    for (int g = 0; g < 4; ++g) {                        // g = i*2 + G
+                        const int i = g >> 1, G = g & 1;
+                        uint32_t v[16];
+                        tmem_ld16(lane_base + R::D0 + ds * 64 + g * 16, v);
+                        tmem_ld_wait();
+                        float2 x[8];
+                        bs_bias16(v, sm.cst.b_up + g * 16, x);
+                        // x[0..3]: 8 channels of output column j = 0, x[4..7]: of j = 1; channel group G: pairs 2, 3 are pad when NP == 6
+#pragma unroll
+                        for (int p = 0; p < 8; ++p)
+                            x[p] = (G == 0 || NP == 8 || (p & 3) < 2) ? bs_act2<ACT_UP>(x[p], a.act_up) : make_float2(0.0f, 0.0f);
+                        const int ia = 2 * j + i;                        // A_c0 row = output row y0 - 2 + ia
+                        const int h = y0 - 2 + ia;
+                        const int k = ia - 2;
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const int lane_o = 2 * m + jj;               // output lane of the strip
+                            const int ocol = sx0 + lane_o;
+                            const bool inside = (ocol >= 0) && (ocol < a.W) && (h >= 0) && (h < a.H);
+                            float2 y[4];
+                            bs_affine8(x + 4 * jj, sm.cst.g0p + 8 * G, sm.cst.beta0 + 8 * G, y);
+                            uint4 uo = bs_pack8(y);
+                            if (!inside) uo = make_uint4(0, 0, 0, 0);
+                            *reinterpret_cast<uint4*>(ubuf + i * BS_XROW_B + static_cast<size_t>(G * 130 + lane_o + 1) * 16) = uo;
+                            if (k >= 0 && k < rows)
+                                *reinterpret_cast<uint4*>(sm.x0_ring[k % BS_NX] + static_cast<size_t>(G * 128 + lane_o) * 16) = bs_pack8(x + 4 * jj);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sm.bars.d_empty[0][ds]));
+                named_bar_sync(1 + par, 128);                            // both u rows are complete
+                // A_c0 rows are built IN ROW ORDER across the three warpgroups (a token from the warpgroup that owns input row
+                // j - 1).  Without it this warpgroup's previous a_empty check (row 2j - 5) does not cover conv0's MMA of row
+                // 2j - 8, the parity test of row 2j's slot could alias and overwrite an A row that MMA still reads.
+                if (j > 0) {
+                    const int pred = (par + NFRONT - 1) % NFRONT;
+                    const int pit = (par > 0) ? it : it - 1;
+                    mbar_wait(smem_u32(&sm.bars.tok[pred]), pit & 1);
+                }
+#pragma unroll 1
+                for (int i = 0; i < 2; ++i)
+                    if (2 * j + i < n_ac0) build_a(1, 2 * j + i, ubuf + i * BS_XROW_B, 130, 0, 129);
+                if (lane == 0) mbar_arrive(smem_u32(&sm.bars.tok[par]));
+            }
+        } else {
+            auto build_up = [&](int i) {                   // i = par (mod 3): this warpgroup's (i / 3)-th input row
+                const int seq = i / NFRONT;
+                const int slot = par * BS_NIK + (seq % BS_NIK);
+                mbar_wait(smem_u32(&sm.bars.in_full[slot]), (seq / BS_NIK) & 1);
+                build_a(0, i, sm.in_ring[slot], 128, 0, 127);
+                if (lane == 0) mbar_arrive(smem_u32(&sm.bars.in_empty[slot]));
+            };
+            // this warpgroup's A_up rows run one of its rows ahead of its epilogue (MMA_up(j) reads A rows j, j+1, j+2; the ring
+            // of 5 must not be overrun: a build that waits for a free slot would hold back the epilogue behind it)
+            if (par < n_in) build_up(par);
+            int it = 0;
+            for (int j = par; j < n_out[0]; j += nwg, ++it) {
+                BS_STAMP(wg, it, 0);
+                if (j + nwg < n_in) build_up(j + nwg);
                 const int h = y0 - 2 + j;
-                const int ds = j % BS_ND;
-                mbar_wait(smem_u32(&sm.bars.d_full[0][ds]), (j / BS_ND) & 1);
+                const int ds = j % R::ND0;
+                BS_STAMP(wg, it, 1);
+                mbar_wait(smem_u32(&sm.bars.d_full[0][ds]), (j / R::ND0) & 1);
+                BS_STAMP(wg, it, 2);
                 tc_fence_after();
                 uint32_t v[16];
-                tmem_ld16(lane_base + BS_D_COL0 + (0 * BS_ND + ds) * 16, v);
+                tmem_ld16(lane_base + R::D0 + ds * 16, v);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -315,7 +445,7 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
                 float2 x[8];
                 bs_bias16(v, sm.cst.b_up, x);
 #pragma unroll
-                for (int p = 0; p < 8; ++p) x[p] = bs_act2<ACT_UP>(x[p], a.act_up);
+                for (int p = 0; p < 8; ++p) x[p] = (p < NP) ? bs_act2<ACT_UP>(x[p], a.act_up) : make_float2(0.0f, 0.0f);
                 const bool inside = col_in && (h >= 0) && (h < a.H);
                 uint4 u0, u1;
                 {
@@ -326,18 +456,20 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
                     u1 = bs_pack8(y);
                     if (!inside) { u0 = make_uint4(0, 0, 0, 0); u1 = u0; }
                 }
-                uint8_t* urow = sm.u_ring[par][it & 1];
+                uint8_t* urow = sm.u_ring[par][it & 1][0];
                 *reinterpret_cast<uint4*>(urow + static_cast<size_t>(m + 1) * 16) = u0;
                 *reinterpret_cast<uint4*>(urow + static_cast<size_t>(130 + m + 1) * 16) = u1;
                 const int k = j - 2;                                     // this row's index in the conv1 / output sequence
                 if (k >= 0 && k < rows) {
+                    // x0 ring, no barriers of its own.  Free slot: this row runs at most NA + ND + NA + ND = 16 (+2) rows ahead of
+                    // the back warpgroup (the A_c0 / D_c0 / A_c1 / D_c1 rings are bounded), the ring holds 32.  Visibility: the
+                    // write precedes this thread's a_full arrive (release), and D_c1(k) - which the reader waits for - is
+                    // downstream of that arrive through the conv0 / conv1 MMAs of rows k+1, k+2.
                     const int xs = k % BS_NX;
-                    mbar_wait(smem_u32(&sm.bars.x0_empty[xs]), ((k / BS_NX) & 1) ^ 1);
                     *reinterpret_cast<uint4*>(sm.x0_ring[xs] + static_cast<size_t>(m) * 16) = bs_pack8(x);
                     *reinterpret_cast<uint4*>(sm.x0_ring[xs] + static_cast<size_t>(128 + m) * 16) = bs_pack8(x + 4);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&sm.bars.x0_full[xs]));
                 }
+                BS_STAMP(wg, it, 3);
                 named_bar_sync(1 + par, 128);                            // the u row is complete
                 build_a(1, j, urow, 130, 0, 129);
                 // the next iteration but one rewrites this exchange row: every thread has passed the next barrier by then
@@ -346,13 +478,15 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
     } else if (stage_of_wg == 1) {
         // =============================== middle warpgroups: conv0 epilogue -> A_c1 ===============================
         int it = 0;
-        for (int k = par; k < n_out[1]; k += BS_WGS, ++it) {
+        for (int k = par; k < n_out[1]; k += nwg, ++it) {
             const int h = y0 - 1 + k;
-            const int ds = k % BS_ND;
-            mbar_wait(smem_u32(&sm.bars.d_full[1][ds]), (k / BS_ND) & 1);
+            const int ds = k % R::ND1;
+            BS_STAMP(wg, it, 0);
+            mbar_wait(smem_u32(&sm.bars.d_full[1][ds]), (k / R::ND1) & 1);
+            BS_STAMP(wg, it, 1);
             tc_fence_after();
             uint32_t v[16];
-            tmem_ld16(lane_base + BS_D_COL0 + (1 * BS_ND + ds) * 16, v);
+            tmem_ld16(lane_base + R::D1 + ds * 16, v);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -360,7 +494,7 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
             float2 x[8];
             bs_bias16(v, sm.cst.b_c0, x);
 #pragma unroll
-            for (int p = 0; p < 8; ++p) x[p] = bs_act2<ACT_IN>(x[p], a.act_inner);
+            for (int p = 0; p < 8; ++p) x[p] = (p < NP) ? bs_act2<ACT_IN>(x[p], a.act_inner) : make_float2(0.0f, 0.0f);
             const bool inside = col_in && (h >= 0) && (h < a.H);
             uint4 w0, w1;
             {
@@ -374,14 +508,16 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
             uint8_t* wrow = sm.w_ring[par][it & 1];
             *reinterpret_cast<uint4*>(wrow + static_cast<size_t>(m + 1) * 16) = w0;
             *reinterpret_cast<uint4*>(wrow + static_cast<size_t>(130 + m + 1) * 16) = w1;
-            named_bar_sync(1 + BS_WGS + par, 128);
+            BS_STAMP(wg, it, 2);
+            named_bar_sync(1 + BS_WG_F + par, 128);
             build_a(2, k, wrow, 130, 0, 129);
+            BS_STAMP(wg, it, 3);
         }
     } else {
         // =============================== back warpgroups: conv1 epilogue + residual -> global ===============================
         const size_t plane = static_cast<size_t>(a.H) * a.W * 8;
         const bool lane_valid = (m >= 2) && (m < 2 + BS_VALID) && col_in;
-        for (int k = par; k < rows; k += BS_WGS) {
+        for (int k = par; k < rows; k += nwg) {
             const int h = y0 + k;
             const size_t goff = ((static_cast<size_t>(fb) * 2) * a.H + h) * static_cast<size_t>(a.W) * 8 + static_cast<size_t>(col) * 8;
             uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
@@ -389,22 +525,21 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
                 r0 = __ldg(reinterpret_cast<const uint4*>(a.resid + goff));
                 r1 = __ldg(reinterpret_cast<const uint4*>(a.resid + goff + plane));
             }
-            const int ds = k % BS_ND;
-            mbar_wait(smem_u32(&sm.bars.d_full[2][ds]), (k / BS_ND) & 1);
+            const int ds = k % R::ND2;
+            BS_STAMP(wg, k, 0);
+            mbar_wait(smem_u32(&sm.bars.d_full[2][ds]), (k / R::ND2) & 1);
+            BS_STAMP(wg, k, 1);
             tc_fence_after();
             uint32_t v[16];
-            tmem_ld16(lane_base + BS_D_COL0 + (2 * BS_ND + ds) * 16, v);
+            tmem_ld16(lane_base + R::D2 + ds * 16, v);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&sm.bars.d_empty[2][ds]));
             if (a.has_up) {
                 const int xs = k % BS_NX;
-                mbar_wait(smem_u32(&sm.bars.x0_full[xs]), (k / BS_NX) & 1);
                 r0 = *reinterpret_cast<const uint4*>(sm.x0_ring[xs] + static_cast<size_t>(m) * 16);
                 r1 = *reinterpret_cast<const uint4*>(sm.x0_ring[xs] + static_cast<size_t>(128 + m) * 16);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&sm.bars.x0_empty[xs]));
             }
             float2 x[8];
             bs_bias16(v, sm.cst.b_c1, x);
@@ -416,6 +551,7 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
                 *reinterpret_cast<uint4*>(a.out + goff) = bs_pack8(x);
                 *reinterpret_cast<uint4*>(a.out + goff + plane) = bs_pack8(x + 4);
             }
+            BS_STAMP(wg, k, 3);
         }
     }
 
@@ -439,6 +575,7 @@ static int bs_launch(const void* x_in, BsArgs& a, cudaStream_t stream) {
         cudaDeviceGetAttribute(&g_bs_sms, cudaDevAttrMultiProcessorCount, dev);
         if (g_bs_sms <= 0) g_bs_sms = 148;
     }
+    a.dbg = g_bf_dbg;
     a.strips = (a.W + BS_VALID - 1) / BS_VALID;
     // One CTA per SM at a time (it owns all of TMEM).  A segment of R rows costs ~R + 12 row times (4 halo rows + pipeline
     // fill/drain): choose the number of segments per strip that minimises (waves over the SMs) x (R + 12).
@@ -457,6 +594,7 @@ static int bs_launch(const void* x_in, BsArgs& a, cudaStream_t stream) {
         }
         int seg_rows = (a.H + best_segs - 1) / best_segs;
         if (forced_rows > 0) seg_rows = forced_rows;
+        if (a.has_up && a.s == 2) seg_rows += seg_rows & 1;             // segments start on even output rows
         a.seg_rows = seg_rows;
         a.segs = (a.H + seg_rows - 1) / seg_rows;
     }
@@ -466,8 +604,9 @@ static int bs_launch(const void* x_in, BsArgs& a, cudaStream_t stream) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return set_error(BNERV_E_NODRIVER, "cuTensorMapEncodeTiled entry point not available");
     CUtensorMap tm;
-    cuuint64_t dims[3] = {2ull * a.W, static_cast<cuuint64_t>(a.H), 2ull * a.B};
-    cuuint64_t strides[2] = {16ull * a.W, 16ull * a.W * a.H};
+    const int inH = (a.has_up && a.s == 2) ? a.H / 2 : a.H, inW = (a.has_up && a.s == 2) ? a.W / 2 : a.W;
+    cuuint64_t dims[3] = {2ull * inW, static_cast<cuuint64_t>(inH), 2ull * a.B};
+    cuuint64_t strides[2] = {16ull * inW, 16ull * inW * inH};
     cuuint32_t box[3] = {256, 1, 2};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(x_in), dims, strides, box, estr,
@@ -476,10 +615,18 @@ static int bs_launch(const void* x_in, BsArgs& a, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) return set_error(static_cast<int>(r), "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
 
     using KernelFn = void (*)(const CUtensorMap, const BsArgs);
-    KernelFn fn = block_stream_kernel<-1, -1>;
-    int slot = 0;
-    if (a.act_up == BNERV_ACT_SIN && a.act_inner == BNERV_ACT_GELU) { fn = block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU>; slot = 1; }
-    static bool attr_set[2][32] = {};
+    // pad channels may be skipped when the activations map 0 to 0 (every block activation but OutImg's tanh01)
+    const bool np6 = a.C <= 12 && a.act_up != BNERV_ACT_TANH01 && a.act_inner != BNERV_ACT_TANH01;
+    const bool spec = (!a.has_up || a.act_up == BNERV_ACT_SIN) && a.act_inner == BNERV_ACT_GELU;
+    const bool s2 = a.has_up && a.s == 2;
+    KernelFn fn;
+    int slot;
+    if (a.dbg && !s2) { fn = block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 6, true, false>; slot = 8; }     // bring-up stamps: the 12-channel sin/GELU form
+    else if (spec && np6) { fn = s2 ? block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 6, false, true> : block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 6, false, false>; slot = 0 + s2; }
+    else if (spec) { fn = s2 ? block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 8, false, true> : block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 8, false, false>; slot = 2 + s2; }
+    else if (np6) { fn = s2 ? block_stream_kernel<-1, -1, 6, false, true> : block_stream_kernel<-1, -1, 6, false, false>; slot = 4 + s2; }
+    else { fn = s2 ? block_stream_kernel<-1, -1, 8, false, true> : block_stream_kernel<-1, -1, 8, false, false>; slot = 6 + s2; }
+    static bool attr_set[9][32] = {};
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     const size_t smem = sizeof(BsSmem) + 1024;
@@ -522,7 +669,7 @@ extern "C" int bnerv_nerv_block_stream(const void* x, int B, int Cin, int H, int
     if (!x || !w_up || !b_up || !w_c0 || !b_c0 || !w_c1 || !b_c1 || !out) return set_error(BNERV_E_BADARG, "nerv_block_stream: null pointer");
     if (!g0p || !beta0 || !g1p || !beta1) return set_error(BNERV_E_BADARG, "nerv_block_stream: the four TAT tables are required");
     if (B <= 0 || Cin <= 0 || C <= 0 || H <= 0 || W <= 0) return set_error(BNERV_E_BADARG, "nerv_block_stream: non-positive size");
-    if (k_up != 3 || s != 1) return set_error(BNERV_E_UNSUPPORTED, "nerv_block_stream: up-conv k = %d, s = %d (only k = 3, s = 1)", k_up, s);
+    if (k_up != 3 || (s != 1 && s != 2)) return set_error(BNERV_E_UNSUPPORTED, "nerv_block_stream: up-conv k = %d, s = %d (only k = 3, s = 1 or 2)", k_up, s);
     if (C > 16 || Cin > 16) return set_error(BNERV_E_UNSUPPORTED, "nerv_block_stream: C = %d / Cin = %d (at most 16 channels)", C, Cin);
     if (act_up < BNERV_ACT_NONE || act_up > BNERV_ACT_TANH01 || act_inner < BNERV_ACT_NONE || act_inner > BNERV_ACT_TANH01)
         return set_error(BNERV_E_UNSUPPORTED, "nerv_block_stream: activation code");
@@ -530,7 +677,7 @@ extern "C" int bnerv_nerv_block_stream(const void* x, int B, int Cin, int H, int
                                reinterpret_cast<uintptr_t>(w_c1) | reinterpret_cast<uintptr_t>(out);
     if (align_or & 15) return set_error(BNERV_E_BADARG, "nerv_block_stream: pointers must be 16-byte aligned");
     BsArgs a{};
-    a.B = B; a.H = H; a.W = W; a.has_up = 1; a.act_up = act_up; a.act_inner = act_inner;
+    a.B = B; a.H = H * s; a.W = W * s; a.C = C; a.s = s; a.has_up = 1; a.act_up = act_up; a.act_inner = act_inner;
     a.w_up = static_cast<const __half*>(w_up); a.w_c0 = static_cast<const __half*>(w_c0); a.w_c1 = static_cast<const __half*>(w_c1);
     a.b_up = b_up; a.b_c0 = b_c0; a.b_c1 = b_c1;
     a.g0p = g0p; a.beta0 = beta0; a.g1p = g1p; a.beta1 = beta1;
@@ -549,7 +696,7 @@ extern "C" int bnerv_resblock_stream(const void* u, const void* x0, int B, int C
                                reinterpret_cast<uintptr_t>(w_c1) | reinterpret_cast<uintptr_t>(out);
     if (align_or & 15) return set_error(BNERV_E_BADARG, "resblock_stream: pointers must be 16-byte aligned");
     BsArgs a{};
-    a.B = B; a.H = H; a.W = W; a.has_up = 0; a.act_up = BNERV_ACT_NONE; a.act_inner = act_inner;
+    a.B = B; a.H = H; a.W = W; a.C = C; a.s = 1; a.has_up = 0; a.act_up = BNERV_ACT_NONE; a.act_inner = act_inner;
     a.w_c0 = static_cast<const __half*>(w_c0); a.w_c1 = static_cast<const __half*>(w_c1);
     a.b_c0 = b_c0; a.b_c1 = b_c1;
     a.g1p = g1p; a.beta1 = beta1;

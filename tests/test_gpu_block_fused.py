@@ -78,6 +78,12 @@ STREAM_CASES = [  # B, cin, C, H, W, s : the row-streaming form (<= 16 channels,
     (1, 16, 16, 33, 123, 1),      # full 16 channels, one column more than a strip
     (1, 12, 12, 360, 640, 1),     # one CTA per SM, long segments
     (1, 9, 12, 50, 245, 1),       # Cin != C, W = 2 strips + 1
+    (1, 12, 12, 45, 80, 2),       # PixelShuffle(2) up-conv inside the kernel: NeRV up stages
+    (1, 15, 12, 33, 47, 2),       # ragged input, Cin != C
+    (2, 12, 12, 20, 24, 2),       # B > 1
+    (1, 12, 12, 7, 9, 2),         # smaller than one strip / segment
+    (1, 12, 12, 180, 320, 2),     # several strips and segments (output 360 x 640)
+    (1, 16, 16, 31, 61, 2),       # 16 channels: no pad channels to skip; output width 122 = exactly one strip
 ]
 
 
@@ -98,13 +104,15 @@ def test_stream_block_is_bit_identical_to_three_launches(ops, case):
     mk = lambda: torch.empty_like(ref)
     x0, u = mk(), mk()
     ops.conv_fused(x, up, cin, H, W, act="sin", g1p=g0, beta=b0, out_pre=x0, out_aff=u)
-    out2 = ops.resblock_fused(u, x0, c0, c1, C, H, W, "gelu", g1, b1, form="stream")
+    out2 = ops.resblock_fused(u, x0, c0, c1, C, H * s, W * s, "gelu", g1, b1, form="stream")
     assert out2 is not None and torch.equal(out2, ref)
 
 
 def test_stream_block_refuses_what_it_does_not_implement(ops):
-    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 12, 12, 20, 24, 2)           # PixelShuffle(2)
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 12, 12, 20, 24, 3)           # PixelShuffle(3)
     assert ops.nerv_block_fused(x, up, c0, c1, 12, 20, 24, "sin", "gelu", g0, b0, g1, b1, form="stream") is None
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 30, 15, 20, 24, 2)           # 30 input channels
+    assert ops.nerv_block_fused(x, up, c0, c1, 30, 20, 24, "sin", "gelu", g0, b0, g1, b1, form="stream") is None
     x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 21, 21, 20, 24, 1)           # 21 channels
     assert ops.nerv_block_fused(x, up, c0, c1, 21, 20, 24, "sin", "gelu", g0, b0, g1, b1, form="stream") is None
 

@@ -41,7 +41,7 @@ def check_stream():
         mk = lambda: torch.empty_like(ref)
         x0b, u = mk(), mk()
         ops.conv_fused(x, up, cin, H, W, act="sin", g1p=g0, beta=b0, out_pre=x0b, out_aff=u)
-        for name, fn in (("resblock", lambda o: ops.resblock_fused(u, x0b, c0, c1, C, H, W, "gelu", g1, b1, out=o, form="stream")),
+        for name, fn in (("resblock", lambda o: ops.resblock_fused(u, x0b, c0, c1, C, H * s, W * s, "gelu", g1, b1, out=o, form="stream")),
                          ("block", lambda o: ops.nerv_block_fused(x, up, c0, c1, cin, H, W, "sin", "gelu", g0, b0, g1, b1, out=o, form="stream"))):
             try:
                 out = torch.full_like(ref, float("nan"))
@@ -138,7 +138,7 @@ def timing():
         bytes_io = 2.0 * B * (ops.round_up(cin, 16) * H * W + cp * H * s * W * s)
         msg = f"{str(case):36s} {t3:14.4f} {tf:10.4f} {t3 / tf:6.2f} {bytes_io / tf / 1e6:12.1f}"
         if cp == 16:
-            if s == 1 and cin <= 16:
+            if cin <= 16:
                 ts = timed(stream)
                 msg += f" | stream {ts:.4f} ms ({t3 / ts:.2f}x, {bytes_io / ts / 1e6:.0f} GB/s)"
             tu = timed(up_stream)
@@ -174,8 +174,35 @@ def stamps(case, n_ctas=300, show=(0, 1, 148, 149, 295)):
                   + (f" | gap to next {int(t[c, r + 1, 0] - st[9])}" if r < 3 and t[c, r + 1, 0] else ""))
 
 
+def stream_stamps(case=(1, 12, 12, 720, 1280, 1)):
+    """Per-role clock64 stamps of CTA 0 of the streaming kernel (BS_STAMP in csrc/block_stream.cu)."""
+    from bnerv_b200._capi import lib, ptr
+    B, cin, C, H, W, s = case
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, *case)
+    out = torch.empty(ops.c8_shape(B, C, H, W), dtype=torch.float16, device="cuda")
+    run = lambda: ops.nerv_block_fused(x, up, c0, c1, cin, H, W, "sin", "gelu", g0, b0, g1, b1, out=out, form="stream")
+    run(); run()
+    buf = torch.zeros(9 * 32 * 4, dtype=torch.int64, device="cuda")
+    lib.bnerv_debug_set_buffer(ptr(buf), 1)
+    run()
+    torch.cuda.synchronize()
+    lib.bnerv_debug_set_buffer(None, 0)
+    t = buf.cpu().view(9, 32, 4)
+    t0 = int(t[t > 0].min())
+    names = ["front0", "front1", "front2", "mid0", "mid1", "back", "issue up", "issue c0", "issue c1"]
+    print(f"stream stamps {case} (cycles since the first stamp; per iteration: 4 stamps)")
+    for r in range(9):
+        print(f" {names[r]}:")
+        for it in range(4, 14):
+            st = [int(v) - t0 if v else -1 for v in t[r, it]]
+            print(f"   it {it:2d}: {st}   deltas {[st[i + 1] - st[i] for i in range(3)]}" + (f"  period {st[0] - (int(t[r, it - 1, 0]) - t0)}" if t[r, it - 1, 0] else ""))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if "--stream-stamps" in sys.argv:
+        stream_stamps()
+        sys.exit(0)
     if "--stream-check" in sys.argv:
         check_stream()
         sys.exit(0)
