@@ -30,7 +30,7 @@ EXPORTS = [
     "bnerv_convnext_stage_fwd", "bnerv_convnext_stage_work_floats", "bnerv_nhwc_to_nchw",
     # one kernel per NeRVBlock for the narrow stages (ABI version 4)
     "bnerv_nerv_block_fused", "bnerv_resblock_fused", "bnerv_debug_set_buffer", "bnerv_nerv_block_stream",
-    "bnerv_resblock_stream",
+    "bnerv_resblock_stream", "bnerv_bwd_set_status",
 ]
 
 
@@ -91,6 +91,7 @@ def _load():
     lib.bnerv_nerv_block_fused.argtypes = [vp, i, i, i, i, vp, vp, i, i, i, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
     lib.bnerv_resblock_fused.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, i, vp, vp, vp, vp]
     lib.bnerv_debug_set_buffer.argtypes = [vp, i]
+    lib.bnerv_bwd_set_status.argtypes = [vp]
     lib.bnerv_nerv_block_stream.argtypes = lib.bnerv_nerv_block_fused.argtypes
     lib.bnerv_resblock_stream.argtypes = lib.bnerv_resblock_fused.argtypes
     lib.bnerv_head_conv1.argtypes = [vp, i, i, i, i, vp, vp, i, i, vp, vp]

@@ -98,7 +98,9 @@ class _BlockPlan:
             self.up = _upconv_slot(blk.conv)
         else:
             raise Unsupported(f"block type {type(blk).__name__}")
-        rb = blk.sft_block
+        rb = getattr(blk, "sft_block", None)
+        if rb is None or not all(hasattr(rb, n) for n in ("conv0", "conv1", "sft0", "sft1", "act")):
+            raise Unsupported("blocks without a ResBlock_SFT (sft_block other than 'res_sft') are not accelerated")
         self.inner_act = act_name(rb.act)
         if self.inner_act is None:
             raise Unsupported(f"activation {rb.act} is not accelerated")
@@ -226,10 +228,22 @@ class DecoderEngine:
                 b = prm.get("bias")
             key.append(id(w))
             key.append(w._version)
+            key.append(w.data_ptr())        # .to(device) / .data swaps keep id and _version
             if b is not None:
                 key.append(id(b))
                 key.append(b._version)
+                key.append(b.data_ptr())
         return tuple(key)
+
+    def sync_weights(self):
+        """Compare the effective weights with the ones the captured graphs were built from and drop the graphs on a
+        mismatch.  ``decode(check_weights=False)`` (model.decode) skips this per frame; the batch entry points
+        (stream.decode_to_host / evaluate_*) call it once per call, so weights changed by an optimiser step,
+        load_state_dict or cal_params between two calls are never served stale."""
+        wk = self.weights_key()
+        if wk != self._wkey:
+            self._graphs.clear()
+            self._wkey = wk
 
     def invalidate(self):
         """Drop captured graphs (call after replacing weights when decoding through ``decode(check_weights=False)``)."""
@@ -268,11 +282,8 @@ class DecoderEngine:
         if not self.use_graph:
             return self._body(inputs, keep)
         if check_weights:
-            wk = self.weights_key()
-            if wk != self._wkey:
-                self._graphs.clear()
-                self._wkey = wk
-        gkey = (tuple((tuple(t.shape), t.dtype) for t in inputs), keep)
+            self.sync_weights()
+        gkey = (tuple((tuple(t.shape), t.dtype, t.device) for t in inputs), keep)
         cap = self._graphs.get(gkey)
         if cap is None:
             cap = self._capture(inputs, keep)

@@ -157,8 +157,9 @@ class NeRV_Boost(_BoostBase):
         self.out_bias, self.outf = args.out_bias, args.outf
 
     def decode(self, input):
-        """Asynchronous decode on the native path: image only, no host sync, no timing, weights assumed frozen
-        (``model.engine().invalidate()`` after changing them).  The returned image is overwritten by the next decode."""
+        """Asynchronous decode on the native path: image only, no host sync, no timing.  The per-frame weight check is
+        skipped: after changing weights call ``model.engine().sync_weights()`` (stream.decode_to_host / evaluate_* do it once
+        per call; forward() checks on every call).  The returned image is overwritten by the next decode."""
         self._use_engine(input)
         return self.engine().decode((input,), False, check_weights=False)[0]
 

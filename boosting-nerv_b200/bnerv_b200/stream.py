@@ -39,6 +39,7 @@ def decode_to_host(model, norm_idx_host, out_host, embed_host=None, batch=1, dep
     if copy is None or copy.device != dev:
         copy = _COPY_STREAMS[model] = torch.cuda.Stream(dev)
     stages, ready, done = {}, {}, {}
+    model.engine().sync_weights()                # model.decode() replays captured graphs: re-check the weights once per call
     with torch.no_grad():
         for j, lo in enumerate(range(0, n, batch)):
             sl = slice(lo, min(lo + batch, n))
@@ -87,6 +88,7 @@ def evaluate_metrics(model, norm_idx_host, gt_host, embed_host=None, batch=1, wi
     total = torch.zeros(2, dtype=torch.float64, device=dev)
     if with_msssim:
         from .losses import ms_ssim
+    model.engine().sync_weights()                # see decode_to_host: weights changed since the last call invalidate the graphs
     with torch.no_grad():
         for lo in range(0, n, batch):
             sl = slice(lo, min(lo + batch, n))

@@ -25,12 +25,14 @@ and replayed: a training step is two graph launches plus the torch stems instead
 ``engine.train_graph = False`` runs the same bodies eagerly.  A second forward issued while the previous one still
 awaits its backward (gradient accumulation over several frames) runs eagerly, because the graph owns one set of maps.
 """
+import os
 import weakref
 
 import torch
 import torch.nn.functional as F
 
 from . import ops
+from ._capi import check, lib, ptr
 from .layers import effective_weight
 
 
@@ -350,12 +352,60 @@ def _graph_key(lay, x):
     return tuple(key)
 
 
+# Gradient-range monitor (bnerv_bwd_set_status): one int per device that the backward kernels OR bits into when an f16
+# gradient map saturates (bit 0) or turns non-finite (bit 1).  Read every CHECK_EVERY native steps (and after steps 1, 2, 4:
+# a bad loss scale shows at once); on a hit the model falls back to torch autograd for the following steps and a
+# RuntimeWarning says so - a diverging or clipped run must not look like a healthy one.
+_STATUS = {}
+CHECK_EVERY = 32
+
+
+def _status_tensor(device):
+    st = _STATUS.get(device)
+    if st is None:
+        st = _STATUS[device] = [torch.zeros(1, dtype=torch.int32, device=device), 0]
+        check("bnerv_bwd_set_status", lib.bnerv_bwd_set_status(ptr(st[0])))
+    return st
+
+
+def gradient_range_status(device=None, reset=True):
+    """Bits seen by the native backward since the last reset: 1 = an f16 gradient map saturated (clipped at 65504 behind the
+    loss scale), 2 = a non-finite gradient.  Synchronises the device."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    st = _STATUS.get(device)
+    if st is None:
+        return 0
+    bits = int(st[0].item())
+    if reset and bits:
+        st[0].zero_()
+    return bits
+
+
+def _check_gradient_range(eng, device):
+    st = _status_tensor(device)
+    st[1] += 1
+    n = st[1]
+    if n in (2, 3, 5) or n % CHECK_EVERY == 0:
+        bits = gradient_range_status(device)
+        if bits:
+            import warnings
+            what = " and ".join(w for b, w in ((1, "saturated f16 gradient maps (clipped at 65504 behind the loss scale)"),
+                                                 (2, "non-finite gradients")) if bits & b)
+            fallback = not os.environ.get("BNERV_TRAIN_NO_FALLBACK")
+            warnings.warn(f"bnerv_b200 native backward: {what} in the last {min(n, CHECK_EVERY)} step(s)"
+                          + ("; switching this model to train_backend = 'torch' (fp32 autograd)" if fallback else ""),
+                          RuntimeWarning, stacklevel=3)
+            if fallback:
+                eng.model.train_backend = "torch"
+
+
 def cascade_train(eng, x, cond):
     """x: [B, C, h, w] stem output (differentiable); cond: time embedding fed to every SFT layer.
     Returns (img [B,3,H,W] f32, first block output NCHW f32 (non-differentiable))."""
     if not x.is_cuda:
         raise RuntimeError("bnerv_b200 native training needs CUDA tensors (no CPU path)")
     ops.require_current_device(x.device)
+    _check_gradient_range(eng, x.device)
     B = x.shape[0]
     lays = eng.__dict__.setdefault("_train_layouts", {})
     lay = lays.get(B)

@@ -42,6 +42,21 @@ __device__ __forceinline__ void block_reduce_atomic(float (&acc)[N_ACC], float* 
 
 constexpr int BW_THREADS = 256;     // 8 warps (block_reduce_atomic assumes <= 8)
 
+// Gradient-range monitor.  Gradient maps are f16 behind one loss scale picked at the head, and every conversion saturates
+// (cvt.satfinite): a gradient that grows past 65504/S deeper in the cascade would be clipped silently.  The two element-wise
+// kernels every block's gradients pass through (inputs = the dgrad conv outputs, outputs = the next dgrad's input) OR bits into
+// status[0] when they see |value| >= 65504 (bit 0: saturated, i.e. clipped here or by the conv that produced it) or a
+// non-finite value (bit 1).  The pointer is set per process by bnerv_bwd_set_status (NULL: monitoring off).
+static int* g_bwd_status = nullptr;
+
+__device__ __forceinline__ void bwd_flag(int* status, float amax) {
+    if (status != nullptr && !(amax < 65504.0f)) {
+        const int bit = (amax <= 3.0e38f) ? 1 : 2;            // NaN / inf fail this comparison as well
+        const int any = __reduce_or_sync(__activemask(), bit);
+        if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicOr(status, any);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // head: dz = S * dimg * d/dz(0.5 tanh z + 0.5) = S * dimg * 2 img (1 - img)
 // ---------------------------------------------------------------------------------------------
@@ -118,7 +133,8 @@ __global__ void channel_sum_kernel(const __half* __restrict__ x, int cp, size_t 
 // ---------------------------------------------------------------------------------------------
 __global__ void mid_bwd_kernel(const __half* __restrict__ dw, const __half* __restrict__ v, const __half* __restrict__ dact,
                                const float* __restrict__ g1p, int cp, size_t hw, __half* __restrict__ dc0,
-                               float* __restrict__ dG, float* __restrict__ dB, float* __restrict__ dbias) {
+                               float* __restrict__ dG, float* __restrict__ dB, float* __restrict__ dbias, int* status) {
+    float amax = 0.0f;
     const int g = blockIdx.y, b = blockIdx.z;
     const size_t base = (static_cast<size_t>(b) * (cp >> 3) + g) * hw;
     float gg[8];
@@ -149,6 +165,8 @@ __global__ void mid_bwd_kernel(const __half* __restrict__ dw, const __half* __re
                 acc[k] += a[k] * vv[k];
                 acc[8 + k] += a[k];
                 acc[16 + k] += o[k];
+                amax = fmaxf(amax, fmaxf(fabsf(a[k]), fabsf(o[k])));
+                if (o[k] != o[k]) amax = __int_as_float(0x7fc00000);
             }
             reinterpret_cast<uint4*>(dc0)[base + (it ? p2 : p)] = pack8f(o);
         }
@@ -160,6 +178,7 @@ __global__ void mid_bwd_kernel(const __half* __restrict__ dw, const __half* __re
                             pB, pB + 1, pB + 2, pB + 3, pB + 4, pB + 5, pB + 6, pB + 7,
                             pb, pb + 1, pb + 2, pb + 3, pb + 4, pb + 5, pb + 6, pb + 7};
     block_reduce_atomic<24>(acc, dst);
+    bwd_flag(status, amax);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -170,7 +189,8 @@ __global__ void mid_bwd_kernel(const __half* __restrict__ dw, const __half* __re
 __global__ void front_bwd_kernel(const __half* __restrict__ du, const __half* __restrict__ dout, const __half* __restrict__ x0,
                                  const __half* __restrict__ dact, const float* __restrict__ g0p, int cp, size_t hw,
                                  __half* __restrict__ dy, float* __restrict__ dG, float* __restrict__ dB,
-                                 float* __restrict__ dbias1, float* __restrict__ dbias_up) {
+                                 float* __restrict__ dbias1, float* __restrict__ dbias_up, int* status) {
+    float amax = 0.0f;
     const int g = blockIdx.y, b = blockIdx.z;
     const size_t base = (static_cast<size_t>(b) * (cp >> 3) + g) * hw;
     float gg[8];
@@ -205,6 +225,8 @@ __global__ void front_bwd_kernel(const __half* __restrict__ du, const __half* __
                 acc[8 + k] += a[k];
                 acc[16 + k] += e[k];
                 acc[24 + k] += o[k];
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a[k]), fabsf(e[k])), fabsf(o[k])));
+                if (o[k] != o[k]) amax = __int_as_float(0x7fc00000);
             }
             reinterpret_cast<uint4*>(dy)[base + (it ? p2 : p)] = pack8f(o);
         }
@@ -219,6 +241,7 @@ __global__ void front_bwd_kernel(const __half* __restrict__ du, const __half* __
                             pu, pu ? pu + 1 : pu, pu ? pu + 2 : pu, pu ? pu + 3 : pu, pu ? pu + 4 : pu, pu ? pu + 5 : pu,
                             pu ? pu + 6 : pu, pu ? pu + 7 : pu};
     block_reduce_atomic<32>(acc, dst);
+    bwd_flag(status, amax);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -403,6 +426,11 @@ extern "C" int bnerv_channel_sum(const void* x_c8, int B, int Cp, int H, int W, 
     return check_launch("channel_sum_kernel");
 }
 
+extern "C" int bnerv_bwd_set_status(int* status) {
+    bnerv::g_bwd_status = status;
+    return 0;
+}
+
 extern "C" int bnerv_resblock_mid_bwd(const void* dw, const void* v, const void* dact, const float* g1p, int B, int C, int H,
                                       int W, void* dc0, float* dG, float* dB, float* dbias0, void* stream) {
     if (!dw || !v || !dact || !g1p || !dc0 || !dG || !dB || !dbias0) return set_error(BNERV_E_BADARG, "resblock_mid_bwd: null pointer");
@@ -411,7 +439,7 @@ extern "C" int bnerv_resblock_mid_bwd(const void* dw, const void* v, const void*
     const size_t hw = static_cast<size_t>(H) * W;
     mid_bwd_kernel<<<grid_planes(B, cp, hw), BW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __half*>(dw), static_cast<const __half*>(v), static_cast<const __half*>(dact), g1p, cp, hw,
-        static_cast<__half*>(dc0), dG, dB, dbias0);
+        static_cast<__half*>(dc0), dG, dB, dbias0, g_bwd_status);
     return check_launch("mid_bwd_kernel");
 }
 
@@ -424,7 +452,7 @@ extern "C" int bnerv_block_front_bwd(const void* du, const void* dout, const voi
     const size_t hw = static_cast<size_t>(H) * W;
     front_bwd_kernel<<<grid_planes(B, cp, hw), BW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __half*>(du), static_cast<const __half*>(dout), static_cast<const __half*>(x0),
-        static_cast<const __half*>(dact), g0p, cp, hw, static_cast<__half*>(dy), dG, dB, dbias1, dbias_up);
+        static_cast<const __half*>(dact), g0p, cp, hw, static_cast<__half*>(dy), dG, dB, dbias1, dbias_up, g_bwd_status);
     return check_launch("front_bwd_kernel");
 }
 

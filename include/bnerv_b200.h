@@ -252,6 +252,14 @@ int bnerv_bias_finalize(const float* acc, int Cout, int s, const float* inv_scal
 /* out[(per_b ? b : 0)][c] += sum_{h,w(,b)} x[b,c,h,w] over a C8 f16 map with Cp (multiple of 8) channels. */
 int bnerv_channel_sum(const void* x_c8, int B, int Cp, int H, int W, int per_b, float* out, void* stream);
 
+/* Gradient-range monitor of the native backward.  Gradient maps are f16 behind ONE power-of-two loss scale chosen at the head
+ * (bnerv_head_bwd) and every conversion saturates, so a gradient that outgrows 65504 / S deeper in the cascade would be clipped
+ * silently.  bnerv_resblock_mid_bwd / bnerv_block_front_bwd - which every block's gradients pass through - OR into
+ * status[0]: bit 0 when they read or produce |value| >= 65504 (saturated), bit 1 for a non-finite value.  `status` is one
+ * device int the caller zeroes and reads when it chooses (no synchronisation here); NULL switches the monitor off.  Process-wide;
+ * kernels captured in a CUDA graph keep the pointer they were launched with. */
+int bnerv_bwd_set_status(int* status);
+
 /* ResBlock_SFT middle transposed (model_blocks.py:86-87; forward v = gelu(c0), w = v*g1p + beta1):
  *   dc0 = dw * g1p * dact;  dG[b][c] += sum dw*v;  dB[b][c] += sum dw;  dbias0[c] += sum dc0
  *   dw, v, dact (= gelu'(c0) from bnerv_conv_fused_ex), dc0 : C8 f16 [B][Cp/8][H][W][8]; g1p, dG, dB : f32 [B][Cp];

@@ -179,6 +179,39 @@ def test_weight_update_invalidates_packed_cache_and_deepcopy_gets_its_own_engine
     assert torch.allclose(a1, b1, atol=1e-6)
 
 
+def test_batch_entry_points_notice_weight_updates_between_calls():
+    """stream.decode_to_host / evaluate_* replay captured graphs through model.decode(check_weights=False); they must
+    re-check the weights once per call, so that an optimiser step / load_state_dict between two calls is not decoded
+    with the packed weights of the first capture."""
+    from bnerv_b200.stream import decode_to_host, evaluate_psnr
+    torch.manual_seed(7)
+    m, a = _build("NeRV_Boost")
+    m = m.cuda()
+    n = 3
+    t_host = torch.tensor([(i + 1) / n for i in range(n)], dtype=torch.float64)
+    out0 = torch.empty(n, 3, *_out_hw(m, t_host), dtype=torch.float32).pin_memory()
+    out1 = torch.empty_like(out0).pin_memory()
+    decode_to_host(m, t_host, out0)
+    with torch.no_grad():
+        ref0 = torch.cat([m(t_host[i:i + 1].cuda())[0] for i in range(n)]).cpu()
+        for blk in m.layers:                                  # what an optimiser step does: in-place updates of conv weights
+            blk.sft_block.conv0.weight.mul_(1.5)
+        ref1 = torch.cat([m(t_host[i:i + 1].cuda())[0] for i in range(n)]).cpu()
+    decode_to_host(m, t_host, out1)
+    assert torch.equal(out0, ref0) and not torch.allclose(ref0, ref1)
+    assert torch.equal(out1, ref1), "decode_to_host served stale packed weights"
+    psnr_a = evaluate_psnr(m, t_host, ref1.clone())[0]
+    with torch.no_grad():
+        m.head_layer.bias.add_(0.05)
+    psnr_b = evaluate_psnr(m, t_host, ref1.clone())[0]
+    assert psnr_a > 80.0 and psnr_b < 40.0, (psnr_a, psnr_b)
+
+
+def _out_hw(m, t_host):
+    with torch.no_grad():
+        return tuple(m(t_host[:1].cuda())[0].shape[-2:])
+
+
 def test_full_resolution_properties_hnerv_1080p():
     """BASELINE-size frame (1080x1920) with a narrow model: finite, in [0,1], deterministic, and the top-left
     crop agrees with the oracle run on the cropped embedding away from the crop border (convs are local)."""

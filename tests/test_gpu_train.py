@@ -356,3 +356,35 @@ def test_benchmarked_presets_full_size_gradients_against_torch_autograd(name):
         assert max_rel(en, et) < 1e-2
     del model
     torch.cuda.empty_cache()
+
+
+def test_gradient_range_monitor_flags_saturation_and_falls_back_to_torch():
+    """The native backward keeps gradient maps in f16 behind one loss scale; the element-wise backward kernels flag maps
+    that saturate (bnerv_bwd_set_status).  A healthy step leaves the status clear; a step whose deeper gradients outgrow the
+    head's (huge conv weights far from the head) sets bit 0, and the periodic check warns and switches the model to torch
+    autograd instead of training on clipped gradients in silence."""
+    import warnings
+    from bnerv_b200 import train
+    torch.manual_seed(3)
+    m = NeRV_Boost(1, tiny_args("NeRV_Boost")).cuda().train()
+    t = torch.tensor([0.3, 0.7], dtype=torch.float64, device="cuda")
+    target = torch.rand(2, 3, *m(t)[0].shape[-2:], device="cuda")
+    train.gradient_range_status()                      # clear
+    ((m(t)[0] - target) ** 2).mean().backward()
+    torch.cuda.synchronize()
+    assert train.gradient_range_status() == 0
+    with torch.no_grad():                              # sin keeps the forward bounded, but the gradient that leaves the last
+        m.layers[-1].conv.upconv[0].weight.mul_(3.0e4)  # block through its up-conv is now ~1e4 times the head's
+    m.zero_grad(set_to_none=True)
+    ((m(t)[0] - target) ** 2).mean().backward()
+    torch.cuda.synchronize()
+    assert train.gradient_range_status(reset=False) & 1
+    assert m.train_backend == "b200"
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        for _ in range(train.CHECK_EVERY + 1):         # the periodic check comes round
+            m.zero_grad(set_to_none=True)
+            ((m(t)[0] - target) ** 2).mean().backward()
+            if m.train_backend == "torch":
+                break
+    assert m.train_backend == "torch" and any("saturated" in str(x.message) for x in w)
