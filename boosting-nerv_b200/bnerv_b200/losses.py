@@ -77,7 +77,10 @@ class _SsimStats(torch.autograd.Function):
 
 
 def ssim(pred, target, data_range=1.0, size_average=False):
-    s = torch.relu(_SsimStats.apply(pred, target, 1, float(data_range))[0, :, :, 0])
+    """pytorch_msssim.ssim as hnerv_utils.loss_fn calls it (:343-366): `nonnegative_ssim` keeps its default False in the
+    pinned 0.2.1, so a channel with a negative mean SSIM is NOT clamped (only ms_ssim clamps, unconditionally) and still
+    receives a gradient."""
+    s = _SsimStats.apply(pred, target, 1, float(data_range))[0, :, :, 0]
     return s.mean() if size_average else s.mean(1)
 
 

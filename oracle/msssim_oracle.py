@@ -4,7 +4,7 @@ The reference's loss (hnerv_utils.py:338-395: `ssim(pred, target, data_range=1, 
 `ms_ssim(...)` inside the 'Fusion*' losses) calls this third-party package, which is neither vendored in the reference
 tree nor installed here.  PARITY UNPINNED: there are no golden vectors of the package to check this file against; it
 restates the package's published algorithm (Gaussian 11-tap window sigma 1.5, separable 'valid' filtering, K = (0.01,
-0.03), relu on the per-channel cs / ssim means, five levels with weights (0.0448, 0.2856, 0.3001, 0.2363, 0.1333),
+0.03), relu on the per-channel cs / ssim means inside ms_ssim only (ssim's nonnegative_ssim defaults to False), five levels with weights (0.0448, 0.2856, 0.3001, 0.2363, 0.1333),
 2x2 average pooling with padding = size % 2 between levels, product of powers).  Only tests/ may import it.
 """
 import torch
@@ -43,7 +43,8 @@ def ssim_stats(x, y, data_range=1.0, k=(0.01, 0.03)):
 
 
 def ssim(x, y, data_range=1.0, size_average=False):
-    v = torch.relu(ssim_stats(x, y, data_range)[0])
+    # nonnegative_ssim=False is the package default in 0.2.1: no clamp on the single-scale path (ms_ssim clamps below)
+    v = ssim_stats(x, y, data_range)[0]
     return v.mean() if size_average else v.mean(1)
 
 

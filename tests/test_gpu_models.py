@@ -2,11 +2,12 @@
 (a) the golden vectors minted from the unmodified reference and (b) the CPU oracle at larger sizes.
 Gate: max|diff|/max|ref| <= 1e-3 (north_star), PSNR(ours, ref) far above the 0.01 dB parity requirement."""
 import copy
+import os
 
 import pytest
 import torch
 
-from conftest import check_trained_golden_outputs, load_golden, max_rel
+from conftest import GOLDEN, check_trained_golden_outputs, load_golden, max_rel
 from oracle import nerv_oracle as orc
 from bnerv_b200 import ENeRV_Boost, HNeRV_Boost, NeRV_Boost, make_args, tiny_args
 
@@ -210,6 +211,43 @@ def test_batch_entry_points_notice_weight_updates_between_calls():
 def _out_hw(m, t_host):
     with torch.no_grad():
         return tuple(m(t_host[:1].cuda())[0].shape[-2:])
+
+
+def test_compression_path_golden_decodes_natively_from_dequantised_weights():
+    """BASELINE config 5 on the device: the reference model built with --quant (scale / scale / scalebeta), after
+    cal_params, decodes with `dequant_w ?? weight` (lib/quant_ops.py:40).  The golden (tests/golden/make_golden_quant.py,
+    minted from the unmodified reference) carries every layer's dequant_w / dequant_b and the dequantised embedding; the
+    native decode of exactly those must match the reference image within 1e-3, and so must the integer-code ingest
+    (bnerv_pack_conv_weight_q) of round(w / scale)."""
+    import numpy as np
+    z = np.load(os.path.join(GOLDEN, "hnerv_tiny_quant.npz"))
+    m, a = _build("HNeRV_Boost")
+    own = m.state_dict()
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    m.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=True)        # the quantiser scales are not parameters here
+    m = m.cuda().eval()
+    mods = dict(m.named_modules())
+    n = 0
+    for k in z.files:
+        if k.startswith("dq/"):
+            name, kind = k[3:].rsplit(".", 1)
+            setattr(mods[name], "dequant_w" if kind == "weight" else "dequant_b", torch.from_numpy(z[k]).cuda())
+            n += 1
+    assert n > 40
+    t, deq_e = torch.from_numpy(z["t"]).cuda(), torch.from_numpy(z["deq_e"]).cuda()
+    with torch.no_grad():
+        img = m.forward_decoder(deq_e, t)[0]
+    assert max_rel(img.cpu(), torch.from_numpy(z["img"])) < REL
+    # integer codes + scale instead of the materialised dequant_w: bit-identical packed weights
+    from bnerv_b200 import ops
+    conv = m.decoder[2].sft_block.conv0
+    name = "decoder.2.sft_block.conv0"
+    w, ws = sd[name + ".weight"], sd[name + ".weight_quantizer.scale"]
+    b, bs = sd[name + ".bias"], sd[name + ".bias_quantizer.scale"]
+    pc_ref = ops.PackedConv(conv.dequant_w, conv.dequant_b, 1)
+    pc_q = ops.PackedConv(torch.zeros_like(conv.dequant_w), None, 1)
+    pc_q.repack_codes(torch.round(w / ws).to(torch.int16).cuda(), ws.cuda(), torch.round(b / bs).to(torch.int16).cuda(), bs.cuda())
+    assert torch.equal(pc_q.w, pc_ref.w) and torch.equal(pc_q.b, pc_ref.b)
 
 
 def test_full_resolution_properties_hnerv_1080p():
