@@ -35,6 +35,26 @@ import torch  # noqa: E402
 N_FRAMES = 600          # UVG sequence length; fixes norm_idx = (i+1)/600
 METRIC = "decode frames/sec @1920x1080"
 ALG_GFLOP = {"hnerv_l": 4429.9, "enerv_m": 443.3, "nerv_s": 19.33, "nerv_xs": 19.04, "hnerv_m": 2782.0}
+# SURVEY.md §8d algorithmic bytes per frame: block-fused, fp32 I/O (block input + block output + weights, summed over blocks)
+ALG_BYTES = {"hnerv_l": 4.35e9, "enerv_m": 1.15e9, "nerv_s": 190e6, "nerv_xs": 190e6}
+# which roofline bounds the preset: configs 3-5 tensor cores, configs 1-2 HBM bandwidth + launch latency
+BOUND = {"hnerv_l": "tensor", "hnerv_m": "tensor", "enerv_m": "tensor", "nerv_s": "hbm", "nerv_xs": "hbm"}
+
+
+def preset_roofline(name, ms_per_frame, pk, pk_src, alg_gflop):
+    """Step-level roofline of one decoded frame: §8d algorithmic work / the timed ms per frame, against the measured peak of
+    the bounding resource; the other resource's fraction is reported beside it."""
+    tf = alg_gflop / ms_per_frame                                   # GFLOP / ms = TFLOP/s
+    out = {"tensor": {"achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"]}}
+    if name in ALG_BYTES:
+        gbs = ALG_BYTES[name] / ms_per_frame / 1e6                  # bytes / ms -> GB/s
+        out["hbm"] = {"achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                      "algorithmic_bytes": ALG_BYTES[name]}
+    bound = BOUND.get(name, "tensor")
+    if bound not in out:
+        bound = "tensor"
+    return {"bound": bound, **out[bound], "other": {k: v for k, v in out.items() if k != bound}, "peak_source": pk_src,
+            "definition": "SURVEY.md 8d algorithmic FLOPs (unpadded channels) / block-fused fp32-I/O bytes per frame, divided by the timed ms per frame"}
 
 
 def algorithmic_gflop(name, model=None, args=None):
@@ -371,7 +391,7 @@ def run_b200(opt):
         "data": "synthetic",
         "config": {"workload": workload_name(opt.config, args), "batch": B, "frames_per_step_per_gpu": B,
                    "sharding": f"frames round-robin over {world} rank(s), no data-path collective",
-                   "launch": "one CUDA-graph replay per frame (PE, stem MLP, SFT table, 28 fused convs chained by programmatic dependent launch)",
+                   "launch": "one CUDA-graph replay per frame (PE, stem MLP, SFT table, the fused-conv / fused-block launches chained by programmatic dependent launch)",
                    "l2": "per-step activation traffic (>=4 GB at 1080p, every map 0.4-0.9 GB) exceeds the 126 MB L2; no explicit flush",
                    "algorithmic_gflop_per_frame": alg_gflop},
         "gpu_launches": launches,
@@ -384,16 +404,27 @@ def run_b200(opt):
                 "per_call": {"value": frames / (ms_percall / 1e3), "ms_per_step": ms_percall / K,
                              "api": ("model.forward_decoder(img_embed, norm_idx)" if is_h else "model(t)") +
                                     " per frame with the reference's semantics (device sync inside the call, model_nerv.py:58-59) + synchronous D2H"}},
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (all fused-conv launches of the step)",
-                     "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach_tf / peak_tf) if ach_tf else None,
-                     "peak_source": pk_src + " bf16 dense sustained; kind::f16 runs at the bf16 rate",
-                     "conv_ms_per_step": conv_ms / K,
-                     "kernel_timing": "separate eager pass of the same K steps, CUDA events around each launch; the timed region replays a CUDA graph",
-                     "traffic": traffic, "traffic_note": traffic_note, "algorithmic_bytes": alg_bytes,
-                     "top_launch": None if top is None else {"shape(cin,cout,k,s,H,W,act)": list(top["shape"]), "ms": top["ms"],
-                                                              "launches_per_step": top["per_step"],
-                                                              "tflops": top["flops"] / top["ms"] / 1e9}},
+        "roofline": None,
     }
+    # step-level roofline: SURVEY.md 8d algorithmic work per frame / the TIMED graph-replay region, per GPU (every rank decodes
+    # B frames per step); the bounding resource per preset (tensor cores for configs 3-5, HBM for the 12-channel NeRV presets)
+    rl = preset_roofline(opt.config, ms / K / B, pk, pk_src, alg_gflop)
+    rl.update({
+        "kernel": "the decode step (all launches of the captured graph; the fused-conv / fused-block kernels are > 90 % of it)",
+        "conv_only": {"achieved": ach_tf, "unit": "TFLOP/s", "frac": (ach_tf / peak_tf) if ach_tf else None, "conv_ms_per_step": conv_ms / K,
+                      "kernel_timing": "separate eager pass of the same K steps, CUDA events around each fused launch (events cannot be "
+                                       "recorded inside a replayed graph); host-bound for the small presets"},
+        "traffic": traffic, "traffic_note": traffic_note,
+        "algorithmic_bytes": None if opt.config not in ALG_BYTES else ALG_BYTES[opt.config] * B,
+        "algorithmic_bytes_note": "SURVEY.md 8d: block-fused, fp32 I/O (block in + block out + weights)",
+        "launch_fused_bytes": alg_bytes,
+        "launch_fused_bytes_note": "what this design's launches must move: C8 f16 input (+ residual) + output map(s) + weights per launch",
+        "measured_hbm": None if (traffic is None) else {"achieved": traffic / (ms / K) / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                                        "frac": traffic / (ms / K) / 1e6 / pk["hbm_gbs"]},
+        "top_launch": None if top is None else {"shape(cin,cout,k,s,H,W,act)": list(top["shape"]), "ms": top["ms"],
+                                                 "launches_per_step": top["per_step"], "tflops": top["flops"] / top["ms"] / 1e9},
+    })
+    line["roofline"] = rl
     if world == 1 and not opt.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         cpu_model = model.cpu()
@@ -424,11 +455,11 @@ def run_b200(opt):
         # extra, outside the metric: device-resident decode frames/s of the other BASELINE.json presets (configs 1-2),
         # same timing rules (CUDA-graph replay per frame, CUDA events, 10 warm-up + 200 timed frames)
         others = {}
-        for name in ("enerv_m", "nerv_s"):
+        for name in ("enerv_m", "nerv_s", "nerv_xs"):
             if name == opt.config:
                 continue
             try:
-                others[name] = other_preset_fps(name, dev)
+                others[name] = other_preset_fps(name, dev, pk, pk_src)
             except Exception as ex:
                 others[name] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
         line["other_presets"] = others
@@ -497,7 +528,7 @@ def norm_index_(i):
     return (i + 1) / N_FRAMES
 
 
-def other_preset_fps(name, dev, steps=200, warm=10):
+def other_preset_fps(name, dev, pk, pk_src, steps=200, warm=10):
     """Device-resident decode frames/s at batch 1 (the reference's -b 1) and batch 8 (frames are independent: batching
     amortises the per-launch latency that dominates the narrow presets)."""
     model, args = build_model(name)
@@ -522,6 +553,7 @@ def other_preset_fps(name, dev, steps=200, warm=10):
         out["frames_per_s" + key] = 1e3 / ms
         out["ms_per_frame" + key] = ms
         out["algorithmic_tflops" + key] = algorithmic_gflop(name, model, args) / ms
+        out["roofline" + key] = preset_roofline(name, ms, pk, pk_src, algorithmic_gflop(name, model, args))
     out["frames_timed"] = steps
     del model
     torch.cuda.empty_cache()

@@ -1,4 +1,5 @@
-"""Decode a few frames of a preset (for ncu captures).  Usage: python tools/frame_once.py [config] [frames]"""
+"""Decode a few frames of a preset (for ncu captures).  Usage: python tools/frame_once.py [config] [frames]
+The last frame is bracketed by cudaProfilerStart/Stop: `ncu --profile-from-start off` captures exactly one warm frame."""
 import os
 import sys
 
@@ -17,7 +18,11 @@ fh, fw = [int(v) for v in args.fc_hw.split("_")]
 emb = torch.rand(1, 16, fh, fw, device="cuda")
 t = torch.tensor([0.5], dtype=torch.float64, device="cuda")
 with torch.no_grad():
-    for _ in range(frames):
+    for i in range(frames):
+        if i == frames - 1:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStart()
         img = model.decode(emb, t) if args.model == "HNeRV_Boost" else model.decode(t)
 torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
 print(tuple(img.shape))
