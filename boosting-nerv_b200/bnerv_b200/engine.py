@@ -44,16 +44,26 @@ class _ConvSlot:
         self.m, self.k, self.s = module, k, s
         self.cin, self.cout = module.in_channels, module.out_channels // (s * s)
         self.key, self.pc = None, None
+        self.skey, self.ps = None, None          # packing for a split input map (precise blocks, ops.split_weight)
         self.dkey, self.pd = None, None          # dgrad packing of the same weights (training path, train.py)
         # HNeRV's 3x3 head to 3 channels has its own kernel form (bnerv_head_conv3); BNERV_NO_HEAD_KERNEL=1 = generic path
         self.head3 = bool(head and k == 3 and self.cout <= 3 and not os.environ.get("BNERV_NO_HEAD_KERNEL"))
         # NeRV / E-NeRV's 1x1 head: HBM-bound CUDA-core kernel (bnerv_head_conv1)
         self.head1 = bool(head and k == 1 and self.cout <= 4 and not os.environ.get("BNERV_NO_HEAD_KERNEL"))
 
-    def packed(self, force=False):
-        """force: re-pack unconditionally (inside a captured training graph the pack kernels ARE the per-step ingest)."""
+    def packed(self, force=False, split_in=False):
+        """force: re-pack unconditionally (inside a captured training graph the pack kernels ARE the per-step ingest).
+        split_in: the packing for a split input map (3 * Cin_p input channels)."""
         w, b = effective_weight(self.m)
         key = (_tensor_key(w), _tensor_key(b))
+        if split_in:
+            if key != self.skey or force:
+                if self.ps is None:
+                    self.ps = ops.PackedHead(w, b, split_in=True) if self.head3 else ops.PackedConv(w, b, self.s, split_in=True)
+                else:
+                    self.ps.repack(w, b)
+                self.skey = key
+            return self.ps
         if key != self.key or force:
             if self.pc is None:
                 self.pc = (ops.PackedHead(w, b) if self.head3 else ops.PackedHead1(w, b) if self.head1
@@ -144,6 +154,11 @@ class _Captured:
 class DecoderEngine:
     use_graph = True
     fuse_blocks = True          # narrow NeRVBlocks as one kernel each (False: always three fused-conv launches)
+    # Blocks decoded in the split ("precise", hi + lo f16) form of bnerv_conv_fused_split: a set of block indices, plus "head"
+    # for the head conv and "stem" for the cascade input.  Three times the tensor work of those blocks for ~2^-21 operands; the
+    # escape hatch for checkpoints whose f16-operand decode is not close enough to f32 (DESIGN.md "precision").  Set it with
+    # set_precise() or BNERV_PRECISE_BLOCKS ("all" | comma-separated indices / head / stem).
+    precise = frozenset()
 
     def __init__(self, model):
         self.model = model
@@ -168,6 +183,25 @@ class DecoderEngine:
         self._ws = {}          # workspaces per (B, h, w)
         self._sft = {}         # SftTable per B
         self._sft_key = None
+        env = os.environ.get("BNERV_PRECISE_BLOCKS")
+        if env:
+            self.set_precise(env)
+
+    def set_precise(self, blocks):
+        """blocks: "all", None/"" (off), or an iterable / comma-separated string of block indices, "head", "stem"."""
+        if isinstance(blocks, str):
+            blocks = blocks.strip()
+            if blocks == "all":
+                blocks = list(range(len(self.blocks))) + ["head", "stem"]
+            else:
+                blocks = [b if b in ("head", "stem") else int(b) for b in blocks.split(",") if b]
+        sel = frozenset(blocks or ())
+        bad = [b for b in sel if b not in ("head", "stem") and not (isinstance(b, int) and 0 <= b < len(self.blocks))]
+        if bad:
+            raise ValueError(f"precise blocks {bad}: not a block index of this model (0..{len(self.blocks) - 1}), 'head' or 'stem'")
+        self.precise = sel
+        self._ws.clear()
+        self.invalidate()
 
     # -- helpers -----------------------------------------------------------------------------------
     def _mlp(self, seq, x):
@@ -210,7 +244,8 @@ class DecoderEngine:
                 n = B * ops.round_up(blk.cout, 16) * H * W
                 for kname in ("cur", "x0", "u", "w", "nxt"):
                     sizes[kname] = max(sizes[kname], n)
-            ws = {kname: torch.empty(max(n, 8), dtype=torch.float16, device=device) for kname, n in sizes.items()}
+            mult = 3 if self.precise else 1         # split maps: [hi | lo | hi]
+            ws = {kname: torch.empty(max(n * mult, 8), dtype=torch.float16, device=device) for kname, n in sizes.items()}
             ws["out_hw"] = (H, W)
             self._ws[(B, h, w)] = ws
         return ws
@@ -317,20 +352,46 @@ class DecoderEngine:
             return buf[:shp[0] * shp[1] * shp[2] * shp[3] * shp[4]].view(shp)
 
         cur_buf, nxt_buf = ws["cur"], ws["nxt"]
-        cur = ops.nchw_to_c8(x)
+        prec = self.precise
+        nb = len(self.blocks)
+        cur_split = bool(prec) and "stem" in prec and 0 in prec
+        if cur_split:                       # the cascade input as a split map: hi / lo / hi channel blocks, each padded to 16
+            xp = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, ops.round_up(C, 16) - C))
+            hi = xp.half().float()
+            cur = ops.nchw_to_c8(torch.cat([hi, xp - hi, hi], dim=1))
+        else:
+            cur = ops.nchw_to_c8(x)
         cin, H, W = C, h, w
         outs = []
         for bi, blk in enumerate(self.blocks):
             g0, b0 = tab.g1p[2 * bi], tab.beta[2 * bi]
             g1, b1 = tab.g1p[2 * bi + 1], tab.beta[2 * bi + 1]
+            precise = bi in prec
             if blk.pre is not None:         # E-NeRV stage 0: conv1 (no activation) feeds conv2
-                mid = view(ws["w"], blk.pre.cout, H * blk.pre.s, W * blk.pre.s)
-                ops.conv_fused(cur, blk.pre.packed(), cin, H, W, act="none", out_pre=mid)
-                cur, cin, H, W = mid, blk.pre.cout, H * blk.pre.s, W * blk.pre.s
+                cmid = 3 * ops.round_up(blk.pre.cout, 16) if precise else blk.pre.cout
+                mid = view(ws["w"], cmid, H * blk.pre.s, W * blk.pre.s)
+                ops.conv_fused(cur, blk.pre.packed(split_in=cur_split), 3 * ops.round_up(cin, 16) if cur_split else cin, H, W,
+                               act="none", out_pre=mid, split=1 if precise else 0)
+                cur, cin, H, W, cur_split = mid, blk.pre.cout, H * blk.pre.s, W * blk.pre.s, precise
             Ho, Wo = H * blk.up.s, W * blk.up.s
-            out = view(nxt_buf, blk.cout, Ho, Wo)
+            cp = ops.round_up(blk.cout, 16)
+            out_split = ((bi + 1) in prec) if bi + 1 < nb else ("head" in prec)
+            out = view(nxt_buf, 3 * cp if out_split else blk.cout, Ho, Wo)
             done = None
-            fuse = blk.fuse if self.fuse_blocks else None
+            fuse = blk.fuse if (self.fuse_blocks and not precise and not out_split) else None
+            if precise:
+                # split form: every map of the block is [hi | lo | hi], every conv reads 3*Cp channels (bnerv_conv_fused_split)
+                cin_k = 3 * ops.round_up(cin, 16) if cur_split else cin
+                x0 = view(ws["x0"], 3 * cp, Ho, Wo)
+                u = view(ws["u"], 3 * cp, Ho, Wo)
+                wbuf = view(ws["w"], 3 * cp, Ho, Wo)
+                ops.conv_fused(cur, blk.up.packed(split_in=cur_split), cin_k, H, W, act=blk.act, g1p=g0, beta=b0, out_pre=x0,
+                               out_aff=u, split=1)
+                ops.conv_fused(u, blk.c0.packed(split_in=True), 3 * cp, Ho, Wo, act=blk.inner_act, g1p=g1, beta=b1, out_aff=wbuf,
+                               split=1)
+                ops.conv_fused(wbuf, blk.c1.packed(split_in=True), 3 * cp, Ho, Wo, act="none", resid=x0, out_pre=out,
+                               split=2 | (1 if out_split else 0))
+                done = True
             if fuse is not None and fuse[1] == "block":
                 done = ops.nerv_block_fused(cur, blk.up.packed(), blk.c0.packed(), blk.c1.packed(), cin, H, W, blk.act,
                                             blk.inner_act, g0, b0, g1, b1, out=out, form=fuse[0])
@@ -344,11 +405,19 @@ class DecoderEngine:
                 if done is None:
                     wbuf = view(ws["w"], blk.cout, Ho, Wo)
                     ops.conv_fused(u, blk.c0.packed(), blk.cout, Ho, Wo, act=blk.inner_act, g1p=g1, beta=b1, out_aff=wbuf)
-                    ops.conv_fused(wbuf, blk.c1.packed(), blk.cout, Ho, Wo, act="none", resid=x0, out_pre=out)
+                    ops.conv_fused(wbuf, blk.c1.packed(), blk.cout, Ho, Wo, act="none", resid=x0, out_pre=out,
+                                   split=1 if out_split else 0)
             if keep is True or (keep == "first" and bi == 0):
-                outs.append(ops.c8_to_nchw(out, blk.cout))
-            cur, cin, H, W = out, blk.cout, Ho, Wo
+                if out_split:               # hi + lo of the split map
+                    g = cp // 8
+                    outs.append(ops.c8_to_nchw(out[:, :g].contiguous(), blk.cout) + ops.c8_to_nchw(out[:, g:2 * g].contiguous(), blk.cout))
+                else:
+                    outs.append(ops.c8_to_nchw(out, blk.cout))
+            cur, cin, H, W, cur_split = out, blk.cout, Ho, Wo, out_split
             cur_buf, nxt_buf = nxt_buf, cur_buf
         img = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
-        ops.conv_fused(cur, self.head.packed(), cin, H, W, act="tanh01", out_nchw=img)
+        if cur_split:
+            ops.conv_fused(cur, self.head.packed(split_in=True), 3 * ops.round_up(cin, 16), H, W, act="tanh01", out_nchw=img)
+        else:
+            ops.conv_fused(cur, self.head.packed(), cin, H, W, act="tanh01", out_nchw=img)
         return img, outs

@@ -74,11 +74,27 @@ def pixel_shuffle(x, s):
     return y
 
 
-class PackedConv:
-    """Kernel-layout copy of one conv's effective weight: f16 [taps][Kp/8][Np][8] + f32 bias [Np]."""
+def split_weight(weight):
+    """OIHW f32 weight -> the weight of the same conv over a split input map [hi | lo | hi] (bnerv_conv_fused_split): input
+    channel blocks [W_hi ; W_hi ; W_lo], each zero-padded to a multiple of 16 channels; both halves are exact in f16."""
+    w = weight.detach().float()
+    pad = round_up(w.shape[1], 16) - w.shape[1]
+    if pad:
+        w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, pad))
+    hi = w.half().float()
+    lo = (w - hi).half().float()
+    return torch.cat([hi, hi, lo], dim=1).contiguous()
 
-    def __init__(self, weight, bias, s=1):
+
+class PackedConv:
+    """Kernel-layout copy of one conv's effective weight: f16 [taps][Kp/8][Np][8] + f32 bias [Np].  split_in: the conv reads a
+    split map (3 * round_up(Cin, 16) input channels, see split_weight)."""
+
+    def __init__(self, weight, bias, s=1, split_in=False):
         _need_cuda(weight, bias)
+        self.split_in = split_in
+        if split_in:
+            weight = split_weight(weight)
         co_s2, self.cin, k, k2 = weight.shape
         assert k == k2 and co_s2 % (s * s) == 0
         self.k, self.s, self.cout = k, s, co_s2 // (s * s)
@@ -88,7 +104,7 @@ class PackedConv:
         self.repack(weight, bias)
 
     def repack(self, weight, bias):
-        w = weight.detach().contiguous().float()
+        w = split_weight(weight) if self.split_in and weight.shape[1] != self.cin else weight.detach().contiguous().float()
         b = None if bias is None else bias.detach().contiguous().float()
         check("bnerv_pack_conv_weight",
               lib.bnerv_pack_conv_weight(ptr(w), ptr(b), self.cout, self.cin, self.k, self.s, ptr(self.w), ptr(self.b), _stream()))
@@ -117,8 +133,11 @@ class PackedHead:
     """Weights of a 3x3 conv to <= 3 channels in the head kernel's layout (bnerv_pack_head_weight): one [Kp][32] slab
     whose column tap*Cout + c holds W[c][:, tap]; the bias stays a raw f32 vector."""
 
-    def __init__(self, weight, bias):
+    def __init__(self, weight, bias, split_in=False):
         _need_cuda(weight, bias)
+        self.split_in = split_in
+        if split_in:
+            weight = split_weight(weight)
         self.cout, self.cin, k, k2 = weight.shape
         assert k == 3 and k2 == 3 and self.cout <= 3
         self.k, self.s = 3, 1
@@ -128,7 +147,7 @@ class PackedHead:
         self.repack(weight, bias)
 
     def repack(self, weight, bias):
-        w = weight.detach().contiguous().float()
+        w = split_weight(weight) if self.split_in and weight.shape[1] != self.cin else weight.detach().contiguous().float()
         check("bnerv_pack_head_weight", lib.bnerv_pack_head_weight(ptr(w), self.cout, self.cin, ptr(self.w), _stream()))
         if bias is None:
             self.b.zero_()
@@ -168,8 +187,9 @@ def conv_flops(B, cin, cout, k, s, H, W):
 
 
 def conv_fused(x_c8, pc, cin, H, W, act="none", resid=None, g1p=None, beta=None, out_pre=None, out_aff=None,
-               out_nchw=None, out_deriv=None):
-    """Launch the tcgen05 fused conv.  Output tensors are caller-provided (see bnerv_conv_fused[_ex])."""
+               out_nchw=None, out_deriv=None, split=0):
+    """Launch the tcgen05 fused conv.  Output tensors are caller-provided (see bnerv_conv_fused[_ex]).
+    split: bit 0 = C8 outputs are split maps, bit 1 = resid is a split map (bnerv_conv_fused_split)."""
     _need_cuda(x_c8)
     B = x_c8.shape[0]
     assert cin == pc.cin
@@ -186,6 +206,13 @@ def conv_fused(x_c8, pc, cin, H, W, act="none", resid=None, g1p=None, beta=None,
             raise ValueError("the head kernel writes the NCHW f32 image only")
         check("bnerv_head_conv3", lib.bnerv_head_conv3(ptr(x_c8), B, cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, ACT_CODES[act],
                                                        ptr(out_nchw), _stream()))
+    elif split:
+        if out_deriv is not None:
+            raise ValueError("the split form is a decode-path form (no derivative output)")
+        check("bnerv_conv_fused_split",
+              lib.bnerv_conv_fused_split(ptr(x_c8), B, cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, pc.k, pc.s, ACT_CODES[act],
+                                         ptr(resid), ptr(g1p), ptr(beta), ptr(out_pre), ptr(out_aff), ptr(out_nchw), split,
+                                         _stream()))
     elif out_deriv is None:
         check("bnerv_conv_fused",
               lib.bnerv_conv_fused(ptr(x_c8), B, cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, pc.k, pc.s, ACT_CODES[act],

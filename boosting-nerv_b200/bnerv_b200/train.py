@@ -16,8 +16,8 @@ is kept for the backward pass.  Backward per block, from dL/dout:
     up    : un-shuffle(dy); wgrad(x, dy_u); db_up; dx = dgrad(dy_u, Wup)  ->  dL/dout of the previous block
 
 Gradient maps are C8 f16 scaled by one power-of-two loss scale chosen on the device (bnerv_head_bwd); all
-reductions are f32.  Precision: f16 operands / f32 accumulation in both passes — the reference's own GPU training
-runs its convs in TF32 (torch.backends.cudnn.allow_tf32 defaults to True), which has the same 11-bit significand.
+reductions are f32.  Precision: f16 operands (11 significant bits) / f32 accumulation in both passes; parameter gradients
+are checked against torch fp32 autograd in tests/test_gpu_train.py.
 
 Both passes are pure stream work on static shapes, so they are captured ONCE per input shape into two CUDA graphs
 (weight packing included: the pack kernels read the live parameter storage, so an optimiser step needs no re-capture)
@@ -363,7 +363,7 @@ CHECK_EVERY = 32
 def _status_tensor(device):
     st = _STATUS.get(device)
     if st is None:
-        st = _STATUS[device] = [torch.zeros(1, dtype=torch.int32, device=device), 0]
+        st = _STATUS[device] = [torch.zeros(4, dtype=torch.int32, device=device), 0]
         check("bnerv_bwd_set_status", lib.bnerv_bwd_set_status(ptr(st[0])))
     return st
 
@@ -375,10 +375,20 @@ def gradient_range_status(device=None, reset=True):
     st = _STATUS.get(device)
     if st is None:
         return 0
-    bits = int(st[0].item())
+    bits = int(st[0][0].item())
     if reset and bits:
-        st[0].zero_()
+        st[0][0].zero_()
     return bits
+
+
+def loss_scale_state(device=None):
+    """(target for S * max|dL/dz_head| chosen by the device-side controller, largest scaled gradient of the last backward)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    st = _STATUS.get(device)
+    if st is None:
+        return None
+    v = st[0][1:3].clone().view(torch.float32).tolist()
+    return {"target": v[1] if v[1] > 0 else 8.0, "last_max_scaled_gradient": v[0]}
 
 
 def _check_gradient_range(eng, device):

@@ -47,14 +47,37 @@ constexpr int BW_THREADS = 256;     // 8 warps (block_reduce_atomic assumes <= 8
 // kernels every block's gradients pass through (inputs = the dgrad conv outputs, outputs = the next dgrad's input) OR bits into
 // status[0] when they see |value| >= 65504 (bit 0: saturated, i.e. clipped here or by the conv that produced it) or a
 // non-finite value (bit 1).  The pointer is set per process by bnerv_bwd_set_status (NULL: monitoring off).
+// status[1] (float bits): the largest |scaled gradient| these kernels saw since the last bnerv_head_bwd - the feedback of the loss-scale
+// controller (scale_ctrl_kernel): gradients of the low-resolution stages GROW relative to the head's while a model trains (15M
+// HNeRV: from 1.6x to 12 000x the head's maximum within 40 Adam steps, tools/grad_range_probe.py), so a scale fixed from the head's
+// maximum alone ends in saturation.  status[2] (float bits): the controller's current target for S * max|dL/dz_head|.
 static int* g_bwd_status = nullptr;
 
 __device__ __forceinline__ void bwd_flag(int* status, float amax) {
-    if (status != nullptr && !(amax < 65504.0f)) {
+    if (status == nullptr) return;
+    float wmax = amax;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, off));
+    if ((threadIdx.x & 31) == 0 && wmax > 0.0f && wmax <= 3.0e38f) atomicMax(status + 1, __float_as_int(wmax));
+    if (!(amax < 65504.0f)) {
         const int bit = (amax <= 3.0e38f) ? 1 : 2;            // NaN / inf fail this comparison as well
         const int any = __reduce_or_sync(__activemask(), bit);
         if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicOr(status, any);
     }
+}
+
+// One thread, before every head_bwd_kernel: target <- target adjusted by the previous backward's largest scaled gradient so that it
+// stays within [2^10, 2^14] (two octaves of margin below 65504 for step-to-step growth; the high-resolution maps, ~1e-4 of the
+// largest, remain f16 normals), never above 8 (13 bits of headroom when nothing is known yet).
+__global__ void scale_ctrl_kernel(int* status) {
+    float target = __int_as_float(status[2]);
+    if (!(target > 0.0f)) target = 8.0f;
+    const float last = __int_as_float(status[1]);
+    if (last > 16384.0f) target *= exp2f(-ceilf(log2f(last / 4096.0f)));
+    else if (last > 0.0f && last < 1024.0f && target < 8.0f) target = fminf(8.0f, target * 2.0f);
+    target = fmaxf(target, 1.0e-30f);
+    status[2] = __float_as_int(target);
+    status[1] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -71,17 +94,19 @@ __global__ void head_absmax_kernel(const float* __restrict__ dimg, const float* 
     if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));   // non-negative floats order like ints
 }
 
-__device__ __forceinline__ float scale_from_amax(float amax) {
-    // largest power of two S with S * amax <= 64: 10 bits of headroom to the f16 maximum, 30 bits above the smallest subnormal
+__device__ __forceinline__ float scale_from_amax(float amax, float target) {
+    // largest power of two S with S * amax <= 8: 13 bits of headroom to the f16 maximum for gradients that GROW on their way
+    // down the cascade (at full size they do: with S * amax <= 64 the 15M HNeRV saturated within 300 Adam steps - the
+    // gradient-range monitor, bnerv_bwd_set_status, caught it), 27 bits above the smallest subnormal for those that shrink
     if (!(amax > 0.0f) || !isfinite(amax)) return 1.0f;
-    float e = floorf(log2f(64.0f / amax));
+    float e = floorf(log2f(target / amax));
     e = fminf(fmaxf(e, -100.0f), 100.0f);
     return exp2f(e);
 }
 
 __global__ void head_bwd_kernel(const float* __restrict__ dimg, const float* __restrict__ img, int B, int C, int H, int W,
-                                const float* __restrict__ amax, float* __restrict__ scale, __half* __restrict__ dz) {
-    const float S = scale_from_amax(*amax);
+                                const float* __restrict__ amax, float* __restrict__ scale, __half* __restrict__ dz, const int* status) {
+    const float S = scale_from_amax(*amax, status ? __int_as_float(status[2]) : 8.0f);
     if (blockIdx.x == 0 && threadIdx.x == 0) { scale[0] = S; scale[1] = 1.0f / S; }
     const int cp = (C + 15) / 16 * 16;
     const size_t hw = static_cast<size_t>(H) * W;
@@ -412,8 +437,13 @@ extern "C" int bnerv_head_bwd(const float* dimg, const float* img, int B, int C,
     head_absmax_kernel<<<grid_1d(n, 256), 256, 0, st>>>(dimg, img, n, amax_scratch);
     int rc = check_launch("head_absmax_kernel");
     if (rc) return rc;
+    if (g_bwd_status != nullptr) {                 // loss-scale controller: feedback from the previous backward's gradient range
+        scale_ctrl_kernel<<<1, 1, 0, st>>>(g_bwd_status);
+        if ((rc = check_launch("scale_ctrl_kernel"))) return rc;
+    }
     const size_t total = static_cast<size_t>(B) * (round_up(C, 16) / 8) * H * W;
-    head_bwd_kernel<<<grid_1d(total, 256), 256, 0, st>>>(dimg, img, B, C, H, W, amax_scratch, scale, static_cast<__half*>(dz_c8));
+    head_bwd_kernel<<<grid_1d(total, 256), 256, 0, st>>>(dimg, img, B, C, H, W, amax_scratch, scale, static_cast<__half*>(dz_c8),
+                                                          g_bwd_status);
     return check_launch("head_bwd_kernel");
 }
 

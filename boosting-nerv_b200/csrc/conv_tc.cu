@@ -98,6 +98,7 @@ struct ConvTcArgs {
     __half* out_aff;        // C8 or null
     float* out_nchw;        // NCHW f32 or null
     __half* out_deriv;      // C8 or null: act'(pre-activation) (training forward)
+    long long split_stride; // halves between the hi and the lo block of a split map: (Cout_p/8) * Ho * Wo * 8
 };
 
 struct TileCoord { int b, h0, w0; };
@@ -130,6 +131,11 @@ constexpr int F_RESID = 1, F_AFF = 2, F_PRE = 4, F_NCHW = 8, F_SHUF = 16;
 constexpr int F_WIDE = 32;   // s == 2 row packing: the two chunks of a group are 32 contiguous output bytes
 constexpr int F_DERIV = 64;  // also write act'(pre-activation) (training forward)
 constexpr int F_HEAD = 128;  // 3x3 conv to <= 3 channels as ONE 1x1 contraction to 9*Cout columns + shift-sum (see mma_role_head)
+// Split ("precise") maps, generic instantiation only: a value v is kept as the f16 pair hi = f16(v), lo = f16(v - hi) (~22
+// significant bits) and a map is laid out [hi | lo | hi] over 3*Cout_p channels, so that the NEXT conv - an ordinary conv over
+// 3*Cout_p input channels with the weight blocks [W_hi ; W_hi ; W_lo] - accumulates hi*W_hi + lo*W_hi + hi*W_lo in f32.
+constexpr int F_SPLIT_OUT = 256;   // out_pre / out_aff are split maps
+constexpr int F_SPLIT_RES = 512;   // resid is a split map (hi + lo are both added)
 
 // Head mode geometry: P[q][(tap, c)] for the 18 x 18 halo pixels q of a 16 x 16 output tile, staged in shared memory
 constexpr int HEAD_N     = 32;                    // UMMA N (27 used for Cout = 3)
@@ -162,6 +168,33 @@ __device__ __forceinline__ uint4 pack8(const float2* x) {
     return o;
 }
 
+// lo half of the split representation of 8 values whose hi half is `hi`
+__device__ __forceinline__ uint4 pack8_lo(const float2* x, const uint4& hi) {
+    float2 d[4];
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float2 f = unpack_h2(h[p]);
+        d[p] = make_float2(x[p].x - f.x, x[p].y - f.y);
+    }
+    return pack8(d);
+}
+
+// the lo and second hi block of a split output map (the first hi block is stored by the regular path)
+__device__ __forceinline__ void store_split_tail(__half* out, size_t off0, size_t off1, long long ss, bool wide,
+                                                 const float2* x, const uint4& o0, const uint4& o1) {
+    const uint4 l0 = pack8_lo(x, o0), l1 = pack8_lo(x + 4, o1);
+    if (wide) {
+        st_global_32B(out + off0 + ss, l0, l1);
+        st_global_32B(out + off0 + 2 * ss, o0, o1);
+    } else {
+        *reinterpret_cast<uint4*>(out + off0 + ss) = l0;
+        *reinterpret_cast<uint4*>(out + off1 + ss) = l1;
+        *reinterpret_cast<uint4*>(out + off0 + 2 * ss) = o0;
+        *reinterpret_cast<uint4*>(out + off1 + 2 * ss) = o1;
+    }
+}
+
 // Epilogue of one 16-column accumulator group of one pixel = two chunks of 8 channels (chunk hh = columns hh*8..+7):
 // bias + activation (+ residual) (+ TAT affine) and the stores.  Constants are LDS broadcasts from the tile's Cst;
 // the bias is fetched by the caller BEFORE the accumulator wait, scale/shift are requested right after the bias add
@@ -171,7 +204,7 @@ struct GroupAddr { size_t off[2]; int cc[2], ho[2], wo[2]; };
 template <int ACT, int FLAGS>
 __device__ __forceinline__ void epilogue_group(const ConvTcArgs& a, int flags, const uint32_t* v, const float4* bs,
                                                const Cst* cb, int col, int b, const GroupAddr& ga, bool valid,
-                                               const uint4* rr, int Ho, int Wo) {
+                                               const uint4* rr, int Ho, int Wo, long long res_adj = 0) {
     float2 x[8];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
@@ -200,6 +233,14 @@ __device__ __forceinline__ void epilogue_group(const ConvTcArgs& a, int flags, c
             x[4 * hh + 0] = add2(x[4 * hh + 0], unpack_h2(rr[hh].x)); x[4 * hh + 1] = add2(x[4 * hh + 1], unpack_h2(rr[hh].y));
             x[4 * hh + 2] = add2(x[4 * hh + 2], unpack_h2(rr[hh].z)); x[4 * hh + 3] = add2(x[4 * hh + 3], unpack_h2(rr[hh].w));
         }
+        if ((flags & F_SPLIT_RES) && valid) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const uint4 rl = __ldg(reinterpret_cast<const uint4*>(a.resid + ga.off[hh] + res_adj + a.split_stride));
+                x[4 * hh + 0] = add2(x[4 * hh + 0], unpack_h2(rl.x)); x[4 * hh + 1] = add2(x[4 * hh + 1], unpack_h2(rl.y));
+                x[4 * hh + 2] = add2(x[4 * hh + 2], unpack_h2(rl.z)); x[4 * hh + 3] = add2(x[4 * hh + 3], unpack_h2(rl.w));
+            }
+        }
     }
     if (!valid) return;
     if (flags & F_DERIV) {
@@ -219,6 +260,7 @@ __device__ __forceinline__ void epilogue_group(const ConvTcArgs& a, int flags, c
             *reinterpret_cast<uint4*>(a.out_pre + ga.off[0]) = o0;
             *reinterpret_cast<uint4*>(a.out_pre + ga.off[1]) = o1;
         }
+        if (flags & F_SPLIT_OUT) store_split_tail(a.out_pre, ga.off[0], ga.off[1], a.split_stride, (flags & F_WIDE) != 0, x, o0, o1);
     }
     if (flags & F_NCHW) {
 #pragma unroll
@@ -245,6 +287,7 @@ __device__ __forceinline__ void epilogue_group(const ConvTcArgs& a, int flags, c
             *reinterpret_cast<uint4*>(a.out_aff + ga.off[0]) = o0;
             *reinterpret_cast<uint4*>(a.out_aff + ga.off[1]) = o1;
         }
+        if (flags & F_SPLIT_OUT) store_split_tail(a.out_aff, ga.off[0], ga.off[1], a.split_stride, (flags & F_WIDE) != 0, y, o0, o1);
     }
 }
 
@@ -252,7 +295,8 @@ __device__ __forceinline__ void epilogue_group(const ConvTcArgs& a, int flags, c
 // different warps so that all 16 epilogue warps work instead of 8).
 template <int ACT, int FLAGS>
 __device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, const uint32_t* v, const Cst* cb, int col, int b,
-                                               size_t off, int cc, int ho, int wo, bool valid, const uint4& rr, int Ho, int Wo) {
+                                               size_t off, int cc, int ho, int wo, bool valid, const uint4& rr, int Ho, int Wo,
+                                               long long res_adj = 0) {
     const float4 b0 = *reinterpret_cast<const float4*>(cb->bias + col), b1 = *reinterpret_cast<const float4*>(cb->bias + col + 4);
     float2 x[4];
     x[0] = add2(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(b0.x, b0.y));
@@ -278,10 +322,22 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, c
     if (flags & F_RESID) {
         x[0] = add2(x[0], unpack_h2(rr.x)); x[1] = add2(x[1], unpack_h2(rr.y));
         x[2] = add2(x[2], unpack_h2(rr.z)); x[3] = add2(x[3], unpack_h2(rr.w));
+        if ((flags & F_SPLIT_RES) && valid) {
+            const uint4 rl = __ldg(reinterpret_cast<const uint4*>(a.resid + off + res_adj + a.split_stride));
+            x[0] = add2(x[0], unpack_h2(rl.x)); x[1] = add2(x[1], unpack_h2(rl.y));
+            x[2] = add2(x[2], unpack_h2(rl.z)); x[3] = add2(x[3], unpack_h2(rl.w));
+        }
     }
     if (!valid) return;
     if (flags & F_DERIV) *reinterpret_cast<uint4*>(a.out_deriv + off) = pack8(dv);
-    if (flags & F_PRE) *reinterpret_cast<uint4*>(a.out_pre + off) = pack8(x);
+    if (flags & F_PRE) {
+        const uint4 o = pack8(x);
+        *reinterpret_cast<uint4*>(a.out_pre + off) = o;
+        if (flags & F_SPLIT_OUT) {
+            *reinterpret_cast<uint4*>(a.out_pre + off + a.split_stride) = pack8_lo(x, o);
+            *reinterpret_cast<uint4*>(a.out_pre + off + 2 * a.split_stride) = o;
+        }
+    }
     if (flags & F_NCHW) {
         const float xs[8] = {x[0].x, x[0].y, x[1].x, x[1].y, x[2].x, x[2].y, x[3].x, x[3].y};
 #pragma unroll
@@ -295,7 +351,12 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcArgs& a, int flags, c
             y[2 * p]     = fma2(x[2 * p],     make_float2(gg[p].x, gg[p].y), make_float2(ee[p].x, ee[p].y));
             y[2 * p + 1] = fma2(x[2 * p + 1], make_float2(gg[p].z, gg[p].w), make_float2(ee[p].z, ee[p].w));
         }
-        *reinterpret_cast<uint4*>(a.out_aff + off) = pack8(y);
+        const uint4 o = pack8(y);
+        *reinterpret_cast<uint4*>(a.out_aff + off) = o;
+        if (flags & F_SPLIT_OUT) {
+            *reinterpret_cast<uint4*>(a.out_aff + off + a.split_stride) = pack8_lo(y, o);
+            *reinterpret_cast<uint4*>(a.out_aff + off + 2 * a.split_stride) = o;
+        }
     }
 }
 
@@ -645,7 +706,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int h = t.h0 + (m >> 3);
                 const int w = t.w0 + mt * 8 + (m & 7);
                 const bool valid = (h < a.H) && (w < a.W);
-                const size_t base_b = static_cast<size_t>(t.b) * cout_groups * plane;
+                const size_t base_b = static_cast<size_t>(t.b) * cout_groups * plane * ((flags & F_SPLIT_OUT) ? 3 : 1);
+                // a residual map whose batch stride differs from the output's (split vs plain)
+                const long long res_adj = static_cast<long long>(t.b) * cout_groups * static_cast<long long>(plane) *
+                                          (((flags & F_SPLIT_RES) ? 3 : 1) - ((flags & F_SPLIT_OUT) ? 3 : 1));
                 const size_t pix = (static_cast<size_t>(h) * s * Wo + static_cast<size_t>(w) * s) * 8;
 
                 // Stage the per-row constants (bias, TAT scale+1, TAT shift) and per-16-column-group addressing in
@@ -702,13 +766,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     wo = w;
                 }
                 uint4 rr = make_uint4(0, 0, 0, 0);
-                if ((flags & F_RESID) && valid) rr = __ldg(reinterpret_cast<const uint4*>(a.resid + off));
+                if ((flags & F_RESID) && valid) rr = __ldg(reinterpret_cast<const uint4*>(a.resid + off + res_adj));
                 mbar_wait(p.tfull + abuf * 8, aphase);
                 tc_fence_after();
                 uint32_t v8[8];
                 tmem_ld8(p.tmem_base + (static_cast<uint32_t>(q * 32) << 16) + abuf * BUF_COLS + mt * G::ACC_STRIDE + cs * 8, v8);
                 tmem_ld_wait();
-                epilogue_chunk<ACT, FLAGS>(a, flags, v8, cb, cs * 8, t.b, off, cc, ho, wo, valid, rr, Ho, Wo);
+                epilogue_chunk<ACT, FLAGS>(a, flags, v8, cb, cs * 8, t.b, off, cc, ho, wo, valid, rr, Ho, Wo, res_adj);
               } else {
                 bool act16[4];
 #pragma unroll
@@ -753,7 +817,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
                             rres[j][hh] = make_uint4(0, 0, 0, 0);
-                            if (act16[j] && valid) rres[j][hh] = __ldg(reinterpret_cast<const uint4*>(a.resid + ga.off[hh]));
+                            if (act16[j] && valid) rres[j][hh] = __ldg(reinterpret_cast<const uint4*>(a.resid + ga.off[hh] + res_adj));
                         }
                     }
                 }
@@ -774,7 +838,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tmem_ld_wait();
                         if (j + 1 < 4 && act16[(j + 1) & 3]) tmem_ld16(taddr + (cs + G::CS * (j + 1)) * 16, v[(j + 1) & 1]);
                         const GroupAddr ga = group_addr(cs + G::CS * j);
-                        epilogue_group<ACT, FLAGS>(a, flags, v[j & 1], bs, cb, col, t.b, ga, valid, rres[j], Ho, Wo);
+                        epilogue_group<ACT, FLAGS>(a, flags, v[j & 1], bs, cb, col, t.b, ga, valid, rres[j], Ho, Wo, res_adj);
                     }
                 }
               }
@@ -955,10 +1019,34 @@ extern "C" int bnerv_conv_fused(const void* x, int B, int Cin, int H, int W, con
                                out_nchw, nullptr, stream);
 }
 
+static int conv_fused_impl(const void* x, int B, int Cin, int H, int W, const void* w_packed,
+                           const float* bias_packed, int Cout, int k, int s, int act, const void* resid,
+                           const float* g1p, const float* beta, void* out_pre, void* out_aff, float* out_nchw,
+                           void* out_deriv, int split, void* stream);
+
 extern "C" int bnerv_conv_fused_ex(const void* x, int B, int Cin, int H, int W, const void* w_packed,
                                    const float* bias_packed, int Cout, int k, int s, int act, const void* resid,
                                    const float* g1p, const float* beta, void* out_pre, void* out_aff, float* out_nchw,
                                    void* out_deriv, void* stream) {
+    return conv_fused_impl(x, B, Cin, H, W, w_packed, bias_packed, Cout, k, s, act, resid, g1p, beta, out_pre, out_aff, out_nchw,
+                           out_deriv, 0, stream);
+}
+
+extern "C" int bnerv_conv_fused_split(const void* x, int B, int Cin, int H, int W, const void* w_packed,
+                                      const float* bias_packed, int Cout, int k, int s, int act, const void* resid,
+                                      const float* g1p, const float* beta, void* out_pre, void* out_aff, float* out_nchw,
+                                      int split, void* stream) {
+    if (split & ~3) return set_error(BNERV_E_BADARG, "conv_fused_split: split = %d (bit 0: split outputs, bit 1: split residual)", split);
+    if ((split & 2) && !resid) return set_error(BNERV_E_BADARG, "conv_fused_split: split residual without a residual");
+    if ((split & 1) && !out_pre && !out_aff) return set_error(BNERV_E_BADARG, "conv_fused_split: split output without a C8 output");
+    return conv_fused_impl(x, B, Cin, H, W, w_packed, bias_packed, Cout, k, s, act, resid, g1p, beta, out_pre, out_aff, out_nchw,
+                           nullptr, split, stream);
+}
+
+static int conv_fused_impl(const void* x, int B, int Cin, int H, int W, const void* w_packed,
+                           const float* bias_packed, int Cout, int k, int s, int act, const void* resid,
+                           const float* g1p, const float* beta, void* out_pre, void* out_aff, float* out_nchw,
+                           void* out_deriv, int split, void* stream) {
     if (!x || !w_packed || !bias_packed) return set_error(BNERV_E_BADARG, "conv_fused: null operand");
     if (B <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || s <= 0) return set_error(BNERV_E_BADARG, "conv_fused: non-positive size");
     if (k != 1 && k != 3) return set_error(BNERV_E_UNSUPPORTED, "conv_fused: kernel size %d (only 1 and 3)", k);
@@ -1016,7 +1104,9 @@ extern "C" int bnerv_conv_fused_ex(const void* x, int B, int Cin, int H, int W, 
     a.out_aff = static_cast<__half*>(out_aff);
     a.out_nchw = out_nchw;
     a.out_deriv = static_cast<__half*>(out_deriv);
-    a.flags = (out_deriv ? F_DERIV : 0) | (resid ? F_RESID : 0) | (g1p ? F_AFF : 0) | (out_pre ? F_PRE : 0) | (out_nchw ? F_NCHW : 0) | (s > 1 ? F_SHUF : 0) | (s == 2 ? F_WIDE : 0);
+    a.flags = (out_deriv ? F_DERIV : 0) | (resid ? F_RESID : 0) | (g1p ? F_AFF : 0) | (out_pre ? F_PRE : 0) | (out_nchw ? F_NCHW : 0) | (s > 1 ? F_SHUF : 0) | (s == 2 ? F_WIDE : 0) |
+              ((split & 1) ? F_SPLIT_OUT : 0) | ((split & 2) ? F_SPLIT_RES : 0);
+    a.split_stride = static_cast<long long>(cout_p / 8) * (1LL * H * s) * (1LL * W * s) * 8;
 
     if (g_num_sms == 0) {
         int dev = 0;

@@ -109,6 +109,21 @@ int bnerv_conv_fused_ex(const void* x, int B, int Cin, int H, int W,
                         int act, const void* resid, const float* g1p, const float* beta,
                         void* out_pre, void* out_aff, float* out_nchw, void* out_deriv, void* stream);
 
+/* The higher-precision ("split") form of bnerv_conv_fused, selectable per layer: f16 operands carry 11 significant bits, which
+ * bounds a deep cascade of 1000+-term contractions at ~2e-3 of the f32 result on trained weights ("precision").  A
+ * split map keeps every value v as the f16 pair hi = f16(v), lo = f16(v - hi) (~22 bits) laid out as ONE C8 map over 3*Cp
+ * channels, [hi | lo | hi].  The conv that consumes it is an ordinary bnerv_conv_fused over Cin = 3*Cp input channels whose
+ * packed weight holds the input-channel blocks [W_hi ; W_hi ; W_lo] (W_hi = f16(W), W_lo = f16(W - W_hi)): the f32 accumulator
+ * receives hi*W_hi + lo*W_hi + hi*W_lo, i.e. the product to ~2^-21 instead of 2^-11 - three times the tensor work, same kernel.
+ *   split bit 0 : out_pre / out_aff are written as split maps [B][3*Cout_p/8][Ho][Wo][8]
+ *   split bit 1 : resid is a split map; hi + lo are both added
+ * x / Cin / w_packed are used as given (a split input is simply a map with 3*Cp channels).  Replaces the same reference lines
+ * as bnerv_conv_fused. */
+int bnerv_conv_fused_split(const void* x, int B, int Cin, int H, int W,
+                           const void* w_packed, const float* bias_packed, int Cout, int k, int s,
+                           int act, const void* resid, const float* g1p, const float* beta,
+                           void* out_pre, void* out_aff, float* out_nchw, int split, void* stream);
+
 /* One NeRVBlock (model_blocks.py:34-46 with the ResBlock_SFT of :74-89) = the three fused-conv launches above issued
  * back to back on `stream` and chained by programmatic dependent launch:
  *     x0 = act_up(PS_s(conv_k(x; w_up)))         u   = x0*g0p + beta0
@@ -255,9 +270,13 @@ int bnerv_channel_sum(const void* x_c8, int B, int Cp, int H, int W, int per_b, 
 /* Gradient-range monitor of the native backward.  Gradient maps are f16 behind ONE power-of-two loss scale chosen at the head
  * (bnerv_head_bwd) and every conversion saturates, so a gradient that outgrows 65504 / S deeper in the cascade would be clipped
  * silently.  bnerv_resblock_mid_bwd / bnerv_block_front_bwd - which every block's gradients pass through - OR into
- * status[0]: bit 0 when they read or produce |value| >= 65504 (saturated), bit 1 for a non-finite value.  `status` is one
- * device int the caller zeroes and reads when it chooses (no synchronisation here); NULL switches the monitor off.  Process-wide;
- * kernels captured in a CUDA graph keep the pointer they were launched with. */
+ * status[0]: bit 0 when they read or produce |value| >= 65504 (saturated), bit 1 for a non-finite value.  They also keep
+ * status[1] = the largest |scaled gradient| of the step (float bits), which bnerv_head_bwd feeds back into the NEXT step's loss
+ * scale: status[2] (float bits, 0 = default 8) is the target for S * max|dL/dz_head|, lowered when the deepest maps exceed 2^14
+ * and raised again (up to 8) when they fall below 2^10 - the gradients of the low-resolution stages grow by orders of magnitude
+ * relative to the head's while a model trains.  `status` = FOUR device ints the caller zeroes once and reads when it chooses (no
+ * synchronisation here); NULL switches monitor and controller off (fixed target 8).  Process-wide; kernels captured in a CUDA
+ * graph keep the pointer they were launched with. */
 int bnerv_bwd_set_status(int* status);
 
 /* ResBlock_SFT middle transposed (model_blocks.py:86-87; forward v = gelu(c0), w = v*g1p + beta1):

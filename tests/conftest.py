@@ -65,6 +65,13 @@ def max_rel(a, b):
     return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-12)).item()
 
 
+def elementwise_rel(a, b, eps=1e-3):
+    """max over elements of |a-b| / (|b| + eps): the element-wise companion of max_rel (which normalises by the LARGEST
+    reference magnitude).  Reported next to it; the 1e-3 gate of north_star is applied to max_rel."""
+    a, b = a.double(), b.double()
+    return ((a - b).abs() / (b.abs() + eps)).max().item()
+
+
 def check_trained_golden_outputs(img, outs, g, psnr_fn):
     """Gates shared by the reference-TRAINED goldens (CPU: the oracle's f16-operand emulation; GPU: the device decode).
     Intermediate maps within 5e-3 of the f32 reference (measured on the device: <= 3.1e-3 HNeRV, 1.6e-3 E-NeRV, 8.9e-4 NeRV,

@@ -55,7 +55,7 @@ def test_model_matches_reference_golden(model, gold):
         check_trained_golden_outputs(img, outs, g, orc.psnr)     # maps within 5e-3 of f32 (measured <= 1.6e-3), PSNR-vs-frames 0.01 dB
         return
     # Reference-TRAINED weights: block outputs reach 3-4x the magnitudes of the initialisation's and the INTERMEDIATE maps
-    # of an 11-bit-significand operand arithmetic (f16 here, TF32 in the reference's own GPU default) move by up to 3e-3
+    # of an 11-bit-significand operand arithmetic (f16) move by up to 3e-3
     # of their maximum, while the image - what north_star gates - stays inside 1e-3 (asserted above).  The oracle's f16-operand
     # emulation predicts those numbers on the CPU (HNeRV: 1.7e-3 / 3.1e-3 / 1.4e-3 / 1.8e-3 for out2..out5; E-NeRV <= 1.4e-3,
     # NeRV <= 7e-4; tests/test_oracle_golden.py); the kernels must sit
@@ -302,6 +302,79 @@ def test_benchmarked_presets_full_frame_against_oracle(name):
     assert img.shape == ref.shape and tuple(img.shape[-2:]) in ((1080, 1920), (720, 1280), (640, 1280))
     assert max_rel(img.cpu(), ref) < REL
     assert orc.psnr(img.cpu(), ref) > 60.0
+
+
+@pytest.mark.parametrize("name,steps", [("nerv_s", 300), ("enerv_m", 300), ("hnerv_l", 300)])
+def test_benchmarked_presets_after_training_against_oracle(name, steps):
+    """SURVEY.md 8d / VERDICT r1 2a+2b: trained pre-sin magnitudes differ from the initialisation's, so the FULL-SIZE presets are
+    also checked after a short training run.  The preset is trained here for `steps` Adam steps with the native forward +
+    backward on synthetic frames (the weights are just inputs: whatever the run produces is handed to the CPU oracle), then
+    one frame is decoded natively and by the oracle in f32.
+      * split ("precise") form on every block: image within 1e-3 of the f32 oracle (max-abs normalised by max|ref|, north_star);
+        measured 1e-5 NeRV-S, 2.8e-4 E-NeRV-M, 1.4e-4 HNeRV-L (profiles/r02_trained_fullsize_report.txt);
+      * default form (f16 operands, 11 significant bits): a trained cascade amplifies operand rounding 5-20x from the first to
+        the last block (the report shows the split form of ONLY the late blocks does not help: the error arrives from upstream),
+        so the image sits 7e-4 .. 3.7e-3 from f32 while the device agrees with the oracle's f16-operand emulation to 5e-4
+        (HNeRV-L; tools/trained_fullsize_report.py).  Gated at 5e-3 and, as north_star's metric
+        asks, PSNR against the frame it was trained on within 0.01 dB of the oracle's; block outputs far from the f16 limit."""
+    import bench
+    from conftest import elementwise_rel
+    model, a = bench.build_model(name)
+    cfg = orc.cfg_from_args(a)
+    fh, fw = [int(v) for v in a.fc_hw.split("_")]
+    up = 1
+    for s_ in a.dec_strds:
+        up *= s_
+    H, W = fh * up, fw * up
+    is_h = a.model == "HNeRV_Boost"
+    n = 2
+    t = torch.tensor([(i + 1) / 600 for i in range(n)], dtype=torch.float64, device="cuda")
+    emb = torch.rand(n, 16, fh, fw, generator=torch.Generator().manual_seed(9)).cuda() if is_h else None
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, H, device="cuda"), torch.linspace(0, 1, W, device="cuda"), indexing="ij")
+    frames = torch.stack([torch.stack([0.5 + 0.45 * torch.sin(6.2832 * ((1 + c) * xx + (2 - 0.5 * c) * yy + 0.13 * (c + 1) * i)) for c in range(3)])
+                          for i in range(n)])
+    model = model.cuda().train()
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4)
+    first = last = None
+    for it in range(steps):
+        i = it % n
+        opt.zero_grad(set_to_none=True)
+        out = (model.forward_decoder(emb[i:i + 1], t[i:i + 1]) if is_h else model(t[i:i + 1]))[0]
+        loss = ((out - frames[i:i + 1]) ** 2).mean()
+        loss.backward()
+        opt.step()
+        if it < n:
+            first = loss.item() if first is None else max(first, loss.item())
+        last = loss.item()
+    assert model.train_backend == "b200", "the gradient-range monitor fell back to torch autograd"
+    assert last < first, (first, last)                            # it did train (slowly: the step size keeps a 300-step run stable)
+    model.eval()
+    model.keep_intermediates = True
+    sd = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    with torch.no_grad():
+        img, outs, _ = model.forward_decoder(emb[:1], t[:1]) if is_h else model(t[:1])
+        if is_h:
+            ref, ref_outs = orc.hnerv_boost_decode(sd, cfg, emb[:1].cpu(), t[:1].cpu())
+        else:
+            ref, ref_outs = orc.forward(a.model, sd, cfg, t[:1].cpu())
+        img = img.clone()
+        model.engine().set_precise("all")
+        img_p = (model.forward_decoder(emb[:1], t[:1]) if is_h else model(t[:1]))[0].clone()
+        model.engine().set_precise(None)
+    err, err_p = max_rel(img.cpu(), ref), max_rel(img_p.cpu(), ref)
+    gt = frames[:1].cpu()
+    d_psnr = abs(orc.psnr(img.cpu(), gt) - orc.psnr(ref, gt))
+    amax = max(float(o.abs().max()) for o in outs[1:])
+    print(f"{name}: trained {steps} steps (loss {first:.4f} -> {last:.5f}); image max_rel default {err:.2e} (element-wise "
+          f"{elementwise_rel(img.cpu(), ref):.2e}), split form {err_p:.2e} (element-wise {elementwise_rel(img_p.cpu(), ref):.2e}); "
+          f"PSNR vs frame ours {orc.psnr(img.cpu(), gt):.4f} / split {orc.psnr(img_p.cpu(), gt):.4f} / oracle {orc.psnr(ref, gt):.4f} dB; "
+          f"max |block output| {amax:.1f} (f16 limit 65504)")
+    assert err_p < REL, err_p
+    assert err < 5e-3, err
+    assert d_psnr < 0.01, d_psnr
+    assert abs(orc.psnr(img_p.cpu(), gt) - orc.psnr(ref, gt)) < 0.002
+    assert amax < 0.25 * 65504
 
 
 @pytest.mark.parametrize("model", ["HNeRV_Boost", "NeRV_Boost"])

@@ -137,7 +137,8 @@ def test_elementwise_transposes_and_reductions():
     assert max_rel(db0[:C], ref.sum((0, 2, 3))) < 1e-5
     assert max_rel(ops.channel_sum(c8(du))[:C], du.sum((0, 2, 3))) < 1e-5
     assert max_rel(ops.channel_sum(c8(du), True)[:, :C], du.sum((2, 3))) < 1e-5
-    # head: loss scale is a power of two chosen so that max|dz| lands in (32, 64]
+    # head: loss scale is a power of two chosen so that max|dz| lands in (target / 2, target], target <= 8 (the device-side controller
+    # lowers it when the deepest gradient maps of the previous step approached the f16 range; 8 when nothing is known)
     img = torch.rand(B, 3, H, W, device="cuda")
     dimg = torch.randn(B, 3, H, W, device="cuda") * 1e-7
     scale = torch.zeros(2, device="cuda")
@@ -145,7 +146,10 @@ def test_elementwise_transposes_and_reductions():
     S, inv = scale.tolist()
     ref = dimg * 2 * img * (1 - img)
     assert S * inv == 1.0 and S == 2.0 ** round(torch.log2(torch.tensor(S)).item())
-    assert 32.0 < ref.abs().max().item() * S <= 64.0
+    from bnerv_b200 import train
+    state = train.loss_scale_state()
+    target = 8.0 if state is None else state["target"]
+    assert target <= 8.0 and target / 2 < ref.abs().max().item() * S <= target
     assert max_rel(ops.c8_to_nchw(dz, 3) / S, ref) < 6e-4
     # all-zero gradient: scale falls back to 1, nothing NaN
     dz0 = ops.head_bwd(torch.zeros_like(dimg), img, scale)
@@ -388,3 +392,33 @@ def test_gradient_range_monitor_flags_saturation_and_falls_back_to_torch():
             if m.train_backend == "torch":
                 break
     assert m.train_backend == "torch" and any("saturated" in str(x.message) for x in w)
+
+
+def test_loss_scale_controller_follows_the_gradient_range():
+    """The deepest gradient maps of a training model outgrow the head's by orders of magnitude (tools/grad_range_probe.py);
+    the backward kernels record the largest scaled gradient of a step (status[1]) and bnerv_head_bwd lowers / raises the next
+    step's scale target to keep it within [2^10, 2^14] - on the device, no host synchronisation."""
+    from bnerv_b200 import train
+    ops = _ops()
+    st = train._status_tensor(torch.device("cuda", torch.cuda.current_device()))[0]
+    B, H, W = 1, 16, 24
+    img = torch.rand(B, 3, H, W, device="cuda")
+    dimg = torch.randn(B, 3, H, W, device="cuda") * 1e-6
+    scale = torch.zeros(2, device="cuda")
+    as_bits = lambda v: int(torch.tensor([v], dtype=torch.float32).view(torch.int32).item())
+    st.zero_()
+    ops.head_bwd(dimg, img, scale)
+    assert train.loss_scale_state()["target"] == 8.0
+    st[1] = as_bits(40000.0)                      # the previous backward nearly saturated: 40000 / 4096 -> 2^-4
+    ops.head_bwd(dimg, img, scale)
+    assert train.loss_scale_state()["target"] == 0.5 and train.loss_scale_state()["last_max_scaled_gradient"] == 0.0
+    amax = (dimg * 2 * img * (1 - img)).abs().max().item()
+    assert 0.25 < amax * scale[0].item() <= 0.5
+    st[1] = as_bits(3000.0)                       # inside the band: unchanged
+    ops.head_bwd(dimg, img, scale)
+    assert train.loss_scale_state()["target"] == 0.5
+    for want in (1.0, 2.0, 4.0, 8.0, 8.0):        # far below the band: doubled per step, capped at 8
+        st[1] = as_bits(100.0)
+        ops.head_bwd(dimg, img, scale)
+        assert train.loss_scale_state()["target"] == want
+    st.zero_()

@@ -8,7 +8,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "boosting-nerv_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
-from conftest import load_golden, max_rel  # noqa: E402
+from conftest import elementwise_rel, load_golden, max_rel  # noqa: E402
 from oracle import nerv_oracle as orc  # noqa: E402  (checker only)
 from bnerv_b200 import ENeRV_Boost, HNeRV_Boost, NeRV_Boost, tiny_args  # noqa: E402
 
@@ -26,7 +26,8 @@ for model, gold in (("HNeRV_Boost", "hnerv_tiny_trained.npz"), ("NeRV_Boost", "n
     emu_img, emu_outs = orc.forward(model, sd, orc.cfg_from_args(a), *inputs)
     orc.EMULATE = None
     f = lambda xs: "[" + ", ".join(f"{x:.1e}" for x in xs) + "]"
-    print(f"{gold}: image vs ref {max_rel(img.cpu(), g['img']):.2e}, vs emulation {max_rel(img.cpu(), emu_img):.2e}; "
+    print(f"{gold}: image vs ref {max_rel(img.cpu(), g['img']):.2e} (element-wise |a-b|/(|b|+1e-3): {elementwise_rel(img.cpu(), g['img']):.2e}), "
+          f"vs emulation {max_rel(img.cpu(), emu_img):.2e}; "
           f"maps vs ref {f([max_rel(o.cpu(), g[f'out{i}']) for i, o in enumerate(outs)])}, vs emulation "
           f"{f([max_rel(o.cpu(), emu_outs[i]) for i, o in enumerate(outs)])}; PSNR vs frames: ours {orc.psnr(img.cpu(), g['frame']):.4f} dB, "
           f"reference {orc.psnr(g['img'], g['frame']):.4f} dB")
