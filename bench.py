@@ -486,13 +486,24 @@ def ptq_extra(cfg_name, dev, frames=50):
     fh, fw = [int(v) for v in args.fc_hw.split("_")]
     emb = torch.rand(N_FRAMES, 16, fh, fw, device=dev, generator=torch.Generator(device=dev).manual_seed(7)) if is_h else None
     torch.cuda.synchronize()
+    tc = time.perf_counter()
+    models, quant_ckt = ptq.quant_model(model, SimpleNamespace(quant_model_bit=8))      # first call: allocator growth, kernel load
+    torch.cuda.synchronize()
+    first_ms = (time.perf_counter() - tc) * 1e3
+    ptq.huffman_bits(quant_ckt)                               # (warm-up of the histogram kernel too)
+    del models, quant_ckt
+    sd = model.state_dict()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    models, quant_ckt = ptq.quant_model(model, SimpleNamespace(quant_model_bit=8))
+    quant_ckt, _ = ptq.quant_state_dict(sd, 8)                # the quantisation itself: ONE multi-tensor call (five launches)
     q_emb, deq_emb = ptq.quant_tensor(emb, 6) if is_h else (None, None)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     bits = ptq.huffman_bits(quant_ckt, q_emb)
     t2 = time.perf_counter()
+    models, quant_ckt = ptq.quant_model(model, SimpleNamespace(quant_model_bit=8))      # the reference-shaped call
+    torch.cuda.synchronize()
+    model_ms = (time.perf_counter() - t2) * 1e3
     qmodel = models[1].eval()
     t = torch.tensor([norm_index_(i) for i in range(frames + 5)], dtype=torch.float64, device=dev)
     psnr = []
@@ -515,7 +526,10 @@ def ptq_extra(cfg_name, dev, frames=50):
         pixels *= s_ * s_
     out = {"what": "8-bit PTQ of the decoder (+ 6-bit embeddings for HNeRV), Huffman-coded size, decode of the quantised model; random-init "
                    "weights, so bits/param ~ 8 and the PSNR only says how far 8-bit weights move the output",
-           "quantise_ms": (t1 - t0) * 1e3, "huffman_ms": (t2 - t1) * 1e3, "bits_per_param": bits["bits_per_param"],
+           "quantise_ms": (t1 - t0) * 1e3, "quantise_note": "quant_state_dict over all decoder tensors (one multi-tensor call) + the "
+           "embedding tensor, second call", "quant_model_ms": model_ms, "quant_model_note": "quant_model() as the reference shapes it "
+           "(train_nerv_all.py:620-641): the same quantisation plus TWO deepcopy(model) and a load_state_dict, which are host-side "
+           "Python and dominate", "quant_model_first_call_ms": first_ms, "huffman_ms": (t2 - t1) * 1e3, "bits_per_param": bits["bits_per_param"],
            "full_bits_per_param": bits["full_bits_per_param"], "total_bpp": bits["total_bits"] / pixels / N_FRAMES,
            "quantised_decode_frames_per_s": 1e3 * frames / e0.elapsed_time(e1),
            "psnr_quantised_vs_unquantised_db": sum(psnr) / len(psnr)}

@@ -24,7 +24,7 @@ EXPORTS = [
     "bnerv_pack_head_weight", "bnerv_head_conv3", "bnerv_nerv_block_fwd", "bnerv_head_conv1",
     "bnerv_ssim_stats", "bnerv_ssim_grad", "bnerv_ssim_scratch_floats",
     # post-training quantisation + Huffman statistics (ABI version 3)
-    "bnerv_ptq_plan_tensor", "bnerv_ptq_quant_tensor", "bnerv_ptq_dequant_tensor", "bnerv_histogram_u8",
+    "bnerv_ptq_plan_tensor", "bnerv_ptq_quant_tensor", "bnerv_ptq_quant_tensors", "bnerv_ptq_quant_tensors_scratch_bytes", "bnerv_ptq_dequant_tensor", "bnerv_histogram_u8",
     "bnerv_huffman_code_lengths",
     # ConvNeXt encoder forward
     "bnerv_convnext_stage_fwd", "bnerv_convnext_stage_work_floats", "bnerv_nhwc_to_nchw",
@@ -55,6 +55,13 @@ class PtqPlan(ctypes.Structure):
     _fields_ = [("n_cand", ctypes.c_int32), ("axis", ctypes.c_int32 * PTQ_MAX_CAND), ("groups", ctypes.c_int64 * PTQ_MAX_CAND),
                 ("table_offset", ctypes.c_int64 * PTQ_MAX_CAND), ("table_floats", ctypes.c_int64),
                 ("scratch_doubles", ctypes.c_int64)]
+
+
+class PtqJob(ctypes.Structure):
+    """struct bnerv_ptq_job"""
+    _fields_ = [("t", ctypes.c_void_p), ("shape", ctypes.c_int64 * (PTQ_MAX_CAND - 1)), ("ndim", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("quant", ctypes.c_void_p), ("new_t", ctypes.c_void_p), ("tables", ctypes.c_void_p),
+                ("tables_f16", ctypes.c_void_p), ("err", ctypes.c_void_p), ("best", ctypes.c_void_p)]
 
 
 class ConvNextBlock(ctypes.Structure):
@@ -105,6 +112,9 @@ def _load():
     lib.bnerv_nhwc_to_nchw.argtypes = [vp, i, i, i, i, vp, vp]
     lib.bnerv_ptq_plan_tensor.argtypes = [vp, i, ctypes.POINTER(PtqPlan)]
     lib.bnerv_ptq_quant_tensor.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp]
+    lib.bnerv_ptq_quant_tensors.argtypes = [vp, i, i, vp, ctypes.c_size_t, vp]
+    lib.bnerv_ptq_quant_tensors_scratch_bytes.argtypes = [vp, i]
+    lib.bnerv_ptq_quant_tensors_scratch_bytes.restype = ctypes.c_size_t
     lib.bnerv_ptq_dequant_tensor.argtypes = [vp, vp, i, i, vp, vp, i, vp, vp]
     lib.bnerv_histogram_u8.argtypes = [vp, ctypes.c_size_t, vp, vp]
     lib.bnerv_huffman_code_lengths.argtypes = [vp, i, vp]

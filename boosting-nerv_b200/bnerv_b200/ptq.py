@@ -28,46 +28,83 @@ def _plan(shape):
     return arr, plan
 
 
-class _Job:
-    """One launched quant_tensor: device buffers + the plan needed to slice the winning tables once `best` is known."""
+class _Jobs:
+    """quant_tensor over a LIST of tensors as one bnerv_ptq_quant_tensors call: five launches over a descriptor table, and six
+    flat device buffers (codes, reconstructions, f32 + f16 tables, errors, winners) that the per-tensor results are views of."""
 
-    def __init__(self, t, bits, want_new_t=True):
-        _need_cuda(t)
-        require_current_device(t.device)
-        if t.dtype != torch.float32:
-            raise TypeError(f"quant_tensor expects float32, got {t.dtype}")
+    def __init__(self, tensors, bits, want_new_t=True):
         if not 1 <= bits <= 8:
             raise ValueError(f"bits = {bits}: codes are uint8 (1..8)")
-        self.shape = tuple(t.shape)
-        t = t.contiguous()
-        arr, self.plan = _plan(self.shape)
-        dev = t.device
-        self.quant = torch.empty(self.shape, dtype=torch.uint8, device=dev)
-        self.new_t = torch.empty(self.shape, dtype=torch.float32, device=dev) if want_new_t else None
-        self.tables = torch.empty(self.plan.table_floats, dtype=torch.float32, device=dev)
-        self.err = torch.empty(_capi.PTQ_MAX_CAND, dtype=torch.float64, device=dev)
-        self.best = torch.empty(1, dtype=torch.int32, device=dev)
-        scratch = torch.empty(self.plan.scratch_doubles, dtype=torch.float64, device=dev)
-        check("bnerv_ptq_quant_tensor",
-              lib.bnerv_ptq_quant_tensor(ptr(t), arr, len(self.shape), bits, ptr(self.quant), ptr(self.new_t), ptr(self.tables),
-                                         ptr(self.err), ptr(self.best), ptr(scratch), _stream()))
+        _need_cuda(*tensors)
+        dev = tensors[0].device
+        require_current_device(dev)
+        self.shapes, self.plans, src = [], [], []
+        n_tot = tab_tot = 0
+        self.offs = []                                  # (element offset, table offset) per tensor
+        for t in tensors:
+            if t.dtype != torch.float32:
+                raise TypeError(f"quant_tensor expects float32, got {t.dtype}")
+            if t.device != dev:
+                raise ValueError("all tensors of one call must live on one device")
+            shape = tuple(t.shape)
+            _, plan = _plan(shape)
+            self.shapes.append(shape)
+            self.plans.append(plan)
+            src.append(t.contiguous())
+            self.offs.append((n_tot, tab_tot))
+            n_tot += t.numel()                          # back to back: the codes of a model are ONE contiguous byte string
+            tab_tot += plan.table_floats
+        n = len(tensors)
+        self.quant = torch.empty(n_tot, dtype=torch.uint8, device=dev)
+        self.new_t = torch.empty(n_tot, dtype=torch.float32, device=dev) if want_new_t else None
+        self.tables = torch.empty(tab_tot, dtype=torch.float32, device=dev)
+        self.tables16 = torch.empty(tab_tot, dtype=torch.float16, device=dev)
+        self.err = torch.empty(n * _capi.PTQ_MAX_CAND, dtype=torch.float64, device=dev)
+        self.best = torch.empty(n, dtype=torch.int32, device=dev)
+        jobs = (_capi.PtqJob * n)()
+        q0, nt0, tb0, th0, e0, b0 = (self.quant.data_ptr(), self.new_t.data_ptr() if want_new_t else 0, self.tables.data_ptr(),
+                                     self.tables16.data_ptr(), self.err.data_ptr(), self.best.data_ptr())
+        for i, (t, shape, (eo, to)) in enumerate(zip(src, self.shapes, self.offs)):
+            j = jobs[i]
+            j.t, j.ndim = t.data_ptr(), len(shape)
+            for d, v in enumerate(shape):
+                j.shape[d] = v
+            j.quant, j.new_t = q0 + eo, (nt0 + 4 * eo) if want_new_t else None
+            j.tables, j.tables_f16 = tb0 + 4 * to, th0 + 2 * to
+            j.err, j.best = e0 + 8 * _capi.PTQ_MAX_CAND * i, b0 + 4 * i
+        need = lib.bnerv_ptq_quant_tensors_scratch_bytes(jobs, n)
+        if need == 0:
+            check("bnerv_ptq_quant_tensors", lib.bnerv_ptq_quant_tensors(jobs, n, bits, None, 0, _stream()))   # reports the bad job
+        scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+        self._keep = src
+        check("bnerv_ptq_quant_tensors", lib.bnerv_ptq_quant_tensors(jobs, n, bits, ptr(scratch), need, _stream()))
 
-    def result(self, best):
-        """-> the reference's dict for candidate `best` (tables as views of the right keepdim shape and dtype)."""
-        p = self.plan
-        off, G, axis = p.table_offset[best], p.groups[best], p.axis[best]
-        tmin, scale = self.tables[off:off + G], self.tables[off + G:off + 2 * G]
-        if axis < 0:
-            tmin, scale = tmin.reshape(()), scale.reshape(())                       # 0-dim f32, like t.min()
-        else:
-            keep = tuple(1 if d == axis else n for d, n in enumerate(self.shape))
-            tmin, scale = tmin.reshape(keep).to(torch.float16), scale.reshape(keep).to(torch.float16)   # exact: already f16 values
-        return {"quant": self.quant, "min": tmin, "scale": scale}
+    def results(self):
+        """-> [(the reference's dict {'quant','min','scale'}, new_t or None)] - ONE read-back (the winning candidates)."""
+        out = []
+        for i, best in enumerate(self.best.tolist()):
+            shape, p, (eo, to) = self.shapes[i], self.plans[i], self.offs[i]
+            numel = 1
+            for v in shape:
+                numel *= v
+            off, G, axis = to + p.table_offset[best], p.groups[best], p.axis[best]
+            if axis < 0:                                # 0-dim f32, like t.min()
+                tmin, scale = self.tables[off:off + G].reshape(()), self.tables[off + G:off + 2 * G].reshape(())
+            else:                                       # keepdim f16 tables (hnerv_utils.py:113); the f16 copy is exact
+                keep = tuple(1 if d == axis else v for d, v in enumerate(shape))
+                tmin, scale = self.tables16[off:off + G].reshape(keep), self.tables16[off + G:off + 2 * G].reshape(keep)
+            q = {"quant": self.quant[eo:eo + numel].view(shape), "min": tmin, "scale": scale}
+            out.append((q, None if self.new_t is None else self.new_t[eo:eo + numel].view(shape)))
+        return out
 
 
 def quant_tensor(t, bits=8):
-    job = _Job(t, bits)
-    return job.result(int(job.best.item())), job.new_t
+    return _Jobs([t], bits).results()[0]
+
+
+def quant_tensors(tensors, bits=8):
+    """quant_tensor for every tensor of a list in one multi-tensor call -> [(quant dict, new_t)]."""
+    return _Jobs(list(tensors), bits).results() if len(tensors) else []
 
 
 def dequant_tensor(quant_t):
@@ -118,22 +155,14 @@ def load_quant_ckt(model, quant_ckt):
 
 def quant_state_dict(state_dict, bits):
     """quant_tensor over every non-encoder tensor of a state_dict (the loop of train_nerv_all.py:630-636), all launches
-    issued before the single read-back of the winning candidate indices.
+    in ONE multi-tensor call (five launches) and one read-back of the winning candidate indices.
     -> (quant_ckt {key: {'quant','min','scale'}}, {key: dequantised tensor} incl. the untouched encoder tensors)."""
-    jobs, cur = {}, {}
-    for k, v in state_dict.items():
-        if "encoder" in k:
-            cur[k] = v
-        else:
-            jobs[k] = _Job(v, bits)
-    if jobs:
-        best = torch.cat([j.best for j in jobs.values()]).tolist()
-        quant_ckt = {}
-        for (k, j), b in zip(jobs.items(), best):
-            quant_ckt[k] = j.result(b)
-            cur[k] = j.new_t
-    else:
-        quant_ckt = {}
+    keys = [k for k in state_dict if "encoder" not in k]
+    cur = {k: v for k, v in state_dict.items() if "encoder" in k}
+    quant_ckt = {}
+    for k, (q, new_t) in zip(keys, quant_tensors([state_dict[k] for k in keys], bits)):
+        quant_ckt[k] = q
+        cur[k] = new_t
     return quant_ckt, {k: cur[k] for k in state_dict}
 
 
@@ -150,6 +179,26 @@ def quant_model(model, args):
     return model_list, quant_ckt
 
 
+def _flat_codes(qs):
+    """If (a subset of) the uint8 code tensors tile one storage back to back - the layout quant_tensors produces - return
+    (address, bytes, membership test) of that byte string, else None."""
+    groups = {}
+    for q in qs:
+        if q.is_cuda and q.dtype == torch.uint8 and q.is_contiguous():
+            groups.setdefault(q.untyped_storage().data_ptr(), []).append(q)
+    best = max(groups.values(), key=len, default=[])
+    if len(best) < 2:
+        return None
+    best = sorted(best, key=lambda q: q.data_ptr())
+    pos = best[0].data_ptr()
+    for q in best:
+        if q.data_ptr() != pos:
+            return None
+        pos += q.numel()
+    ids = {id(q) for q in best}
+    return ctypes.c_void_p(best[0].data_ptr()), pos - best[0].data_ptr(), (lambda q: id(q) in ids)
+
+
 def code_histogram(quant_ckt, quant_embed=None):
     """-> (u64[256] counts of all codes on the device, number of min + scale entries stored beside them)."""
     layers = ([quant_embed] if quant_embed is not None else []) + list(quant_ckt.values())
@@ -159,6 +208,13 @@ def code_histogram(quant_ckt, quant_embed=None):
     require_current_device(dev)
     counts = torch.zeros(256, dtype=torch.int64, device=dev)
     tmin_scale_len = 0
+    flat = _flat_codes([l["quant"] for l in layers])
+    if flat is not None:                           # codes produced by one quant_tensors call: one launch over the whole string
+        check("bnerv_histogram_u8", lib.bnerv_histogram_u8(flat[0], flat[1], ptr(counts), _stream()))
+        for layer in layers:
+            if flat[2](layer["quant"]):
+                tmin_scale_len += layer["min"].nelement() + layer["scale"].nelement()
+        layers = [l for l in layers if not flat[2](l["quant"])]
     for layer in layers:
         q = layer["quant"]
         _need_cuda(q)

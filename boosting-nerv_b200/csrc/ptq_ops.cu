@@ -13,6 +13,7 @@
 // into FMAs, so codes, tables and reconstructions are bit-identical to the torch CPU result.  All kernels are one-pass
 // HBM-bound sweeps; the whole job of a 15 M parameter model is a few hundred launches of a few microseconds.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 #include "common.cuh"
 
@@ -43,31 +44,86 @@ static int splits_for(long long G, long long A) {
 
 __device__ __forceinline__ float round_f16(float x) { return __half2float(__float2half_rn(x)); }
 
-// ---- min / max over the reduced axis --------------------------------------------------------------------------
-__global__ void ptq_minmax_thread_kernel(const float* __restrict__ t, PtqView v, int S, float2* __restrict__ partial) {
-    const unsigned G = v.outer * v.inner;
-    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
-    const unsigned sp = blockIdx.y;
-    const unsigned a0 = static_cast<unsigned>(static_cast<unsigned long long>(v.A) * sp / S);
-    const unsigned a1 = static_cast<unsigned>(static_cast<unsigned long long>(v.A) * (sp + 1) / S);
-    const unsigned o = g / v.inner, i = g - o * v.inner;
-    const float* p = t + (static_cast<size_t>(o) * v.A) * v.inner + i;
-    float mn = INFINITY, mx = -INFINITY;
-    for (unsigned a = a0; a < a1; ++a) {
-        const float x = __ldg(p + static_cast<size_t>(a) * v.inner);
-        mn = fminf(mn, x);
-        mx = fmaxf(mx, x);
+// ---- multi-tensor work tables ----------------------------------------------------------------------------------
+// One PtqJobDev per tensor, one PtqSeg per (tensor, candidate).  Every pass is ONE launch over all segments: a block finds its
+// segment by binary search over the segments' first-block prefix, then does exactly what the single-tensor grid did (same
+// splits of the reduced axis, same 592-block strided error sums), so results do not depend on how many tensors share a launch.
+struct PtqJobDev {
+    const float* t;
+    uint8_t* quant;
+    float* new_t;
+    float* tables;
+    __half* tables_f16;
+    double* err;
+    int* best;
+    unsigned n;
+    int n_cand;
+    int err_blocks;
+    int first_seg;
+    unsigned apply_first;       // first block of this job in the apply pass
+    PtqView view[BNERV_PTQ_MAX_CAND];
+    long long table_off[BNERV_PTQ_MAX_CAND];
+};
+
+struct PtqSeg {
+    int job, cand;
+    int S;                      // splits of the reduced axis in the min/max pass
+    int block_mode;             // 1: one block per (group, split); 0: one thread per group
+    unsigned G;
+    unsigned mm_first, table_first, err_first;     // first block of this segment in the three passes
+    long long mm_off;           // float2 offset of its [G][S] min/max partials
+    long long errp_off;         // double offset of its err_blocks partial sums
+};
+
+struct PtqTables {
+    const PtqJobDev* jobs;
+    const PtqSeg* segs;
+    int n_jobs, n_segs;
+    float2* mm;
+    double* errp;
+    float levels;
+};
+
+template <unsigned PtqSeg::*FIRST>
+__device__ __forceinline__ int ptq_find_seg(const PtqTables& T, unsigned blk) {
+    int lo = 0, hi = T.n_segs - 1;
+    while (lo < hi) {           // last segment whose first block is <= blk
+        const int mid = (lo + hi + 1) >> 1;
+        if (T.segs[mid].*FIRST <= blk) lo = mid; else hi = mid - 1;
     }
-    partial[static_cast<size_t>(g) * S + sp] = make_float2(mn, mx);
+    return lo;
 }
 
-__global__ void ptq_minmax_block_kernel(const float* __restrict__ t, PtqView v, int S, float2* __restrict__ partial) {
-    const unsigned g = blockIdx.x, sp = blockIdx.y;
+// ---- pass 1: min / max over the reduced axis ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ptq_minmax_kernel(PtqTables T) {
+    const PtqSeg sg = T.segs[ptq_find_seg<&PtqSeg::mm_first>(T, blockIdx.x)];
+    const PtqJobDev& jb = T.jobs[sg.job];
+    const PtqView v = jb.view[sg.cand];
+    const unsigned local = blockIdx.x - sg.mm_first;
+    float2* partial = T.mm + sg.mm_off;
+    const int S = sg.S;
+    if (!sg.block_mode) {
+        const unsigned nbx = (sg.G + 255u) / 256u;
+        const unsigned g = (local % nbx) * 256u + threadIdx.x, sp = local / nbx;
+        if (g >= sg.G) return;
+        const unsigned a0 = static_cast<unsigned>(static_cast<unsigned long long>(v.A) * sp / S);
+        const unsigned a1 = static_cast<unsigned>(static_cast<unsigned long long>(v.A) * (sp + 1) / S);
+        const unsigned o = g / v.inner, i = g - o * v.inner;
+        const float* p = jb.t + (static_cast<size_t>(o) * v.A) * v.inner + i;
+        float mn = INFINITY, mx = -INFINITY;
+        for (unsigned a = a0; a < a1; ++a) {
+            const float x = __ldg(p + static_cast<size_t>(a) * v.inner);
+            mn = fminf(mn, x);
+            mx = fmaxf(mx, x);
+        }
+        partial[static_cast<size_t>(g) * S + sp] = make_float2(mn, mx);
+        return;
+    }
+    const unsigned g = local % sg.G, sp = local / sg.G;
     const unsigned a0 = static_cast<unsigned>(static_cast<unsigned long long>(v.A) * sp / S);
     const unsigned a1 = static_cast<unsigned>(static_cast<unsigned long long>(v.A) * (sp + 1) / S);
     const unsigned o = g / v.inner, i = g - o * v.inner;
-    const float* p = t + (static_cast<size_t>(o) * v.A) * v.inner + i;
+    const float* p = jb.t + (static_cast<size_t>(o) * v.A) * v.inner + i;
     float mn = INFINITY, mx = -INFINITY;
     for (unsigned a = a0 + threadIdx.x; a < a1; a += blockDim.x) {
         const float x = __ldg(p + static_cast<size_t>(a) * v.inner);
@@ -87,21 +143,29 @@ __global__ void ptq_minmax_block_kernel(const float* __restrict__ t, PtqView v, 
     }
 }
 
-// scale = (max - min) / (2^bits - 1) in f32 (hnerv_utils.py:106,111); per-axis tables are then stored as f16 (:113)
-__global__ void ptq_table_kernel(const float2* __restrict__ partial, unsigned G, int S, float levels, int as_f16,
-                                 float* __restrict__ table) {
-    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
+// ---- pass 2: scale = (max - min) / (2^bits - 1) in f32 (hnerv_utils.py:106,111); per-axis tables are stored as f16 (:113)
+__global__ void __launch_bounds__(256) ptq_table_kernel(PtqTables T) {
+    const PtqSeg sg = T.segs[ptq_find_seg<&PtqSeg::table_first>(T, blockIdx.x)];
+    const PtqJobDev& jb = T.jobs[sg.job];
+    const unsigned g = (blockIdx.x - sg.table_first) * 256u + threadIdx.x;
+    if (g >= sg.G) return;
+    const float2* partial = T.mm + sg.mm_off;
     float mn = INFINITY, mx = -INFINITY;
-    for (int s = 0; s < S; ++s) {
-        const float2 p = partial[static_cast<size_t>(g) * S + s];
+    for (int s = 0; s < sg.S; ++s) {
+        const float2 p = partial[static_cast<size_t>(g) * sg.S + s];
         mn = fminf(mn, p.x);
         mx = fmaxf(mx, p.y);
     }
-    float scale = __fdiv_rn(__fsub_rn(mx, mn), levels);
-    if (as_f16) { mn = round_f16(mn); scale = round_f16(scale); }
+    float scale = __fdiv_rn(__fsub_rn(mx, mn), T.levels);
+    if (sg.cand > 0) { mn = round_f16(mn); scale = round_f16(scale); }
+    float* table = jb.tables + jb.table_off[sg.cand];
     table[g] = mn;
-    table[G + g] = scale;
+    table[sg.G + g] = scale;
+    if (jb.tables_f16) {
+        __half* th = jb.tables_f16 + jb.table_off[sg.cand];
+        th[g] = __float2half_rn(mn);
+        th[sg.G + g] = __float2half_rn(scale);
+    }
 }
 
 // quant = clamp(round((t - min) / scale), 0, levels); new_t = min + scale * quant   (hnerv_utils.py:120-121)
@@ -117,17 +181,21 @@ __device__ __forceinline__ unsigned ptq_group_of(unsigned idx, const PtqView& v)
     return o * v.inner + rem % v.inner;
 }
 
-// mean |t - new_t| of one candidate, stage 1: fixed grid, fixed per-thread order, one f64 partial per block
-__global__ void __launch_bounds__(256) ptq_error_kernel(const float* __restrict__ t, unsigned n, PtqView v,
-                                                        const float* __restrict__ table, float levels,
-                                                        double* __restrict__ partial) {
-    const unsigned G = v.outer * v.inner;
+// ---- pass 3: mean |t - new_t| of every candidate, stage 1: err_blocks blocks per segment, fixed per-thread order, one f64
+// partial per block
+__global__ void __launch_bounds__(256) ptq_error_kernel(PtqTables T) {
+    const PtqSeg sg = T.segs[ptq_find_seg<&PtqSeg::err_first>(T, blockIdx.x)];
+    const PtqJobDev& jb = T.jobs[sg.job];
+    const PtqView v = jb.view[sg.cand];
+    const unsigned lb = blockIdx.x - sg.err_first, nb = jb.err_blocks;
+    const float* table = jb.tables + jb.table_off[sg.cand];
+    const float* t = jb.t;
     double acc = 0.0;
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    for (unsigned idx = lb * 256u + threadIdx.x; idx < jb.n; idx += nb * 256u) {
         const unsigned g = ptq_group_of(idx, v);
         const float x = __ldg(t + idx);
         float q;
-        const float nt = ptq_reconstruct(x, __ldg(table + g), __ldg(table + G + g), levels, q);
+        const float nt = ptq_reconstruct(x, __ldg(table + g), __ldg(table + sg.G + g), T.levels, q);
         acc += static_cast<double>(fabsf(__fsub_rn(x, nt)));
     }
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
@@ -136,45 +204,59 @@ __global__ void __launch_bounds__(256) ptq_error_kernel(const float* __restrict_
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) acc += sw[w];
-        partial[blockIdx.x] = acc;
+        T.errp[sg.errp_off + lb] = acc;
     }
 }
 
-__global__ void ptq_error_final_kernel(const double* __restrict__ partial, int nb, unsigned n, double* __restrict__ err_out) {
+// ---- pass 4: one block per tensor: sum the partials of each candidate, best = first candidate with the smallest error
+// (min(err_t_list) + list.index, hnerv_utils.py:127-128)
+__global__ void __launch_bounds__(256) ptq_select_kernel(PtqTables T) {
+    const PtqJobDev& jb = T.jobs[blockIdx.x];
     __shared__ double s[256];
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < nb; i += 256) acc += partial[i];
-    s[threadIdx.x] = acc;
-    __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
-        if (static_cast<int>(threadIdx.x) < d) s[threadIdx.x] += s[threadIdx.x + d];
+    __shared__ double errs[BNERV_PTQ_MAX_CAND];
+    for (int c = 0; c < jb.n_cand; ++c) {
+        const double* partial = T.errp + T.segs[jb.first_seg + c].errp_off;
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < jb.err_blocks; i += 256) acc += partial[i];
+        s[threadIdx.x] = acc;
+        __syncthreads();
+        for (int d = 128; d > 0; d >>= 1) {
+            if (static_cast<int>(threadIdx.x) < d) s[threadIdx.x] += s[threadIdx.x + d];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            errs[c] = s[0] / static_cast<double>(jb.n);
+            jb.err[c] = errs[c];
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *err_out = s[0] / static_cast<double>(n);
+    if (threadIdx.x == 0) {
+        int best = 0;
+        for (int c = 1; c < jb.n_cand; ++c)
+            if (errs[c] < errs[best]) best = c;
+        *jb.best = best;
+    }
 }
 
-// best = first candidate with the smallest error (min(err_t_list) + list.index, hnerv_utils.py:127-128), then the
-// codes and the reconstruction of that candidate
-__global__ void __launch_bounds__(256) ptq_apply_kernel(const float* __restrict__ t, unsigned n, PtqCandSet cs,
-                                                        const float* __restrict__ tables, const double* __restrict__ err,
-                                                        float levels, uint8_t* __restrict__ quant, float* __restrict__ new_t,
-                                                        int* __restrict__ best_out) {
-    int best = 0;
-    for (int c = 1; c < cs.n; ++c)
-        if (err[c] < err[best]) best = c;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *best_out = best;
-    PtqView v = cs.view[0];
-    long long off = cs.table_off[0];
-    for (int c = 1; c < cs.n; ++c)
-        if (c == best) { v = cs.view[c]; off = cs.table_off[c]; }
+// ---- pass 5: the codes and the reconstruction of the winning candidate
+__global__ void __launch_bounds__(256) ptq_apply_kernel(PtqTables T) {
+    int lo = 0, hi = T.n_jobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (T.jobs[mid].apply_first <= blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const PtqJobDev& jb = T.jobs[lo];
+    const int best = *jb.best;
+    const PtqView v = jb.view[best];
     const unsigned G = v.outer * v.inner;
-    const float* table = tables + off;
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const float* table = jb.tables + jb.table_off[best];
+    const unsigned lb = blockIdx.x - jb.apply_first, nb = jb.err_blocks;
+    for (unsigned idx = lb * 256u + threadIdx.x; idx < jb.n; idx += nb * 256u) {
         const unsigned g = ptq_group_of(idx, v);
         float q;
-        const float nt = ptq_reconstruct(__ldg(t + idx), __ldg(table + g), __ldg(table + G + g), levels, q);
-        quant[idx] = static_cast<uint8_t>(q);
-        if (new_t) new_t[idx] = nt;
+        const float nt = ptq_reconstruct(__ldg(jb.t + idx), __ldg(table + g), __ldg(table + G + g), T.levels, q);
+        jb.quant[idx] = static_cast<uint8_t>(q);
+        if (jb.new_t) jb.new_t[idx] = nt;
     }
 }
 
@@ -248,7 +330,8 @@ static int ptq_make_plan(const int64_t* shape, int ndim, bnerv_ptq_plan* plan, P
     }
     p.n_cand = nc;
     p.table_floats = off;
-    p.scratch_doubles = PTQ_ERR_BLOCKS + gmax + PTQ_TARGET_THREADS + PTQ_ERR_BLOCKS;
+    // one job's multi-tensor scratch: job + segment tables, [G][S] min/max pairs and 592 partial sums per candidate (+ alignment)
+    p.scratch_doubles = 512 + BNERV_PTQ_MAX_CAND * (64 + PTQ_ERR_BLOCKS + gmax + PTQ_TARGET_THREADS + 32);
     c.n = nc;
     for (int k = 0; k < nc; ++k) { c.table_off[k] = p.table_offset[k]; c.groups[k] = p.groups[k]; }
     if (plan) *plan = p;
@@ -266,41 +349,133 @@ extern "C" int bnerv_ptq_plan_tensor(const int64_t* shape, int ndim, bnerv_ptq_p
     return ptq_make_plan(shape, ndim, plan, nullptr, nullptr);
 }
 
+namespace bnerv {
+
+// splits of the reduced axis for the min/max pass: enough threads to fill the GPU when a tensor is alone, but never fewer
+// than ~32 elements per thread (min/max are exact, so the split changes nothing but the scratch size)
+static int splits_multi(long long G, long long A) {
+    const long long s = splits_for(G, A);
+    return static_cast<int>(std::max<long long>(1, std::min<long long>(s, A / 32)));
+}
+
+struct PtqHostLayout {
+    std::vector<PtqJobDev> jobs;
+    std::vector<PtqSeg> segs;
+    unsigned mm_blocks = 0, table_blocks = 0, err_blocks = 0, apply_blocks = 0;
+    long long mm_floats2 = 0, errp_doubles = 0;
+    size_t off_jobs = 0, off_segs = 0, off_mm = 0, off_errp = 0, total = 0;
+};
+
+static int ptq_layout(const bnerv_ptq_job* jobs, int n_jobs, PtqHostLayout& L) {
+    if (!jobs || n_jobs <= 0) return set_error(BNERV_E_BADARG, "ptq_quant_tensors: no jobs");
+    L.jobs.resize(n_jobs);
+    for (int j = 0; j < n_jobs; ++j) {
+        const bnerv_ptq_job& in = jobs[j];
+        bnerv_ptq_plan plan;
+        PtqCandSet cs;
+        long long n = 0;
+        if (int rc = ptq_make_plan(in.shape, in.ndim, &plan, &cs, &n)) return rc;
+        PtqJobDev& d = L.jobs[j];
+        d.t = in.t; d.quant = in.quant; d.new_t = in.new_t; d.tables = in.tables;
+        d.tables_f16 = static_cast<__half*>(in.tables_f16); d.err = in.err; d.best = in.best;
+        d.n = static_cast<unsigned>(n);
+        d.n_cand = cs.n;
+        d.err_blocks = static_cast<int>(std::min<long long>(PTQ_ERR_BLOCKS, (n + 255) / 256));
+        d.first_seg = static_cast<int>(L.segs.size());
+        d.apply_first = L.apply_blocks;
+        L.apply_blocks += d.err_blocks;
+        for (int c = 0; c < cs.n; ++c) {
+            d.view[c] = cs.view[c];
+            d.table_off[c] = cs.table_off[c];
+            PtqSeg sg{};
+            sg.job = j; sg.cand = c;
+            sg.G = static_cast<unsigned>(cs.groups[c]);
+            sg.S = splits_multi(cs.groups[c], cs.view[c].A);
+            sg.block_mode = cs.groups[c] < PTQ_BLOCK_MODE_BELOW ? 1 : 0;
+            sg.mm_first = L.mm_blocks; sg.table_first = L.table_blocks; sg.err_first = L.err_blocks;
+            sg.mm_off = L.mm_floats2; sg.errp_off = L.errp_doubles;
+            const long long nb_mm = sg.block_mode ? 1LL * sg.G * sg.S : 1LL * ((sg.G + 255) / 256) * sg.S;
+            if (L.mm_blocks + nb_mm > 0x7fffffffLL) return set_error(BNERV_E_UNSUPPORTED, "ptq_quant_tensors: too many blocks");
+            L.mm_blocks += static_cast<unsigned>(nb_mm);
+            L.table_blocks += (sg.G + 255) / 256;
+            L.err_blocks += d.err_blocks;
+            L.mm_floats2 += 1LL * sg.G * sg.S;
+            L.errp_doubles += d.err_blocks;
+            L.segs.push_back(sg);
+        }
+    }
+    auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+    L.off_jobs = 0;
+    L.off_segs = up(L.jobs.size() * sizeof(PtqJobDev));
+    L.off_mm   = L.off_segs + up(L.segs.size() * sizeof(PtqSeg));
+    L.off_errp = L.off_mm + up(static_cast<size_t>(L.mm_floats2) * sizeof(float2));
+    L.total    = L.off_errp + up(static_cast<size_t>(L.errp_doubles) * sizeof(double));
+    return 0;
+}
+
+static int ptq_run(const bnerv_ptq_job* jobs, int n_jobs, int bits, void* scratch, size_t scratch_bytes, void* stream) {
+    if (bits < 1 || bits > 8) return set_error(BNERV_E_UNSUPPORTED, "ptq_quant_tensors: %d bits (codes are uint8: 1..8)", bits);
+    if (!scratch) return set_error(BNERV_E_BADARG, "ptq_quant_tensors: null scratch");
+    if (reinterpret_cast<uintptr_t>(scratch) & 255) return set_error(BNERV_E_BADARG, "ptq_quant_tensors: scratch must be 256-byte aligned");
+    for (int j = 0; j < n_jobs; ++j)
+        if (!jobs[j].t || !jobs[j].quant || !jobs[j].tables || !jobs[j].err || !jobs[j].best)
+            return set_error(BNERV_E_BADARG, "ptq_quant_tensors: null pointer in job %d", j);
+    PtqHostLayout L;
+    if (int rc = ptq_layout(jobs, n_jobs, L)) return rc;
+    if (scratch_bytes < L.total) return set_error(BNERV_E_BADARG, "ptq_quant_tensors: scratch of %zu bytes, %zu needed", scratch_bytes, L.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* base = static_cast<uint8_t*>(scratch);
+    // one upload of both tables (pageable source: the call returns once it has been staged)
+    std::vector<uint8_t> stage(L.off_mm, 0);
+    memcpy(stage.data() + L.off_jobs, L.jobs.data(), L.jobs.size() * sizeof(PtqJobDev));
+    memcpy(stage.data() + L.off_segs, L.segs.data(), L.segs.size() * sizeof(PtqSeg));
+    cudaError_t e = cudaMemcpyAsync(base, stage.data(), stage.size(), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return set_error(static_cast<int>(e), "ptq_quant_tensors: table upload: %s", cudaGetErrorString(e));
+    PtqTables T;
+    T.jobs = reinterpret_cast<const PtqJobDev*>(base + L.off_jobs);
+    T.segs = reinterpret_cast<const PtqSeg*>(base + L.off_segs);
+    T.n_jobs = n_jobs; T.n_segs = static_cast<int>(L.segs.size());
+    T.mm = reinterpret_cast<float2*>(base + L.off_mm);
+    T.errp = reinterpret_cast<double*>(base + L.off_errp);
+    T.levels = static_cast<float>((1 << bits) - 1);
+    ptq_minmax_kernel<<<L.mm_blocks, 256, 0, st>>>(T);
+    if (int rc = check_launch("ptq_minmax_kernel")) return rc;
+    ptq_table_kernel<<<L.table_blocks, 256, 0, st>>>(T);
+    if (int rc = check_launch("ptq_table_kernel")) return rc;
+    ptq_error_kernel<<<L.err_blocks, 256, 0, st>>>(T);
+    if (int rc = check_launch("ptq_error_kernel")) return rc;
+    ptq_select_kernel<<<n_jobs, 256, 0, st>>>(T);
+    if (int rc = check_launch("ptq_select_kernel")) return rc;
+    ptq_apply_kernel<<<L.apply_blocks, 256, 0, st>>>(T);
+    return check_launch("ptq_apply_kernel");
+}
+
+}  // namespace bnerv
+
+extern "C" size_t bnerv_ptq_quant_tensors_scratch_bytes(const bnerv_ptq_job* jobs, int n_jobs) {
+    PtqHostLayout L;
+    if (ptq_layout(jobs, n_jobs, L)) return 0;
+    return L.total;
+}
+
+extern "C" int bnerv_ptq_quant_tensors(const bnerv_ptq_job* jobs, int n_jobs, int bits, void* scratch, size_t scratch_bytes,
+                                       void* stream) {
+    if (!jobs || n_jobs <= 0) return set_error(BNERV_E_BADARG, "ptq_quant_tensors: no jobs");
+    return ptq_run(jobs, n_jobs, bits, scratch, scratch_bytes, stream);
+}
+
 extern "C" int bnerv_ptq_quant_tensor(const float* t, const int64_t* shape, int ndim, int bits, uint8_t* quant, float* new_t,
                                       float* tables, double* err, int32_t* best, double* scratch, void* stream) {
     if (!t || !quant || !tables || !err || !best || !scratch) return set_error(BNERV_E_BADARG, "ptq_quant_tensor: null pointer");
-    if (bits < 1 || bits > 8) return set_error(BNERV_E_UNSUPPORTED, "ptq_quant_tensor: %d bits (codes are uint8: 1..8)", bits);
+    if (!shape || ndim < 0 || ndim > BNERV_PTQ_MAX_CAND - 1) return set_error(BNERV_E_UNSUPPORTED, "ptq: %d dimensions (at most %d)", ndim, BNERV_PTQ_MAX_CAND - 1);
+    bnerv_ptq_job job{};
+    job.t = t; job.ndim = ndim;
+    for (int d = 0; d < ndim; ++d) job.shape[d] = shape[d];
+    job.quant = quant; job.new_t = new_t; job.tables = tables; job.tables_f16 = nullptr; job.err = err; job.best = best;
     bnerv_ptq_plan plan;
-    PtqCandSet cs;
-    long long n = 0;
-    if (int rc = ptq_make_plan(shape, ndim, &plan, &cs, &n)) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const float levels = static_cast<float>((1 << bits) - 1);
-    double* err_partial = scratch;
-    float2* mm_partial = reinterpret_cast<float2*>(scratch + PTQ_ERR_BLOCKS);
-    const int err_blocks = static_cast<int>(std::min<long long>(PTQ_ERR_BLOCKS, (n + 255) / 256));
-    for (int c = 0; c < cs.n; ++c) {
-        const PtqView v = cs.view[c];
-        const long long G = cs.groups[c];
-        const int S = splits_for(G, v.A);
-        if (G >= PTQ_BLOCK_MODE_BELOW) {
-            dim3 grid(static_cast<unsigned>((G + 255) / 256), S);
-            ptq_minmax_thread_kernel<<<grid, 256, 0, st>>>(t, v, S, mm_partial);
-        } else {
-            dim3 grid(static_cast<unsigned>(G), S);
-            ptq_minmax_block_kernel<<<grid, 256, 0, st>>>(t, v, S, mm_partial);
-        }
-        if (int rc = check_launch("ptq_minmax_kernel")) return rc;
-        ptq_table_kernel<<<static_cast<unsigned>((G + 255) / 256), 256, 0, st>>>(mm_partial, static_cast<unsigned>(G), S, levels, c > 0,
-                                                                                  tables + cs.table_off[c]);
-        if (int rc = check_launch("ptq_table_kernel")) return rc;
-        ptq_error_kernel<<<err_blocks, 256, 0, st>>>(t, static_cast<unsigned>(n), v, tables + cs.table_off[c], levels, err_partial);
-        if (int rc = check_launch("ptq_error_kernel")) return rc;
-        ptq_error_final_kernel<<<1, 256, 0, st>>>(err_partial, err_blocks, static_cast<unsigned>(n), err + c);
-        if (int rc = check_launch("ptq_error_final_kernel")) return rc;
-    }
-    ptq_apply_kernel<<<err_blocks, 256, 0, st>>>(t, static_cast<unsigned>(n), cs, tables, err, levels, quant, new_t, best);
-    return check_launch("ptq_apply_kernel");
+    if (int rc = ptq_make_plan(shape, ndim, &plan, nullptr, nullptr)) return rc;
+    // the single-tensor entry point: `scratch` (plan.scratch_doubles doubles) is the multi-tensor scratch of one job
+    return ptq_run(&job, 1, bits, scratch, static_cast<size_t>(plan.scratch_doubles) * sizeof(double), stream);
 }
 
 extern "C" int bnerv_ptq_dequant_tensor(const uint8_t* quant, const int64_t* shape, int ndim, int axis, const void* tmin,

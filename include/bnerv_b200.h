@@ -353,6 +353,27 @@ typedef struct bnerv_ptq_plan {
 int bnerv_ptq_plan_tensor(const int64_t* shape, int ndim, bnerv_ptq_plan* plan);
 int bnerv_ptq_quant_tensor(const float* t, const int64_t* shape, int ndim, int bits, uint8_t* quant, float* new_t,
                            float* tables, double* err, int32_t* best, double* scratch, void* stream);
+/* Multi-tensor form: ALL tensors of a model in five launches (min/max, tables, candidate errors, selection, codes) over a
+ * descriptor table instead of ~13 launches per tensor - the loop of train_nerv_all.py:630-636 as one call.  Per tensor the
+ * arithmetic, the partition of the error sums and therefore every output bit are those of bnerv_ptq_quant_tensor (which is this
+ * call with one job).  Pointers are device buffers laid out as described above; `tables_f16` (optional) receives the same
+ * tables as f16 values - exact for the per-axis candidates, whose entries are f16 values already - so the caller can hand out
+ * the stored form without a conversion launch per tensor.  `scratch`: 256-byte aligned device buffer of
+ * bnerv_ptq_quant_tensors_scratch_bytes(jobs, n_jobs) bytes (host-only helper, 0 on a bad job list). */
+typedef struct bnerv_ptq_job {
+    const float* t;
+    int64_t shape[BNERV_PTQ_MAX_CAND - 1];
+    int32_t ndim;
+    int32_t reserved;
+    uint8_t* quant;
+    float* new_t;          /* may be NULL */
+    float* tables;         /* f32 [plan.table_floats] */
+    void* tables_f16;      /* f16 [plan.table_floats] or NULL */
+    double* err;           /* f64 [BNERV_PTQ_MAX_CAND] */
+    int32_t* best;         /* i32 [1] */
+} bnerv_ptq_job;
+size_t bnerv_ptq_quant_tensors_scratch_bytes(const bnerv_ptq_job* jobs, int n_jobs);
+int bnerv_ptq_quant_tensors(const bnerv_ptq_job* jobs, int n_jobs, int bits, void* scratch, size_t scratch_bytes, void* stream);
 /* Decode side of the same format: out = min + scale * quant in f32 from the stored u8 codes and the winning candidate's
  * tables (axis = -1: one f32 pair, tables_f16 = 0; axis >= 0: f16 keepdim tables over that axis, tables_f16 = 1) -
  * bit-identical to the `new_t` bnerv_ptq_quant_tensor produced, i.e. to what quant_model loads into the quantised model

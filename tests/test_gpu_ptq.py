@@ -66,6 +66,27 @@ def test_quant_tensor_matches_oracle_at_model_sizes(shape, bits, kind):
     assert torch.equal(ptq.reconstruct_tensor(q), new_t)
 
 
+def test_quant_tensors_multi_call_is_bitwise_the_single_tensor_call():
+    """One bnerv_ptq_quant_tensors call over a model's worth of mixed shapes (five launches in total) returns, tensor by
+    tensor, exactly what the per-tensor call returns: codes, tables (dtype, keepdim shape), reconstruction."""
+    from bnerv_b200 import _capi, ptq
+    g = torch.Generator().manual_seed(11)
+    shapes = [(448, 135, 3, 3), (1746,), (3, 112, 3, 3), (6120, 256), (7,), (2, 1, 1, 3), (600, 16, 9, 16), (51, 60), (2,), (64, 52, 1, 1)]
+    ts = [(torch.randn(s, generator=g) * 0.05 * (1 + i)).cuda() for i, s in enumerate(shapes)]
+    ts.append(ts[3].t())                                            # non-contiguous input
+    n0 = _capi.launch_count()
+    multi = ptq.quant_tensors(ts, 8)
+    assert _capi.launch_count() - n0 == 5
+    for t, (q, new_t) in zip(ts, multi):
+        q1, new_1 = ptq.quant_tensor(t, 8)
+        _same(q, new_t, {k: v.cpu() for k, v in q1.items()}, new_1.cpu())
+        want_q, want_new = po.quant_tensor(t.cpu(), 8)
+        _same(q, new_t, want_q, want_new)
+    assert ptq.quant_tensors([], 8) == []
+    with pytest.raises(TypeError):
+        ptq.quant_tensors([ts[0], ts[1].double()], 8)
+
+
 def test_constant_tensor_is_reconstructed_exactly():
     """max == min makes the reference divide 0 by 0 (NaN codes, NaN weights); here the clamp absorbs the NaN: code 0 and
     min + 0 * 0 = the constant.  Defined behaviour where the reference has none - not a parity case."""
