@@ -183,6 +183,7 @@ class DecoderEngine:
         self._ws = {}          # workspaces per (B, h, w)
         self._sft = {}         # SftTable per B
         self._sft_key = None
+        self._xy, self._xy_key = None, None     # E-NeRV: frame-independent half of the stem
         env = os.environ.get("BNERV_PRECISE_BLOCKS")
         if env:
             self.set_precise(env)
@@ -301,10 +302,38 @@ class DecoderEngine:
             t_embed = self._mlp(m.stem_t, v)
             img, outs = self.run_cascade(x, t_embed, keep)
             return img, outs, None
-        (t,) = inputs                           # ENeRV_Boost.forward (model_enerv.py:281-313); transformer stem stays in torch
-        emb, t_manip = m._stem(t)
+        (t,) = inputs                           # ENeRV_Boost.forward (model_enerv.py:281-313)
+        emb, t_manip = self._enerv_stem(t)
         img, outs = self.run_cascade(emb.contiguous(), t_manip.flatten(1), keep)
         return img, outs, t_manip
+
+    def _enerv_stem(self, t):
+        """ENeRV_Boost's stem (model_enerv.py:281-303) for the decode path.  Same values as model._stem(t), arranged for a
+        per-frame decode: (i) the two time MLPs run on the f32 bnerv_linear_act kernel; (ii) the coordinate branch
+        trans1(stem_xy(pe_xy(grid))) does not depend on the frame, so it is computed once per weight version and captured
+        graphs hold it as a constant (about half of the stem's ~65 small torch kernels per frame); (iii) the transformer and
+        the 1x1 `toconv` stay torch modules but with cuDNN's TF32 convs switched off - the reference arithmetic is f32, and
+        `t_manip` feeds every SFT layer of the cascade."""
+        m = self.model
+        b = t.size(0)
+        tt = t[:, None].float()
+        t_emb = self._mlp(m.stem_t, m.pe_t(tt).flatten(1).float())
+        t_manip = self._mlp(m.t_branch, m.pe_t_manipulate(tt).flatten(1).float())
+        tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            key = (self.weights_key(), tuple(_tensor_key(p) for p in m.trans1.parameters()), t.device)
+            if self._xy_key != key:
+                with torch.no_grad():
+                    xy = m._xy_grid(t.device)
+                    xy_emb = torch.cat([m.pe_xy(xy[0][:, None]), m.pe_xy(xy[1][:, None])], dim=1)
+                    self._xy = m.trans1(m.stem_xy(xy_emb).view(1, m.fc_h * m.fc_w, -1)).contiguous()
+                self._xy_key = key
+            emb = m.trans2(self._xy.expand(b, -1, -1) * t_emb[:, None, :])
+            emb = m.toconv(emb.reshape(b, m.fc_h, m.fc_w, emb.shape[-1]).permute(0, 3, 1, 2))
+        finally:
+            torch.backends.cudnn.allow_tf32 = tf32
+        return emb, t_manip.view(b, -1, 1, 1)
 
     def decode(self, inputs, keep=False, check_weights=True):
         """inputs: (img_embed, norm_idx) for HNeRV_Boost, (t,) otherwise.  Returns (img, outs, extra).

@@ -304,6 +304,32 @@ def test_benchmarked_presets_full_frame_against_oracle(name):
     assert orc.psnr(img.cpu(), ref) > 60.0
 
 
+def test_enerv_frame_independent_stem_half_follows_the_weights():
+    """The engine computes E-NeRV's coordinate branch trans1(stem_xy(pe_xy(grid))) once per weight version (it does not depend
+    on the frame) and runs the stem without cuDNN's TF32 convs.  Changing those weights in place must be picked up by the next
+    forward(), and the result must still be the oracle's for the new weights - also with torch's TF32 default switched on."""
+    torch.manual_seed(4)
+    m, a = _build("ENeRV_Boost")
+    m = m.cuda()
+    t = torch.tensor([0.3, 0.7]).cuda()
+    cfg = orc.cfg_from_args(a)
+    was = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True          # PyTorch's default outside this test suite
+    try:
+        with torch.no_grad():
+            img0 = m(t)[0].clone()
+            for p in list(m.trans1.parameters()) + list(m.stem_xy.parameters()):
+                p.add_(0.02 * torch.randn_like(p))
+            img1 = m(t)[0].clone()
+    finally:
+        torch.backends.cudnn.allow_tf32 = was
+    assert torch.backends.cudnn.allow_tf32 == was
+    sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+    ref, _ = orc.forward("ENeRV_Boost", sd, cfg, t.cpu())
+    assert max_rel(img1.cpu(), ref) < REL
+    assert max_rel(img0.cpu(), ref) > 10 * max_rel(img1.cpu(), ref)       # the first decode used the old weights
+
+
 @pytest.mark.parametrize("name,steps", [("nerv_s", 300), ("enerv_m", 300), ("hnerv_l", 300)])
 def test_benchmarked_presets_after_training_against_oracle(name, steps):
     """SURVEY.md 8d / VERDICT r1 2a+2b: trained pre-sin magnitudes differ from the initialisation's, so the FULL-SIZE presets are
