@@ -184,6 +184,7 @@ class DecoderEngine:
         self._sft = {}         # SftTable per B
         self._sft_key = None
         self._xy, self._xy_key = None, None     # E-NeRV: frame-independent half of the stem
+        self._front = {}       # NeRV: stem buffers per B
         env = os.environ.get("BNERV_PRECISE_BLOCKS")
         if env:
             self.set_precise(env)
@@ -297,6 +298,11 @@ class DecoderEngine:
             return img, outs, None
         if self.kind == "nerv":                 # NeRV_Boost.forward (model_nerv.py:47-57)
             (t,) = inputs
+            front = self._nerv_front(t)
+            if front is not None:               # PE + both MLPs in two launches, cascade input written as C8 directly
+                x, x_c8, t_embed = front
+                img, outs = self.run_cascade(x, t_embed, keep, x_c8=x_c8)
+                return img, outs, None
             v = m.pe_t(t[:, None].float()).flatten(1).float()
             x = self._mlp(m.stem, v).view(v.size(0), m.fc_dim, m.fc_h, m.fc_w)
             t_embed = self._mlp(m.stem_t, v)
@@ -306,6 +312,51 @@ class DecoderEngine:
         emb, t_manip = self._enerv_stem(t)
         img, outs = self.run_cascade(emb.contiguous(), t_manip.flatten(1), keep)
         return img, outs, t_manip
+
+    def _mlp2(self, seq):
+        """[(weight [Cout, Cin] f32, bias, act)] x 2 of a two-layer NeRV_MLP, or None if it has another form."""
+        mods = list(seq)
+        if len(mods) != 4:
+            return None
+        out = []
+        for conv, act in ((mods[0], mods[1]), (mods[2], mods[3])):
+            a = act_name(act)
+            if not isinstance(conv, nn.Conv2d) or conv.kernel_size != (1, 1) or a is None:
+                return None
+            w, b = effective_weight(conv)
+            if w.dtype != torch.float32:
+                return None
+            out.append((w.detach().reshape(w.shape[0], -1).contiguous(), None if b is None else b.detach().float().contiguous(), a))
+        return out
+
+    def _nerv_front(self, t):
+        """NeRV_Boost's stem (model_nerv.py:47-52) as two launches: position encoding + first layer of stem and stem_t, then
+        their second layers with the stem's output stored as the cascade's C8 input (and f32 for callers that want it).
+        -> (x [B, C, h, w] f32, x_c8, t_embed) or None when the stem has another shape (then the generic path runs)."""
+        m = self.model
+        if os.environ.get("BNERV_NO_FRONT_FUSION") or "pe" not in getattr(m.pe_t, "pe_embed", ""):
+            return None
+        stem, stem_t = self._mlp2(m.stem), self._mlp2(m.stem_t)
+        if stem is None or stem_t is None:
+            return None
+        B, dev = t.shape[0], t.device
+        hw = m.fc_h * m.fc_w
+        (w1, b1, a1), (w2, b2, a2) = stem
+        (v1, c1, e1), (v2, c2, e2) = stem_t
+        if w2.shape[0] != m.fc_dim * hw or B * max(w1.shape[0], v1.shape[0], w1.shape[1]) * 4 > 48 * 1024:
+            return None
+        bases = m.pe_t.pe_bases
+        if bases.device != dev or bases.dtype != torch.float32:
+            bases = m.pe_t.pe_bases = bases.to(dev, torch.float32)
+        bufs = self._front.get(B)
+        if bufs is None:
+            f32 = lambda n: torch.empty((B, n), dtype=torch.float32, device=dev)
+            bufs = self._front[B] = (f32(w1.shape[0]), f32(v1.shape[0]), f32(w2.shape[0]), f32(v2.shape[0]),
+                                     torch.zeros(ops.c8_shape(B, m.fc_dim, m.fc_h, m.fc_w), dtype=torch.float16, device=dev))
+        h, ht, x, t_embed, x_c8 = bufs
+        ops.pe_linear_pair(t.float(), bases, [dict(w=w1, b=b1, act=a1, y=h), dict(w=v1, b=c1, act=e1, y=ht)])
+        ops.linear_pair([dict(x=h, w=w2, b=b2, act=a2, y=x, y_c8=x_c8, hw=hw), dict(x=ht, w=v2, b=c2, act=e2, y=t_embed)], B)
+        return x.view(B, m.fc_dim, m.fc_h, m.fc_w), x_c8, t_embed
 
     def _enerv_stem(self, t):
         """ENeRV_Boost's stem (model_enerv.py:281-303) for the decode path.  Same values as model._stem(t), arranged for a
@@ -367,9 +418,9 @@ class DecoderEngine:
             cap.outputs = self._body(cap.inputs, keep)
         return cap
 
-    def run_cascade(self, x, t_embed, keep=False):
-        """x: [B, C, h, w] f32 NCHW stem output; t_embed: [B, ch_t] f32.  Returns (img, [block outputs]).
-        keep: True = every block output as NCHW f32, "first" = only block 0's, False = none."""
+    def run_cascade(self, x, t_embed, keep=False, x_c8=None):
+        """x: [B, C, h, w] f32 NCHW stem output (x_c8: the same map already in C8 f16); t_embed: [B, ch_t] f32.
+        Returns (img, [block outputs]).  keep: True = every block output as NCHW f32, "first" = only block 0's, False = none."""
         B, C, h, w = x.shape
         dev = x.device
         ws = self._workspace(B, h, w, dev)
@@ -389,7 +440,7 @@ class DecoderEngine:
             hi = xp.half().float()
             cur = ops.nchw_to_c8(torch.cat([hi, xp - hi, hi], dim=1))
         else:
-            cur = ops.nchw_to_c8(x)
+            cur = x_c8 if x_c8 is not None else ops.nchw_to_c8(x)
         cin, H, W = C, h, w
         outs = []
         for bi, blk in enumerate(self.blocks):

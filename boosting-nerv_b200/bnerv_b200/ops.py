@@ -256,6 +256,46 @@ def linear_act(x, weight, bias, act="none"):
     return y
 
 
+def _linear_problems(specs, B, need_x):
+    """specs: two dicts(x=, w=, b=, act=, y=, y_c8=, hw=) -> (ctypes array, tensors kept alive)."""
+    arr = (_capi.LinearProblem * 2)()
+    keep = []
+    for k, sp in enumerate(specs):
+        w = sp["w"]
+        cout = w.shape[0]
+        cin = w.numel() // cout
+        assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+        p = arr[k]
+        if need_x:
+            x = sp["x"].contiguous()
+            assert x.dtype == torch.float32 and tuple(x.shape) == (B, cin)
+            p.x = x.data_ptr()
+            keep.append(x)
+        b = sp.get("b")
+        p.w, p.bias = w.data_ptr(), (b.data_ptr() if b is not None else None)
+        y, y_c8 = sp.get("y"), sp.get("y_c8")
+        p.y = y.data_ptr() if y is not None else None
+        p.y_c8 = y_c8.data_ptr() if y_c8 is not None else None
+        p.Cin, p.Cout, p.act, p.hw = cin, cout, ACT_CODES[sp["act"]], int(sp.get("hw") or 0)
+        keep += [w, b, y, y_c8]
+    return arr, keep
+
+
+def pe_linear_pair(t, bases, specs):
+    """First layers of two MLPs on the position encoding of t ([B] f32) in one launch (bnerv_pe_linear_pair)."""
+    _need_cuda(t, bases)
+    assert t.dtype == torch.float32 and bases.dtype == torch.float32 and t.dim() == 1
+    t, bases = t.contiguous(), bases.contiguous()
+    arr, keep = _linear_problems(specs, t.shape[0], False)
+    check("bnerv_pe_linear_pair", lib.bnerv_pe_linear_pair(ptr(t), t.shape[0], ptr(bases), bases.numel(), arr, _stream()))
+
+
+def linear_pair(specs, B):
+    """Two independent y = act(W x + b) layers in one launch (bnerv_linear_pair); outputs are caller-provided."""
+    arr, keep = _linear_problems(specs, B, True)
+    check("bnerv_linear_pair", lib.bnerv_linear_pair(arr, B, _stream()))
+
+
 class SftTable:
     """Device-side array of bnerv_sft_layer descriptors + the g1p/beta output tables for a batch size."""
 

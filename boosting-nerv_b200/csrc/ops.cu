@@ -1,6 +1,7 @@
 // Small kernels around the tensor-core conv: weight packing, layout conversion at the model boundary,
 // the TAT (SFT) affine-parameter MLP, the 1x1 stem MLP layer, standalone PixelShuffle, and an f32
 // CUDA-core fused conv on the reference's own layouts (exact-arithmetic cross-check path).
+#include <algorithm>
 #include "common.cuh"
 
 namespace bnerv {
@@ -216,6 +217,67 @@ __global__ void linear_act_kernel(const float* __restrict__ x, int B, int Cin, c
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
             if (lane == 0) y[static_cast<size_t>(b) * Cout + o] = apply_act_precise(acc + (bias ? bias[o] : 0.0f), act);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The stem of a frame in two launches (NeRV_Boost: model_nerv.py:47-52; the time MLP of HNeRV_Boost / ENeRV_Boost):
+//   linear_pair_kernel<true> : x = PE(t) = cat(sin(t*bases), cos(t*bases)) built in shared memory (model_blocks.py:120-126,
+//                              the f32 product and libdevice sinf/cosf torch's own kernels evaluate), then the FIRST layer
+//                              of two MLPs that share it;
+//   linear_pair_kernel<false>: the next layer of both MLPs; problem 0 may also write its output as the C8 f16 map
+//                              [B][Cp/8][hw][8] the conv cascade reads (channel = o / hw, pixel = o % hw: the .view(B, C, h, w)
+//                              of model_nerv.py:50) - the layout pass of the cascade input fused into the producer.
+// Same per-output arithmetic as linear_act_kernel (one warp per output row, lane-strided FMAs, xor-shuffle tree).
+// ---------------------------------------------------------------------------------------------
+struct LinearProblem {
+    const float* x;       // [B][Cin] (ignored when the input is the position encoding)
+    const float* w;       // [Cout][Cin]
+    const float* bias;    // [Cout] or null
+    float* y;             // [B][Cout] or null
+    __half* y_c8;         // C8 map or null
+    int Cin, Cout, act, hw, cp;
+};
+
+template <bool PE>
+__global__ void __launch_bounds__(256) linear_pair_kernel(LinearProblem p0, LinearProblem p1, int B, const float* __restrict__ t,
+                                                          const float* __restrict__ bases, int levels, int blocks0) {
+    extern __shared__ float sx[];           // [B][Cin]
+    const bool second = static_cast<int>(blockIdx.x) >= blocks0;
+    const LinearProblem& p = second ? p1 : p0;
+    const int Cin = p.Cin;
+    if (PE) {
+        for (int i = threadIdx.x; i < B * levels; i += blockDim.x) {
+            const int b = i / levels, l = i - b * levels;
+            const float ang = __fmul_rn(t[b], bases[l]);
+            sx[b * Cin + l] = sinf(ang);
+            sx[b * Cin + levels + l] = cosf(ang);
+        }
+    } else {
+        for (int i = threadIdx.x; i < B * Cin; i += blockDim.x) sx[i] = p.x[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int blk = second ? blockIdx.x - blocks0 : blockIdx.x;
+    const int nblk = second ? gridDim.x - blocks0 : blocks0;
+    for (int o = blk * warps_per_block + (threadIdx.x >> 5); o < p.Cout; o += nblk * warps_per_block) {
+        const float* wr = p.w + static_cast<size_t>(o) * Cin;
+        for (int b = 0; b < B; ++b) {
+            float acc = 0.0f;
+            for (int i = lane; i < Cin; i += 32) acc = fmaf(wr[i], sx[b * Cin + i], acc);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane == 0) {
+                const float v = apply_act_precise(acc + (p.bias ? p.bias[o] : 0.0f), p.act);
+                if (p.y) p.y[static_cast<size_t>(b) * p.Cout + o] = v;
+                if (p.y_c8) {
+                    const int c = o / p.hw, px = o - c * p.hw;
+                    p.y_c8[((static_cast<size_t>(b) * (p.cp >> 3) + (c >> 3)) * p.hw + px) * 8 + (c & 7)] =
+                        __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+                }
+            }
         }
     }
 }
@@ -458,6 +520,43 @@ extern "C" int bnerv_linear_act(const float* x, int B, int Cin, const float* w, 
     if (grid > 148 * 8) grid = 148 * 8;
     linear_act_kernel<<<grid, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(x, B, Cin, w, bias, Cout, act, y);
     return check_launch("linear_act_kernel");
+}
+
+static int linear_pair_launch(bool pe, const bnerv_linear_problem* probs, int B, const float* t, const float* bases, int levels,
+                              void* stream) {
+    if (!probs) return set_error(BNERV_E_BADARG, "linear_pair: null problems");
+    if (B <= 0) return set_error(BNERV_E_BADARG, "linear_pair: non-positive batch");
+    LinearProblem p[2];
+    int blocks[2], cin_max = 0;
+    for (int k = 0; k < 2; ++k) {
+        const bnerv_linear_problem& q = probs[k];
+        if (!q.w || (!q.y && !q.y_c8) || (!pe && !q.x)) return set_error(BNERV_E_BADARG, "linear_pair: null pointer in problem %d", k);
+        if (q.Cin <= 0 || q.Cout <= 0) return set_error(BNERV_E_BADARG, "linear_pair: non-positive size in problem %d", k);
+        if (pe && q.Cin != 2 * levels) return set_error(BNERV_E_BADARG, "linear_pair: Cin = %d but the position encoding has %d entries", q.Cin, 2 * levels);
+        if (q.act < BNERV_ACT_NONE || q.act > BNERV_ACT_TANH01) return set_error(BNERV_E_UNSUPPORTED, "linear_pair: act %d", q.act);
+        if (q.y_c8 && (q.hw <= 0 || q.Cout % q.hw != 0)) return set_error(BNERV_E_BADARG, "linear_pair: C8 output needs Cout = C * hw");
+        p[k].x = q.x; p[k].w = q.w; p[k].bias = q.bias; p[k].y = q.y; p[k].y_c8 = static_cast<__half*>(q.y_c8);
+        p[k].Cin = q.Cin; p[k].Cout = q.Cout; p[k].act = q.act; p[k].hw = q.y_c8 ? q.hw : 1;
+        p[k].cp = q.y_c8 ? round_up(q.Cout / q.hw, 16) : 16;
+        blocks[k] = std::min((q.Cout + 7) / 8, 148 * 8);
+        cin_max = std::max(cin_max, q.Cin);
+    }
+    const size_t smem = static_cast<size_t>(B) * cin_max * sizeof(float);
+    if (smem > 48 * 1024) return set_error(BNERV_E_UNSUPPORTED, "linear_pair: B*Cin = %d floats exceeds 48 KB of shared memory", B * cin_max);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pe) linear_pair_kernel<true><<<blocks[0] + blocks[1], 256, smem, st>>>(p[0], p[1], B, t, bases, levels, blocks[0]);
+    else    linear_pair_kernel<false><<<blocks[0] + blocks[1], 256, smem, st>>>(p[0], p[1], B, nullptr, nullptr, 0, blocks[0]);
+    return check_launch("linear_pair_kernel");
+}
+
+extern "C" int bnerv_pe_linear_pair(const float* t, int B, const float* bases, int levels, const bnerv_linear_problem* probs,
+                                    void* stream) {
+    if (!t || !bases || levels <= 0) return set_error(BNERV_E_BADARG, "pe_linear_pair: null / empty position encoding");
+    return linear_pair_launch(true, probs, B, t, bases, levels, stream);
+}
+
+extern "C" int bnerv_linear_pair(const bnerv_linear_problem* probs, int B, void* stream) {
+    return linear_pair_launch(false, probs, B, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int bnerv_conv_fused_f32(const float* x, int B, int Cin, int H, int W, const float* w, const float* bias,

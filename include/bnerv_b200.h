@@ -220,6 +220,26 @@ int bnerv_sft_affine(const bnerv_sft_layer* layers_dev, int n_layers, const floa
 int bnerv_linear_act(const float* x, int B, int Cin, const float* w, const float* bias, int Cout,
                      int act, float* y, void* stream);
 
+/* Two independent layers in ONE launch - the stem of a frame is two small MLPs (NeRV_Boost: stem and stem_t,
+ * model_nerv.py:47-52), and at batch 1 each of their layers is launch-latency, not work.
+ *   bnerv_pe_linear_pair : both problems read x = cat(sin(t*bases), cos(t*bases)) (PositionEncoding.forward,
+ *                          model_blocks.py:120-126: f32 product, sinf / cosf as torch's CUDA kernels evaluate them), built
+ *                          in shared memory; Cin of both must be 2*levels, `x` is ignored.
+ *   bnerv_linear_pair    : x given per problem.
+ * y (f32 [B][Cout]) and/or y_c8: the output as the C8 f16 map [B][Cp/8][hw][8] of its .view(B, Cout/hw, h, w) (the cascade
+ * input, model_nerv.py:50; padding channels are NOT written - zero the buffer once).  Per-output arithmetic is
+ * bnerv_linear_act's, so results are bit-identical to it. */
+typedef struct bnerv_linear_problem {
+    const float* x;       /* [B][Cin] */
+    const float* w;       /* [Cout][Cin] */
+    const float* bias;    /* [Cout] or NULL */
+    float* y;             /* [B][Cout] or NULL */
+    void* y_c8;           /* C8 f16 map or NULL */
+    int32_t Cin, Cout, act, hw;
+} bnerv_linear_problem;
+int bnerv_pe_linear_pair(const float* t, int B, const float* bases, int levels, const bnerv_linear_problem* probs, void* stream);
+int bnerv_linear_pair(const bnerv_linear_problem* probs, int B, void* stream);
+
 /* Layout conversion at the model boundary. */
 int bnerv_nchw_to_c8(const float* x, int B, int C, int H, int W, void* y_c8, void* stream);
 int bnerv_c8_to_nchw(const void* x_c8, int B, int C, int H, int W, float* y, void* stream);

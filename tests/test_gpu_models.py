@@ -304,6 +304,29 @@ def test_benchmarked_presets_full_frame_against_oracle(name):
     assert orc.psnr(img.cpu(), ref) > 60.0
 
 
+def test_nerv_fused_front_is_bitwise_the_generic_stem(monkeypatch):
+    """NeRV_Boost's stem as two launches (bnerv_pe_linear_pair + bnerv_linear_pair, C8 cascade input written by the producer)
+    against the generic path (torch position encoding, four bnerv_linear_act launches, bnerv_nchw_to_c8): same image, same
+    block outputs, bit for bit, and 8 launches of this library fewer per frame."""
+    from bnerv_b200 import _capi
+    torch.manual_seed(6)
+    m, a = _build("NeRV_Boost")
+    m = m.cuda()
+    m.keep_intermediates = True
+    m.engine().use_graph = False
+    t = torch.tensor([0.2, 0.9]).cuda()
+    with torch.no_grad():
+        m(t)                                   # packs the weights
+        n0 = _capi.launch_count()
+        img, outs, _ = m(t)
+        n1 = _capi.launch_count()
+        monkeypatch.setenv("BNERV_NO_FRONT_FUSION", "1")
+        img_g, outs_g, _ = m(t)
+        n2 = _capi.launch_count()
+    assert torch.equal(img, img_g) and all(torch.equal(p, q) for p, q in zip(outs, outs_g))
+    assert (n2 - n1) - (n1 - n0) == 3          # 4 linear + 1 layout launch -> 2 (the 5 torch kernels of the PE are not counted)
+
+
 def test_enerv_frame_independent_stem_half_follows_the_weights():
     """The engine computes E-NeRV's coordinate branch trans1(stem_xy(pe_xy(grid))) once per weight version (it does not depend
     on the frame) and runs the stem without cuDNN's TF32 convs.  Changing those weights in place must be picked up by the next

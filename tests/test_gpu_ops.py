@@ -331,3 +331,32 @@ def test_head1x1_kernel_matches_reference(ops, B, cin, cout, H, W, act):
     ref = F.conv2d(x.half().float(), w, b)
     ref = torch.tanh(ref) * 0.5 + 0.5 if act == "tanh01" else ref
     assert max_rel(out, ref) < 1e-5                   # f32 accumulation; tanh through ex2.approx (measured <= 1e-6)
+
+
+def test_pe_linear_pair_and_linear_pair_are_bitwise_the_separate_launches():
+    """bnerv_pe_linear_pair / bnerv_linear_pair (the stem of a frame in two launches): the position encoding built in the
+    kernel is torch's bit for bit at the reference's frequencies (1.25^79 * pi rad), each layer is bnerv_linear_act's result
+    bit for bit, and the C8 output is bnerv_nchw_to_c8 of the f32 output."""
+    from bnerv_b200 import ops
+    from bnerv_b200.layers import PositionEncoding
+    torch.manual_seed(3)
+    B, hw, C = 3, 6, 10
+    pe = PositionEncoding("pe_1.25_80", "pi")
+    t = torch.tensor([1 / 600, 0.5, 599 / 600], device="cuda")
+    v = pe(t[:, None]).flatten(1)
+    L = v.shape[1]
+    w1, b1 = torch.randn(48, L, device="cuda") / L ** 0.5, torch.randn(48, device="cuda")
+    v1 = torch.randn(20, L, device="cuda") / L ** 0.5
+    h, ht = torch.empty(B, 48, device="cuda"), torch.empty(B, 20, device="cuda")
+    ops.pe_linear_pair(t, pe.pe_bases, [dict(w=w1, b=b1, act="gelu", y=h), dict(w=v1, b=None, act="sin", y=ht)])
+    assert torch.equal(h, ops.linear_act(v, w1, b1, "gelu")) and torch.equal(ht, ops.linear_act(v, v1, None, "sin"))
+    w2, b2 = torch.randn(C * hw, 48, device="cuda") / 7, torch.randn(C * hw, device="cuda")
+    v2, c2 = torch.randn(12, 20, device="cuda") / 4, torch.randn(12, device="cuda")
+    x, te = torch.empty(B, C * hw, device="cuda"), torch.empty(B, 12, device="cuda")
+    x_c8 = torch.zeros(ops.c8_shape(B, C, 2, 3), dtype=torch.float16, device="cuda")
+    ops.linear_pair([dict(x=h, w=w2, b=b2, act="gelu", y=x, y_c8=x_c8, hw=hw), dict(x=ht, w=v2, b=c2, act="none", y=te)], B)
+    assert torch.equal(x, ops.linear_act(h, w2, b2, "gelu")) and torch.equal(te, ops.linear_act(ht, v2, c2, "none"))
+    assert torch.equal(x_c8, ops.nchw_to_c8(x.view(B, C, 2, 3)))
+    from bnerv_b200 import _capi
+    arr = (_capi.LinearProblem * 2)()
+    assert _capi.lib.bnerv_linear_pair(arr, B, None) == _capi.E_BADARG
