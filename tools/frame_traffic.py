@@ -1,4 +1,5 @@
-"""Turn an ncu CSV (`--metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:bnerv`) of decoded frames into
+"""Turn an ncu CSV (`--metrics dram__bytes_read.sum,dram__bytes_write.sum --kernel-name-base demangled -k regex:bnerv`: only this
+library's kernels are captured; the CSV prints their names without the namespace) of decoded frames into
 profiles/frame_traffic_<config>.json (what bench.py reports as roofline.traffic), next to the bytes the same launches must
 move by design (C8 f16 input (+ residual) + output map(s) + packed weights per launch; a fused block: input + output + weights;
 the head writes NCHW f32).  `launches per frame` = this library's kernels in one decoded frame (the last frame is used).
@@ -13,7 +14,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "boosting-nerv_b200"))
 
 path, cfg, per_frame, cmd = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
-rows = [r for r in csv.DictReader(l for l in open(path) if not l.startswith("==")) if "bnerv" in r.get("Kernel Name", "")]
+rows = [r for r in csv.DictReader(l for l in open(path) if not l.startswith("==")) if r.get("Kernel Name") and "at::" not in r["Kernel Name"] and "cutlass" not in r["Kernel Name"]]
 unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 rd = [float(r["Metric Value"].replace(",", "")) * unit[r["Metric Unit"]] for r in rows if r["Metric Name"] == "dram__bytes_read.sum"]
 wr = [float(r["Metric Value"].replace(",", "")) * unit[r["Metric Unit"]] for r in rows if r["Metric Name"] == "dram__bytes_write.sum"]
