@@ -231,9 +231,11 @@ __global__ void __launch_bounds__(256) ptq_select_kernel(PtqTables T) {
         __syncthreads();
     }
     if (threadIdx.x == 0) {
+        // the reference compares f32 means (torch .mean() of an f32 tensor): round before comparing, so candidates whose errors
+        // agree to f32 precision tie exactly as they do there (first one wins)
         int best = 0;
         for (int c = 1; c < jb.n_cand; ++c)
-            if (errs[c] < errs[best]) best = c;
+            if (static_cast<float>(errs[c]) < static_cast<float>(errs[best])) best = c;
         *jb.best = best;
     }
 }

@@ -360,7 +360,10 @@ size_t bnerv_ssim_scratch_floats(int planes, int H, int W);
  * Every arithmetic step is the reference's in round-to-nearest f32 (true division as torch's CPU kernels do; torch's CUDA
  * kernel multiplies by 1/(2^bits-1) when dividing by a scalar, which can move a whole-tensor scale by 1 ulp), so codes,
  * tables and reconstruction are bit-identical to the CPU reference; the candidate errors are summed in f64 in a fixed
- * order (the reference: f32 pairwise), which can only matter for exact near-ties between candidates. */
+ * order and compared after rounding to f32 (the reference: f32 pairwise means), which can only matter for near-ties between
+ * candidates.  Preconditions - NOT checked, and where behaviour deliberately differs from the reference: inputs must be finite
+ * (CUDA fminf / fmaxf drop NaN where torch propagates it), and a group whose range is zero - a constant tensor, or a per-axis
+ * slice whose f16 scale rounds to 0 - gets code 0 and new_t = min here, where the reference divides by zero and stores NaN. */
 #define BNERV_PTQ_MAX_CAND 5
 typedef struct bnerv_ptq_plan {
     int32_t n_cand;                           /* 1 + number of eligible axes                                  */
