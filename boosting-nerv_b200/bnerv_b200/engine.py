@@ -136,6 +136,8 @@ class _BlockPlan:
             elif form == "stream" and cp <= 16:
                 whole = self.up.k == 3 and self.up.s in (1, 2) and cin_p <= 16
                 self.fuse = ("stream", "block" if whole else "res")
+            elif form == "stream" and cp == 32 and not os.environ.get("BNERV_NO_STREAM32"):
+                self.fuse = ("stream", "res")       # 17..32 channels: up-conv launch + the ResBlock_SFT half as one kernel
 
 
 def _sft_tensors(sft):
@@ -479,7 +481,7 @@ class DecoderEngine:
                 x0 = view(ws["x0"], blk.cout, Ho, Wo)
                 u = view(ws["u"], blk.cout, Ho, Wo)
                 ops.conv_fused(cur, blk.up.packed(), cin, H, W, act=blk.act, g1p=g0, beta=b0, out_pre=x0, out_aff=u)
-                if fuse is not None:
+                if fuse is not None and (cp <= 16 or Ho * Wo >= 65536):      # the 32-channel form pays off on large maps only
                     done = ops.resblock_fused(u, x0, blk.c0.packed(), blk.c1.packed(), blk.cout, Ho, Wo, blk.inner_act, g1, b1,
                                               out=out, form=fuse[0])
                 if done is None:

@@ -658,6 +658,11 @@ static int bs_launch(const void* x_in, BsArgs& a, cudaStream_t stream) {
     return check_launch("block_stream_kernel");
 }
 
+// 17..32 channels: block_stream32.cu
+int resblock_stream32(const void* u, const void* x0, int B, int C, int H, int W, const void* w_c0, const float* b_c0,
+                      const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1, void* out,
+                      cudaStream_t stream);
+
 }  // namespace bnerv
 
 using namespace bnerv;
@@ -690,11 +695,13 @@ extern "C" int bnerv_resblock_stream(const void* u, const void* x0, int B, int C
                                      void* out, void* stream) {
     if (!u || !x0 || !w_c0 || !b_c0 || !w_c1 || !b_c1 || !g1p || !beta1 || !out) return set_error(BNERV_E_BADARG, "resblock_stream: null pointer");
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return set_error(BNERV_E_BADARG, "resblock_stream: non-positive size");
-    if (C > 16) return set_error(BNERV_E_UNSUPPORTED, "resblock_stream: C = %d (at most 16 channels)", C);
+    if (C > 32) return set_error(BNERV_E_UNSUPPORTED, "resblock_stream: C = %d (at most 32 channels)", C);
     if (act_inner < BNERV_ACT_NONE || act_inner > BNERV_ACT_TANH01) return set_error(BNERV_E_UNSUPPORTED, "resblock_stream: activation code");
     const uintptr_t align_or = reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(w_c0) |
                                reinterpret_cast<uintptr_t>(w_c1) | reinterpret_cast<uintptr_t>(out);
     if (align_or & 15) return set_error(BNERV_E_BADARG, "resblock_stream: pointers must be 16-byte aligned");
+    if (C > 16)
+        return resblock_stream32(u, x0, B, C, H, W, w_c0, b_c0, w_c1, b_c1, act_inner, g1p, beta1, out, static_cast<cudaStream_t>(stream));
     BsArgs a{};
     a.B = B; a.H = H; a.W = W; a.C = C; a.s = 1; a.has_up = 0; a.act_up = BNERV_ACT_NONE; a.act_inner = act_inner;
     a.w_c0 = static_cast<const __half*>(w_c0); a.w_c1 = static_cast<const __half*>(w_c1);

@@ -1,0 +1,486 @@
+// ResBlock_SFT half of a NeRVBlock (model_blocks.py:83-89 with the SFTLayer affine of :101-105) as ONE row-streaming kernel for
+// 17..32 channels (Cp = 32: E-NeRV-M's 1080p stages, NeRV-S's 45x80 stage): out = x0 + conv3(gelu(conv3(u))*g1p + beta1).
+// Same design as block_stream.cu (read its header first) - A operands of both convs are rings of image rows in TENSOR MEMORY,
+// the horizontal tap is baked into three pre-shifted copies of a row, the vertical tap is a choice of ring row - widened to
+// four channel groups: a row copy is K = 32 = two K steps of 8 TMEM columns, an A row 3 x 2 x 8 = 48 columns, an accumulator
+// row 32 columns.  Tensor memory (512 columns): two A rings of 4 rows (384) + two accumulator rings of 2 rows (128).
+//
+//     TMA warp    : u rows -> shared-memory ring (6 slots)
+//     front  WG   : builds A_c0(h) from the u rows
+//     middle WGs  : 4; epilogue of D_c0(h): w = act(. + b0)*g1p + beta1 -> exchange row in shared memory -> builds A_c1(h)
+//     back   WG   : epilogue of D_c1(h): out = . + b1 + x0 (x0 read from global) -> global
+//     MMA warps   : one issuer per conv; per output row 3 ring rows x 3 shifts x 2 K steps = 18 MMAs (M = 128, N = 32, K = 16)
+//
+// One thing differs from block_stream.cu: the two accumulator slots of conv0 are shared by FOUR consumer warpgroups.  A
+// warpgroup that waited on a slot's own "full" barrier would see only every second use of it, and an mbarrier parity wait
+// cannot tell "one use behind" from "done".  So "full" is signalled per CONSUMER WARPGROUP (it sees every phase of its own
+// barrier), while "empty" stays per slot (its only waiter, the MMA issuer, sees every use in order).  This is safe because row
+// k + 4 of a warpgroup cannot complete before ALL its warps have released row k (the slot chain k -> k+2 -> k+4 passes through
+// row k's "empty"); a single "full" barrier for both slots of ONE warpgroup would not be (row k+1 can complete while a slow
+// warp has not yet waited for row k) - conv1's single consumer warpgroup therefore keeps one "full" barrier per slot.
+//
+// Arithmetic = two bnerv_conv_fused launches, operation by operation (tap order r*3+sx, K steps in channel order, same
+// epilogue functions, f16 rounding of w at the same place): bit-identical results (tests/test_gpu_block_fused.py).
+#include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include "common.cuh"
+
+namespace bnerv {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();          // conv_tc.cu
+
+constexpr int B32_CG = 4;                     // channel groups of 8 (Cp = 32)
+constexpr int B32_WG_M = 4;                   // middle warpgroups
+constexpr int B32_WARP_M = 4, B32_WARP_B = 4 + 4 * B32_WG_M, B32_WARP_MMA = B32_WARP_B + 4;   // + 2 issuers + TMA
+constexpr int B32_THREADS = (B32_WARP_MMA + 3) * 32;                 // 27 warps
+constexpr int B32_NA = 4;                     // A-row ring slots per conv (TMEM)
+constexpr int B32_ND = 2;                     // accumulator slots per conv (TMEM)
+constexpr int B32_NX = 4;                     // residual (x0) rows in flight: the global-load latency is ~1 row period
+constexpr int B32_NI = 6;                     // input-row slots (shared memory); one consumer warpgroup sees every use
+constexpr int B32_VALID = 122;                // valid output columns per strip: lanes [2, 124) (geometry of block_stream.cu)
+constexpr int B32_ACOLS = 48;                 // TMEM columns of one A row: 3 shifts x 2 K steps x 8
+constexpr int B32_A0 = 0, B32_A1 = B32_NA * B32_ACOLS;               // A rings of conv0 / conv1
+constexpr int B32_D0 = 2 * B32_NA * B32_ACOLS, B32_D1 = B32_D0 + B32_ND * 32;
+static_assert(B32_D1 + B32_ND * 32 <= 512, "TMEM columns");
+constexpr int B32_ROW_B = B32_CG * 128 * 16;  // one input row in shared memory: [4 groups][128 px][16 B]
+constexpr int B32_XROW_B = B32_CG * 130 * 16; // one exchange row: [4 groups][130 px][16 B] (px 0 and 129 stay zero)
+constexpr int B32_W_B = 9 * B32_CG * 32 * 16; // one conv's weights: [tap][4 groups][32 rows][16 B]
+
+struct B32Cst { float b_c0[32], b_c1[32], g1p[32], beta1[32]; };
+
+struct B32Bars {
+    uint64_t in_full[B32_NI], in_empty[B32_NI];
+    uint64_t a_full[2][B32_NA], a_empty[2][B32_NA];
+    uint64_t d_full0[B32_WG_M];               // conv0: per consumer warpgroup (see the header)
+    uint64_t d_full1[B32_ND];                 // conv1: per slot (one consumer warpgroup sees every use)
+    uint64_t d_empty[2][B32_ND];              // per slot
+    uint32_t tmem_slot, pad;
+};
+
+struct B32Smem {
+    uint8_t w_c[2][B32_W_B];
+    uint8_t in_ring[B32_NI][B32_ROW_B];
+    uint8_t w_ring[B32_WG_M][2][B32_XROW_B];
+    uint8_t x0_ring[B32_NX][B32_ROW_B];       // residual rows, prefetched by the back warpgroup's own lanes (cp.async)
+    B32Cst cst;
+    B32Bars bars;
+};
+
+struct B32Args {
+    int B, H, W, C;
+    int act_inner;
+    int strips, segs, seg_rows;
+    const __half *w_c0, *w_c1;
+    const float *b_c0, *b_c1, *g1p, *beta1;
+    const __half* resid;
+    __half* out;
+};
+
+__device__ __forceinline__ void b32_tmem_st8(uint32_t taddr, const uint4& lo, const uint4& hi) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+}
+__device__ __forceinline__ void b32_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void b32_umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ uint4 b32_pack8(const float2* x) {
+    uint4 o;
+    o.x = pack_h2_satfinite(x[0]); o.y = pack_h2_satfinite(x[1]);
+    o.z = pack_h2_satfinite(x[2]); o.w = pack_h2_satfinite(x[3]);
+    return o;
+}
+template <int ACT>
+__device__ __forceinline__ float2 b32_act2(float2 x, int act) {
+    if (ACT >= 0) return act2<ACT>(x);
+    switch (act) {
+        case BNERV_ACT_SIN:    return sin2(x);
+        case BNERV_ACT_GELU:   return gelu2(x);
+        case BNERV_ACT_RELU:   return act2<BNERV_ACT_RELU>(x);
+        case BNERV_ACT_TANH01: return tanh01_2(x);
+        default:               return x;
+    }
+}
+__device__ __forceinline__ void b32_bias16(const uint32_t* v, const float* bias, float2* x) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float4 bs = *reinterpret_cast<const float4*>(bias + 4 * p);
+        x[2 * p]     = add2(make_float2(__uint_as_float(v[4 * p]),     __uint_as_float(v[4 * p + 1])), make_float2(bs.x, bs.y));
+        x[2 * p + 1] = add2(make_float2(__uint_as_float(v[4 * p + 2]), __uint_as_float(v[4 * p + 3])), make_float2(bs.z, bs.w));
+    }
+}
+__device__ __forceinline__ void b32_affine8(const float2* x, const float* g, const float* e, float2* y) {
+    const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+    const float4 e0 = *reinterpret_cast<const float4*>(e), e1 = *reinterpret_cast<const float4*>(e + 4);
+    y[0] = fma2(x[0], make_float2(g0.x, g0.y), make_float2(e0.x, e0.y));
+    y[1] = fma2(x[1], make_float2(g0.z, g0.w), make_float2(e0.z, e0.w));
+    y[2] = fma2(x[2], make_float2(g1.x, g1.y), make_float2(e1.x, e1.y));
+    y[3] = fma2(x[3], make_float2(g1.z, g1.w), make_float2(e1.z, e1.w));
+}
+
+// NPAIR: channel pairs that carry data (11: C <= 22, 12: C <= 24, 16: all).  A pad channel's conv0 output is exactly 0 (zero
+// weight rows, zero bias) and every block activation maps 0 to 0, so a skipped pair is set to the 0 it would have computed and
+// goes through the same affine; conv1 has zero weights for pad input channels either way.
+template <int ACT_IN, int NPAIR>
+__global__ void __launch_bounds__(B32_THREADS, 1)
+resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    B32Smem& sm = *reinterpret_cast<B32Smem*>(smem_raw);
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                      // TMEM lane == column of the strip
+
+    const int seg = blockIdx.x % a.segs;
+    const int strip = (blockIdx.x / a.segs) % a.strips;
+    const int fb = blockIdx.x / (a.segs * a.strips);
+    const int y0 = seg * a.seg_rows;
+    const int y1 = (y0 + a.seg_rows < a.H) ? y0 + a.seg_rows : a.H;
+    const int rows = y1 - y0;
+    const int sx0 = strip * B32_VALID - 2;            // image column of lane 0
+    const int col = sx0 + m;
+    const bool col_in = (col >= 0) && (col < a.W);
+    // conv0 output rows y0-1 .. y1 (rows + 2), its A rows (u) y0-2 .. y1+1 (rows + 4); conv1 output rows y0 .. y1-1
+    const int n_in = rows + 4, n_c0 = rows + 2;
+    const int in_row0 = y0 - 2, in_x0 = sx0 - 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < B32_NI; ++i) { mbar_init(smem_u32(&sm.bars.in_full[i]), 1); mbar_init(smem_u32(&sm.bars.in_empty[i]), 4); }
+        for (int s = 0; s < 2; ++s) {
+            for (int i = 0; i < B32_NA; ++i) { mbar_init(smem_u32(&sm.bars.a_full[s][i]), 4); mbar_init(smem_u32(&sm.bars.a_empty[s][i]), 1); }
+            for (int i = 0; i < B32_ND; ++i) mbar_init(smem_u32(&sm.bars.d_empty[s][i]), 4);
+        }
+        for (int i = 0; i < B32_WG_M; ++i) mbar_init(smem_u32(&sm.bars.d_full0[i]), 1);
+        for (int i = 0; i < B32_ND; ++i) mbar_init(smem_u32(&sm.bars.d_full1[i]), 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&tmIn);
+    }
+    if (warp == B32_WARP_MMA) tmem_alloc(smem_u32(&sm.bars.tmem_slot), 512);
+    {   // weights: the packed global form [tap][4 groups][32 rows][8 halves] is the shared-memory form
+        const uint4* s0 = reinterpret_cast<const uint4*>(a.w_c0);
+        const uint4* s1 = reinterpret_cast<const uint4*>(a.w_c1);
+        uint4* d0 = reinterpret_cast<uint4*>(sm.w_c[0]);
+        uint4* d1 = reinterpret_cast<uint4*>(sm.w_c[1]);
+        for (int i = threadIdx.x; i < B32_W_B / 16; i += B32_THREADS) { d0[i] = __ldg(s0 + i); d1[i] = __ldg(s1 + i); }
+    }
+    if (threadIdx.x < 32) {
+        sm.cst.b_c0[threadIdx.x] = __ldg(a.b_c0 + threadIdx.x);
+        sm.cst.b_c1[threadIdx.x] = __ldg(a.b_c1 + threadIdx.x);
+    }
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(sm.w_ring) / 16); i += B32_THREADS)      // exchange rows: the edge pixels stay zero
+        reinterpret_cast<uint4*>(sm.w_ring)[i] = make_uint4(0, 0, 0, 0);
+    pdl_wait();                       // TAT tables / activations come from earlier kernels
+    pdl_launch_dependents();
+    if (threadIdx.x < 32) {
+        sm.cst.g1p[threadIdx.x] = __ldg(a.g1p + fb * 32 + threadIdx.x);
+        sm.cst.beta1[threadIdx.x] = __ldg(a.beta1 + fb * 32 + threadIdx.x);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.bars.tmem_slot;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+    // builds A row `iA` of conv S (0 / 1) from a [4 groups][pitch px][16 B] shared-memory row: lane m <- pixels m .. m+2
+    auto build_a = [&](int S, int iA, const uint8_t* row, int pitch, int px_max) {
+        const int as = iA % B32_NA;
+        const uint32_t t = lane_base + (S ? B32_A1 : B32_A0) + as * B32_ACOLS;
+        uint4 g[3][B32_CG];
+#pragma unroll
+        for (int sx = 0; sx < 3; ++sx) {
+            int px = m + sx;
+            px = px > px_max ? px_max : px;                  // lanes >= 126 of an input row: not valid lanes, any finite data
+#pragma unroll
+            for (int c = 0; c < B32_CG; ++c)
+                g[sx][c] = *reinterpret_cast<const uint4*>(row + static_cast<size_t>(c * pitch + px) * 16);
+        }
+        mbar_wait(smem_u32(&sm.bars.a_empty[S][as]), ((iA / B32_NA) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int sx = 0; sx < 3; ++sx) {
+            b32_tmem_st8(t + (sx * 2 + 0) * 8, g[sx][0], g[sx][1]);
+            b32_tmem_st8(t + (sx * 2 + 1) * 8, g[sx][2], g[sx][3]);
+        }
+        b32_tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.bars.a_full[S][as]));
+    };
+
+    if (warp == B32_WARP_MMA + 2) {
+        // =============================== TMA producer: u rows -> ring ===============================
+        for (int i = 0; i < n_in; ++i) {
+            const int slot = i % B32_NI;
+            mbar_wait(smem_u32(&sm.bars.in_empty[slot]), ((i / B32_NI) & 1) ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(smem_u32(&sm.bars.in_full[slot]), B32_ROW_B);
+                tma_load_3d(smem_u32(sm.in_ring[slot]), &tmIn, smem_u32(&sm.bars.in_full[slot]), 2 * in_x0, in_row0 + i, fb * B32_CG);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= B32_WARP_MMA) {
+        // =============================== MMA issuers: warp B32_WARP_MMA + S issues conv S ===============================
+        const int S = warp - B32_WARP_MMA;
+        const uint32_t idesc = umma_idesc_f16(128, 32);
+        const uint64_t b_d = umma_desc_hi_noswz(32u * 16u, 128u);
+        const uint32_t b_hi = static_cast<uint32_t>(b_d >> 32);
+        const uint32_t b_lo = static_cast<uint32_t>(b_d) | ((smem_u32(sm.w_c[S]) & 0x3FFFFu) >> 4);
+        const uint32_t d_base = tmem_base + (S ? B32_D1 : B32_D0);
+        const uint32_t a_base = tmem_base + (S ? B32_A1 : B32_A0);
+        const int n = S ? rows : n_c0;
+        int a_waited = 0;
+        for (int j = 0; j < n; ++j) {
+            while (a_waited <= j + 2) {                             // A rows j, j+1, j+2 (image rows h-1, h, h+1)
+                mbar_wait(smem_u32(&sm.bars.a_full[S][a_waited % B32_NA]), (a_waited / B32_NA) & 1);
+                ++a_waited;
+            }
+            const int ds = j % B32_ND;
+            mbar_wait(smem_u32(&sm.bars.d_empty[S][ds]), ((j / B32_ND) & 1) ^ 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d = d_base + ds * 32;
+                // accumulation order of conv_tc_kernel: K steps outermost, the nine taps (r*3 + sx) inside a K step
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {                   // one K step = 2 channel groups x 32 rows x 16 B = 64 units of 16 B
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const uint32_t at = a_base + ((j + r) % B32_NA) * B32_ACOLS;
+#pragma unroll
+                        for (int sx = 0; sx < 3; ++sx)
+                            b32_umma_ts(d, at + (sx * 2 + ks) * 8, b_lo + ((r * 3 + sx) * 2 + ks) * 64, b_hi, idesc, (ks | r | sx) ? 1u : 0u);
+                    }
+                }
+                umma_commit(smem_u32(S ? &sm.bars.d_full1[ds] : &sm.bars.d_full0[j % B32_WG_M]));
+                umma_commit(smem_u32(&sm.bars.a_empty[S][j % B32_NA]));      // A row j has had its last reader
+            }
+            __syncwarp();
+        }
+    } else if (warp < B32_WARP_M) {
+        // =============================== front warpgroup: u rows -> A_c0 rows ===============================
+        for (int i = 0; i < n_in; ++i) {
+            const int slot = i % B32_NI;
+            mbar_wait(smem_u32(&sm.bars.in_full[slot]), (i / B32_NI) & 1);
+            build_a(0, i, sm.in_ring[slot], 128, 127);
+            if (lane == 0) mbar_arrive(smem_u32(&sm.bars.in_empty[slot]));
+        }
+    } else if (warp < B32_WARP_B) {
+        // =============================== middle warpgroups: conv0 epilogue -> A_c1 ===============================
+        const int par = (warp - B32_WARP_M) >> 2;
+        int it = 0;
+        for (int k = par; k < n_c0; k += B32_WG_M, ++it) {
+            const int h = y0 - 1 + k;
+            const int ds = k % B32_ND;
+            const bool inside = col_in && (h >= 0) && (h < a.H);
+            uint8_t* wrow = sm.w_ring[par][it & 1];
+            mbar_wait(smem_u32(&sm.bars.d_full0[par]), it & 1);
+            tc_fence_after();
+            uint32_t v0[16], v1[16];
+            tmem_ld16(lane_base + B32_D0 + ds * 32, v0);
+            tmem_ld16(lane_base + B32_D0 + ds * 32 + 16, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.bars.d_empty[0][ds]));
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float2 x[8];
+                b32_bias16(half ? v1 : v0, sm.cst.b_c0 + 16 * half, x);
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+                    x[p] = (half * 8 + p < NPAIR) ? b32_act2<ACT_IN>(x[p], a.act_inner) : make_float2(0.0f, 0.0f);
+                float2 y[4];
+                uint4 w0, w1;
+                b32_affine8(x, sm.cst.g1p + 16 * half, sm.cst.beta1 + 16 * half, y);
+                w0 = b32_pack8(y);
+                b32_affine8(x + 4, sm.cst.g1p + 16 * half + 8, sm.cst.beta1 + 16 * half + 8, y);
+                w1 = b32_pack8(y);
+                if (!inside) { w0 = make_uint4(0, 0, 0, 0); w1 = w0; }
+                *reinterpret_cast<uint4*>(wrow + static_cast<size_t>((2 * half) * 130 + m + 1) * 16) = w0;
+                *reinterpret_cast<uint4*>(wrow + static_cast<size_t>((2 * half + 1) * 130 + m + 1) * 16) = w1;
+            }
+            named_bar_sync(1 + par, 128);                            // the w row is complete
+            build_a(1, k, wrow, 130, 129);
+            // the next iteration but one rewrites this exchange row: every thread has passed the next barrier by then
+        }
+    } else {
+        // =============================== back warpgroup: conv1 epilogue + residual -> global ===============================
+        const size_t plane = static_cast<size_t>(a.H) * a.W * 8;
+        const bool lane_valid = (m >= 2) && (m < 2 + B32_VALID) && col_in;
+        // x0 rows come from global memory; a load issued when its row is needed would expose the DRAM latency once per row (it
+        // was the whole row period).  Every lane copies ITS OWN 16-byte pieces B32_NX - 1 rows ahead with cp.async into a
+        // shared-memory ring and reads them back itself: no cross-thread hand-off, only cp.async.wait_group.
+        auto prefetch = [&](int k) {
+            if (k < rows && lane_valid) {
+                const size_t g = ((static_cast<size_t>(fb) * B32_CG) * a.H + (y0 + k)) * static_cast<size_t>(a.W) * 8 + static_cast<size_t>(col) * 8;
+#pragma unroll
+                for (int c = 0; c < B32_CG; ++c)
+                    if (4 * c < NPAIR) {
+                        const uint32_t dst = smem_u32(sm.x0_ring[k % B32_NX] + static_cast<size_t>(c * 128 + m) * 16);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(a.resid + g + c * plane) : "memory");
+                    }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int k = 0; k < B32_NX - 1; ++k) prefetch(k);
+        for (int k = 0; k < rows; ++k) {
+            const int h = y0 + k;
+            const size_t goff = ((static_cast<size_t>(fb) * B32_CG) * a.H + h) * static_cast<size_t>(a.W) * 8 + static_cast<size_t>(col) * 8;
+            prefetch(k + B32_NX - 1);
+            const int ds = k % B32_ND;
+            mbar_wait(smem_u32(&sm.bars.d_full1[ds]), (k / B32_ND) & 1);
+            tc_fence_after();
+            uint32_t v0[16], v1[16];
+            tmem_ld16(lane_base + B32_D1 + ds * 32, v0);
+            tmem_ld16(lane_base + B32_D1 + ds * 32 + 16, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.bars.d_empty[1][ds]));
+            asm volatile("cp.async.wait_group %0;" ::"n"(B32_NX - 1) : "memory");       // row k's pieces have landed
+            uint4 r[B32_CG];
+#pragma unroll
+            for (int c = 0; c < B32_CG; ++c)
+                r[c] = (lane_valid && 4 * c < NPAIR) ? *reinterpret_cast<const uint4*>(sm.x0_ring[k % B32_NX] + static_cast<size_t>(c * 128 + m) * 16)
+                                                     : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float2 x[8];
+                b32_bias16(half ? v1 : v0, sm.cst.b_c1 + 16 * half, x);
+                const uint4 r0 = r[2 * half], r1 = r[2 * half + 1];
+                x[0] = add2(x[0], unpack_h2(r0.x)); x[1] = add2(x[1], unpack_h2(r0.y));
+                x[2] = add2(x[2], unpack_h2(r0.z)); x[3] = add2(x[3], unpack_h2(r0.w));
+                x[4] = add2(x[4], unpack_h2(r1.x)); x[5] = add2(x[5], unpack_h2(r1.y));
+                x[6] = add2(x[6], unpack_h2(r1.z)); x[7] = add2(x[7], unpack_h2(r1.w));
+                if (lane_valid) {
+                    *reinterpret_cast<uint4*>(a.out + goff + (2 * half) * plane) = b32_pack8(x);
+                    *reinterpret_cast<uint4*>(a.out + goff + (2 * half + 1) * plane) = b32_pack8(x + 4);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == B32_WARP_MMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int g_b32_sms = 0;
+
+int resblock_stream32_launch(const void* u, B32Args& a, cudaStream_t stream) {
+    if (g_b32_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_b32_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_b32_sms <= 0) g_b32_sms = 148;
+    }
+    a.strips = (a.W + B32_VALID - 1) / B32_VALID;
+    // a segment of R rows costs ~R + 10 row times (4 halo rows + pipeline fill / drain): see block_stream.cu
+    static const int forced_rows = getenv("BNERV_BS_ROWS") ? atoi(getenv("BNERV_BS_ROWS")) : 0;
+    {
+        int best_segs = 1;
+        long long best_cost = -1;
+        const int max_segs = (a.H + 7) / 8;
+        for (int sg = 1; sg <= max_segs; ++sg) {
+            const int r = (a.H + sg - 1) / sg;
+            const int real = (a.H + r - 1) / r;
+            const long long ctas = 1LL * a.B * a.strips * real;
+            const long long waves = (ctas + g_b32_sms - 1) / g_b32_sms;
+            const long long cost = waves * (r + 10);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_segs = sg; }
+        }
+        int seg_rows = (a.H + best_segs - 1) / best_segs;
+        if (forced_rows > 0) seg_rows = forced_rows;
+        a.seg_rows = seg_rows;
+        a.segs = (a.H + seg_rows - 1) / seg_rows;
+    }
+    const long long grid = 1LL * a.B * a.strips * a.segs;
+    if (grid > 0x3fffffffLL) return set_error(BNERV_E_UNSUPPORTED, "resblock_stream: too many CTAs");
+
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return set_error(BNERV_E_NODRIVER, "cuTensorMapEncodeTiled entry point not available");
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {2ull * a.W, static_cast<cuuint64_t>(a.H), 1ull * B32_CG * a.B};
+    cuuint64_t strides[2] = {16ull * a.W, 16ull * a.W * a.H};
+    cuuint32_t box[3] = {256, 1, B32_CG};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(u), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(static_cast<int>(r), "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+
+    using KernelFn = void (*)(const CUtensorMap, const B32Args);
+    // whole dead channel pairs are skipped when the activation maps 0 to 0 (every block activation but OutImg's tanh01)
+    const int pairs = (a.act_inner == BNERV_ACT_TANH01) ? 16 : (a.C + 1) / 2;
+    const bool gelu = a.act_inner == BNERV_ACT_GELU;
+    KernelFn fn;
+    int slot;
+    if (pairs <= 11)      { fn = gelu ? resblock_stream32_kernel<BNERV_ACT_GELU, 11> : resblock_stream32_kernel<-1, 11>; slot = 0 + gelu; }
+    else if (pairs <= 12) { fn = gelu ? resblock_stream32_kernel<BNERV_ACT_GELU, 12> : resblock_stream32_kernel<-1, 12>; slot = 2 + gelu; }
+    else                  { fn = gelu ? resblock_stream32_kernel<BNERV_ACT_GELU, 16> : resblock_stream32_kernel<-1, 16>; slot = 4 + gelu; }
+    static bool attr_set[6][32] = {};
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    const size_t smem = sizeof(B32Smem) + 1024;
+    if (!attr_set[slot][cur_dev & 31]) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return set_error(static_cast<int>(e), "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+        attr_set[slot][cur_dev & 31] = true;
+    }
+    static const bool verbose = getenv("BNERV_BF_VERBOSE") != nullptr;
+    if (verbose)
+        fprintf(stderr, "resblock_stream32: %dx%d B=%d C=%d -> %d strips x %d segments of %d rows = %lld CTAs, smem %zu B\n",
+                a.H, a.W, a.B, a.C, a.strips, a.segs, a.seg_rows, grid, smem);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(B32_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("BNERV_NO_PDL") != nullptr;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, tm, a);
+    if (e != cudaSuccess) {
+        count_launch();
+        return set_error(static_cast<int>(e), "resblock_stream32_kernel launch: %s", cudaGetErrorString(e));
+    }
+    return check_launch("resblock_stream32_kernel");
+}
+
+// called by bnerv_resblock_stream (block_stream.cu) for 17..32 channels
+int resblock_stream32(const void* u, const void* x0, int B, int C, int H, int W, const void* w_c0, const float* b_c0,
+                      const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1, void* out,
+                      cudaStream_t stream) {
+    B32Args a{};
+    a.B = B; a.H = H; a.W = W; a.C = C; a.act_inner = act_inner;
+    a.w_c0 = static_cast<const __half*>(w_c0); a.w_c1 = static_cast<const __half*>(w_c1);
+    a.b_c0 = b_c0; a.b_c1 = b_c1; a.g1p = g1p; a.beta1 = beta1;
+    a.resid = static_cast<const __half*>(x0);
+    a.out = static_cast<__half*>(out);
+    return resblock_stream32_launch(u, a, stream);
+}
+
+}  // namespace bnerv

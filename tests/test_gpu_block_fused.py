@@ -108,6 +108,39 @@ def test_stream_block_is_bit_identical_to_three_launches(ops, case):
     assert out2 is not None and torch.equal(out2, ref)
 
 
+RES32_CASES = [  # B, C, H, W : ResBlock_SFT half, 17..32 channels (block_stream32.cu)
+    (1, 21, 64, 96),              # E-NeRV-M's 1080p stages: 21 channels, 11 live pairs
+    (1, 21, 135, 250),            # three strips (250 = 2 * 122 + 6), several row segments
+    (2, 21, 37, 51),              # B > 1, ragged
+    (1, 21, 5, 9),                # fewer rows than middle warpgroups
+    (1, 30, 45, 80),              # NeRV-S stage 0
+    (1, 24, 33, 123),             # 12 live pairs, one column more than a strip
+    (1, 32, 40, 122),             # all 32 channels, exactly one strip
+    (1, 17, 21, 30),
+    (1, 21, 270, 480),            # one CTA per SM and more
+]
+
+
+@pytest.mark.parametrize("case", RES32_CASES, ids=lambda c: "B%d_C%d_%dx%d" % c)
+@pytest.mark.parametrize("act", ["gelu", "relu"])
+def test_stream_resblock_32_channels_is_bit_identical_to_two_launches(ops, case, act):
+    B, C, H, W = case
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, B, C, C, H, W, 1)
+    mk = lambda: torch.empty(ops.c8_shape(B, C, H, W), dtype=torch.float16, device="cuda")
+    x0, u, wmap, ref = mk(), mk(), mk(), mk()
+    ops.conv_fused(x, up, C, H, W, act="sin", g1p=g0, beta=b0, out_pre=x0, out_aff=u)
+    ops.conv_fused(u, c0, C, H, W, act=act, g1p=g1, beta=b1, out_aff=wmap)
+    ops.conv_fused(wmap, c1, C, H, W, act="none", resid=x0, out_pre=ref)
+    out = ops.resblock_fused(u, x0, c0, c1, C, H, W, act, g1, b1, form="stream")
+    assert out is not None, "shape unexpectedly outside the streaming kernel's range"
+    torch.cuda.synchronize()
+    if not torch.equal(out, ref):
+        d = (out.float() - ref.float()).abs()
+        bad = d > 0
+        raise AssertionError(f"{int(bad.sum())} of {bad.numel()} values differ, max |diff| {d.max().item():.3e} "
+                             f"(max |ref| {ref.float().abs().max().item():.3e}); first [b, group, y, x, c]: {bad.nonzero()[:8].tolist()}")
+
+
 def test_stream_block_refuses_what_it_does_not_implement(ops):
     x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 12, 12, 20, 24, 3)           # PixelShuffle(3)
     assert ops.nerv_block_fused(x, up, c0, c1, 12, 20, 24, "sin", "gelu", g0, b0, g1, b1, form="stream") is None
