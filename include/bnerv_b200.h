@@ -159,8 +159,10 @@ int bnerv_resblock_fused(const void* u, const void* x0, int B, int C, int H, int
  * comes from TENSOR MEMORY - the threads that own a row's pixels write its "row-im2col" (3 horizontal taps x 16 channels)
  * into TMEM once, the vertical taps select among the A rows of a ring - instead of being re-read from shared memory nine
  * times (17.6 vs 50.4 cycles per N = 16 MMA, profiles/r02_ts_probe_umma_ts_vs_ss.txt).  Bit-identical to
- * bnerv_nerv_block_fwd.  Supported: k_up = 3, s = 1, C <= 16, Cin <= 16 (bnerv_resblock_stream: C <= 16);
- * anything else returns BNERV_E_UNSUPPORTED with nothing launched. */
+ * bnerv_nerv_block_fwd.  Supported: k_up = 3, s = 1 or 2 (PixelShuffle inside the kernel), C <= 16, Cin <= 16;
+ * bnerv_resblock_stream: C <= 32 (17..32 channels run the K = 32 form of block_stream32.cu: A rows of two K steps, the
+ * residual rows prefetched from global memory; E-NeRV-Boost M's 1080p stages).  Anything else returns BNERV_E_UNSUPPORTED
+ * with nothing launched. */
 int bnerv_nerv_block_stream(const void* x, int B, int Cin, int H, int W, const void* w_up, const float* b_up, int k_up,
                             int s, int act_up, const void* w_c0, const float* b_c0, const void* w_c1, const float* b_c1,
                             int C, int act_inner, const float* g0p, const float* beta0, const float* g1p,
