@@ -186,7 +186,12 @@ class DecoderEngine:
         self._sft = {}         # SftTable per B
         self._sft_key = None
         self._xy, self._xy_key = None, None     # E-NeRV: frame-independent half of the stem
-        self._front = {}       # NeRV: stem buffers per B
+        self._front = {}       # NeRV / E-NeRV: stem buffers per B
+        self._pe_same = False  # E-NeRV: pe_t and pe_t_manipulate are the same encoding (decided here, outside any graph capture)
+        if self.kind == "enerv":
+            pe, pe2 = model.pe_t, model.pe_t_manipulate
+            self._pe_same = ("pe" in getattr(pe, "pe_embed", "") and pe.pe_embed == pe2.pe_embed
+                             and torch.equal(pe.pe_bases.detach().cpu(), pe2.pe_bases.detach().cpu()))
         env = os.environ.get("BNERV_PRECISE_BLOCKS")
         if env:
             self.set_precise(env)
@@ -360,6 +365,32 @@ class DecoderEngine:
         ops.linear_pair([dict(x=h, w=w2, b=b2, act=a2, y=x, y_c8=x_c8, hw=hw), dict(x=ht, w=v2, b=c2, act=e2, y=t_embed)], B)
         return x.view(B, m.fc_dim, m.fc_h, m.fc_w), x_c8, t_embed
 
+    def _time_mlp_pair(self, t):
+        """E-NeRV's stem_t(pe_t(t)) and t_branch(pe_t_manipulate(t)) (model_enerv.py:283-286) through bnerv_pe_linear_pair +
+        bnerv_linear_pair when both are two-layer NeRV_MLPs over the same position encoding; None otherwise."""
+        m = self.model
+        pe, pe2 = m.pe_t, m.pe_t_manipulate
+        if os.environ.get("BNERV_NO_FRONT_FUSION") or not self._pe_same:
+            return None
+        a, c = self._mlp2(m.stem_t), self._mlp2(m.t_branch)
+        if a is None or c is None:
+            return None
+        B, dev = t.shape[0], t.device
+        (w1, b1, a1), (w2, b2, a2) = a
+        (v1, c1, e1), (v2, c2, e2) = c
+        if B * max(w1.shape[0], v1.shape[0], w1.shape[1]) * 4 > 48 * 1024:
+            return None
+        if pe.pe_bases.device != dev or pe.pe_bases.dtype != torch.float32:
+            pe.pe_bases = pe.pe_bases.to(dev, torch.float32)
+        bufs = self._front.get(B)
+        if bufs is None:
+            f32 = lambda n: torch.empty((B, n), dtype=torch.float32, device=dev)
+            bufs = self._front[B] = (f32(w1.shape[0]), f32(v1.shape[0]), f32(w2.shape[0]), f32(v2.shape[0]))
+        h, ht, t_emb, t_manip = bufs
+        ops.pe_linear_pair(t.float(), pe.pe_bases, [dict(w=w1, b=b1, act=a1, y=h), dict(w=v1, b=c1, act=e1, y=ht)])
+        ops.linear_pair([dict(x=h, w=w2, b=b2, act=a2, y=t_emb), dict(x=ht, w=v2, b=c2, act=e2, y=t_manip)], B)
+        return t_emb, t_manip
+
     def _enerv_stem(self, t):
         """ENeRV_Boost's stem (model_enerv.py:281-303) for the decode path.  Same values as model._stem(t), arranged for a
         per-frame decode: (i) the two time MLPs run on the f32 bnerv_linear_act kernel; (ii) the coordinate branch
@@ -369,9 +400,13 @@ class DecoderEngine:
         `t_manip` feeds every SFT layer of the cascade."""
         m = self.model
         b = t.size(0)
-        tt = t[:, None].float()
-        t_emb = self._mlp(m.stem_t, m.pe_t(tt).flatten(1).float())
-        t_manip = self._mlp(m.t_branch, m.pe_t_manipulate(tt).flatten(1).float())
+        pair = self._time_mlp_pair(t)
+        if pair is not None:                    # both time MLPs read the same position encoding: two launches for the lot
+            t_emb, t_manip = pair
+        else:
+            tt = t[:, None].float()
+            t_emb = self._mlp(m.stem_t, m.pe_t(tt).flatten(1).float())
+            t_manip = self._mlp(m.t_branch, m.pe_t_manipulate(tt).flatten(1).float())
         tf32 = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = False
         try:
