@@ -517,6 +517,13 @@ class DecoderEngine:
                 u = view(ws["u"], blk.cout, Ho, Wo)
                 ops.conv_fused(cur, blk.up.packed(), cin, H, W, act=blk.act, g1p=g0, beta=b0, out_pre=x0, out_aff=u)
                 if fuse is not None and (cp <= 16 or Ho * Wo >= 65536):      # the 32-channel form pays off on large maps only
+                    if (bi + 1 == nb and cp == 32 and fuse[0] == "stream" and self.head.head1 and keep is not True
+                            and blk.inner_act == "gelu" and not os.environ.get("BNERV_NO_HEAD_FUSION")):
+                        # last block: the 1x1 head conv + OutImg ride in the same kernel, the block output is never stored
+                        img = torch.empty((B, self.head.cout, Ho, Wo), dtype=torch.float32, device=dev)
+                        if ops.resblock_head_fused(u, x0, blk.c0.packed(), blk.c1.packed(), blk.cout, Ho, Wo, blk.inner_act, g1, b1,
+                                                   self.head.packed(), img) is not None:
+                            return img, outs
                     done = ops.resblock_fused(u, x0, blk.c0.packed(), blk.c1.packed(), blk.cout, Ho, Wo, blk.inner_act, g1, b1,
                                               out=out, form=fuse[0])
                 if done is None:

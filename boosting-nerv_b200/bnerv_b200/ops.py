@@ -296,6 +296,21 @@ def linear_pair(specs, B):
     check("bnerv_linear_pair", lib.bnerv_linear_pair(arr, B, _stream()))
 
 
+def resblock_head_fused(u_c8, x0_c8, c0, c1, C, H, W, act_inner, g1p, beta1, head, img, head_act="tanh01"):
+    """bnerv_resblock_stream_head: the last block's ResBlock_SFT half + the 1x1 head conv + OutImg in one kernel; `head` is a
+    PackedHead1, `img` the [B, Cout, H, W] f32 output.  None = unsupported shape (nothing launched)."""
+    _need_cuda(u_c8, x0_c8, img)
+    assert isinstance(head, PackedHead1) and head.cin == C and img.dtype == torch.float32 and img.is_contiguous()
+    B = u_c8.shape[0]
+    rc = lib.bnerv_resblock_stream_head(ptr(u_c8), ptr(x0_c8), B, C, H, W, ptr(c0.w), ptr(c0.b), ptr(c1.w), ptr(c1.b),
+                                        ACT_CODES[act_inner], ptr(g1p), ptr(beta1), ptr(head.w), ptr(head.b), head.cout,
+                                        ACT_CODES[head_act], ptr(img), _stream())
+    if rc == _capi.E_UNSUPPORTED:
+        return None
+    check("bnerv_resblock_stream_head", rc)
+    return img
+
+
 class SftTable:
     """Device-side array of bnerv_sft_layer descriptors + the g1p/beta output tables for a batch size."""
 

@@ -661,7 +661,7 @@ static int bs_launch(const void* x_in, BsArgs& a, cudaStream_t stream) {
 // 17..32 channels: block_stream32.cu
 int resblock_stream32(const void* u, const void* x0, int B, int C, int H, int W, const void* w_c0, const float* b_c0,
                       const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1, void* out,
-                      cudaStream_t stream);
+                      const float* head_w, const float* head_b, int head_cout, int head_act, float* img, cudaStream_t stream);
 
 }  // namespace bnerv
 
@@ -701,7 +701,8 @@ extern "C" int bnerv_resblock_stream(const void* u, const void* x0, int B, int C
                                reinterpret_cast<uintptr_t>(w_c1) | reinterpret_cast<uintptr_t>(out);
     if (align_or & 15) return set_error(BNERV_E_BADARG, "resblock_stream: pointers must be 16-byte aligned");
     if (C > 16)
-        return resblock_stream32(u, x0, B, C, H, W, w_c0, b_c0, w_c1, b_c1, act_inner, g1p, beta1, out, static_cast<cudaStream_t>(stream));
+        return resblock_stream32(u, x0, B, C, H, W, w_c0, b_c0, w_c1, b_c1, act_inner, g1p, beta1, out, nullptr, nullptr, 0, 0, nullptr,
+                                 static_cast<cudaStream_t>(stream));
     BsArgs a{};
     a.B = B; a.H = H; a.W = W; a.C = C; a.s = 1; a.has_up = 0; a.act_up = BNERV_ACT_NONE; a.act_inner = act_inner;
     a.w_c0 = static_cast<const __half*>(w_c0); a.w_c1 = static_cast<const __half*>(w_c1);
@@ -710,4 +711,21 @@ extern "C" int bnerv_resblock_stream(const void* u, const void* x0, int B, int C
     a.resid = static_cast<const __half*>(x0);
     a.out = static_cast<__half*>(out);
     return bs_launch(u, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bnerv_resblock_stream_head(const void* u, const void* x0, int B, int C, int H, int W, const void* w_c0, const float* b_c0,
+                                          const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1,
+                                          const float* head_w, const float* head_b, int head_cout, int head_act, float* img,
+                                          void* stream) {
+    if (!u || !x0 || !w_c0 || !b_c0 || !w_c1 || !b_c1 || !g1p || !beta1 || !head_w || !img) return set_error(BNERV_E_BADARG, "resblock_stream_head: null pointer");
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return set_error(BNERV_E_BADARG, "resblock_stream_head: non-positive size");
+    if (C <= 16 || C > 32) return set_error(BNERV_E_UNSUPPORTED, "resblock_stream_head: C = %d (17..32 channels)", C);
+    if (head_cout < 1 || head_cout > 4) return set_error(BNERV_E_UNSUPPORTED, "resblock_stream_head: %d head channels (1..4)", head_cout);
+    if (act_inner < BNERV_ACT_NONE || act_inner > BNERV_ACT_TANH01 || head_act < BNERV_ACT_NONE || head_act > BNERV_ACT_TANH01)
+        return set_error(BNERV_E_UNSUPPORTED, "resblock_stream_head: activation code");
+    const uintptr_t align_or = reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(w_c0) |
+                               reinterpret_cast<uintptr_t>(w_c1);
+    if (align_or & 15) return set_error(BNERV_E_BADARG, "resblock_stream_head: pointers must be 16-byte aligned");
+    return resblock_stream32(u, x0, B, C, H, W, w_c0, b_c0, w_c1, b_c1, act_inner, g1p, beta1, nullptr, head_w, head_b, head_cout,
+                             head_act, img, static_cast<cudaStream_t>(stream));
 }

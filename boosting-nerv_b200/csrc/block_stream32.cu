@@ -50,7 +50,7 @@ constexpr int B32_ROW_B = B32_CG * 128 * 16;  // one input row in shared memory:
 constexpr int B32_XROW_B = B32_CG * 130 * 16; // one exchange row: [4 groups][130 px][16 B] (px 0 and 129 stay zero)
 constexpr int B32_W_B = 9 * B32_CG * 32 * 16; // one conv's weights: [tap][4 groups][32 rows][16 B]
 
-struct B32Cst { float b_c0[32], b_c1[32], g1p[32], beta1[32]; };
+struct B32Cst { float b_c0[32], b_c1[32], g1p[32], beta1[32]; float head_w[4][32], head_b[4]; };
 
 struct B32Bars {
     uint64_t in_full[B32_NI], in_empty[B32_NI];
@@ -78,6 +78,10 @@ struct B32Args {
     const float *b_c0, *b_c1, *g1p, *beta1;
     const __half* resid;
     __half* out;
+    // fused 1x1 head conv + OutImg (HEAD instantiations): img = act(head_w . f16(out) + head_b), NCHW f32; `out` is not stored
+    const float *head_w, *head_b;
+    float* img;
+    int head_cout, head_act;
 };
 
 __device__ __forceinline__ void b32_tmem_st8(uint32_t taddr, const uint4& lo, const uint4& hi) {
@@ -134,7 +138,7 @@ __device__ __forceinline__ void b32_affine8(const float2* x, const float* g, con
 // NPAIR: channel pairs that carry data (11: C <= 22, 12: C <= 24, 16: all).  A pad channel's conv0 output is exactly 0 (zero
 // weight rows, zero bias) and every block activation maps 0 to 0, so a skipped pair is set to the 0 it would have computed and
 // goes through the same affine; conv1 has zero weights for pad input channels either way.
-template <int ACT_IN, int NPAIR>
+template <int ACT_IN, int NPAIR, bool HEAD>
 __global__ void __launch_bounds__(B32_THREADS, 1)
 resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -179,6 +183,11 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
     if (threadIdx.x < 32) {
         sm.cst.b_c0[threadIdx.x] = __ldg(a.b_c0 + threadIdx.x);
         sm.cst.b_c1[threadIdx.x] = __ldg(a.b_c1 + threadIdx.x);
+    }
+    if (HEAD && threadIdx.x < 128) {                 // head weights [Cout][C] -> [4][32], zero beyond (Cout, C)
+        const int c = threadIdx.x >> 5, k = threadIdx.x & 31;
+        sm.cst.head_w[c][k] = (c < a.head_cout && k < a.C) ? __ldg(a.head_w + c * a.C + k) : 0.0f;
+        if (k == 0) sm.cst.head_b[c] = (c < a.head_cout && a.head_b) ? __ldg(a.head_b + c) : 0.0f;
     }
     for (int i = threadIdx.x; i < static_cast<int>(sizeof(sm.w_ring) / 16); i += B32_THREADS)      // exchange rows: the edge pixels stay zero
         reinterpret_cast<uint4*>(sm.w_ring)[i] = make_uint4(0, 0, 0, 0);
@@ -357,6 +366,11 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
             for (int c = 0; c < B32_CG; ++c)
                 r[c] = (lane_valid && 4 * c < NPAIR) ? *reinterpret_cast<const uint4*>(sm.x0_ring[k % B32_NX] + static_cast<size_t>(c * 128 + m) * 16)
                                                      : make_uint4(0, 0, 0, 0);
+            float hacc[4];
+            if (HEAD) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) hacc[c] = sm.cst.head_b[c];
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float2 x[8];
@@ -366,10 +380,36 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
                 x[2] = add2(x[2], unpack_h2(r0.z)); x[3] = add2(x[3], unpack_h2(r0.w));
                 x[4] = add2(x[4], unpack_h2(r1.x)); x[5] = add2(x[5], unpack_h2(r1.y));
                 x[6] = add2(x[6], unpack_h2(r1.z)); x[7] = add2(x[7], unpack_h2(r1.w));
-                if (lane_valid) {
-                    *reinterpret_cast<uint4*>(a.out + goff + (2 * half) * plane) = b32_pack8(x);
-                    *reinterpret_cast<uint4*>(a.out + goff + (2 * half + 1) * plane) = b32_pack8(x + 4);
+                const uint4 o0 = b32_pack8(x), o1 = b32_pack8(x + 4);
+                if (!HEAD) {
+                    if (lane_valid) {
+                        *reinterpret_cast<uint4*>(a.out + goff + (2 * half) * plane) = o0;
+                        *reinterpret_cast<uint4*>(a.out + goff + (2 * half + 1) * plane) = o1;
+                    }
+                } else {
+                    // bnerv_head_conv1's arithmetic on the f16 values the map would have held: bias first, then one FMA per
+                    // channel in channel order -> the image is bit-identical to the separate head launch
+                    const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        if (half * 8 + p < NPAIR) {
+                            const float2 v = unpack_h2(ow[p]);
+                            const int k = half * 16 + 2 * p;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                hacc[c] = fmaf(v.x, sm.cst.head_w[c][k], hacc[c]);
+                                hacc[c] = fmaf(v.y, sm.cst.head_w[c][k + 1], hacc[c]);
+                            }
+                        }
+                    }
                 }
+            }
+            if (HEAD && lane_valid) {
+                const size_t hw = static_cast<size_t>(a.H) * a.W;
+                const size_t pix = static_cast<size_t>(h) * a.W + col;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < a.head_cout) a.img[(static_cast<size_t>(fb) * a.head_cout + c) * hw + pix] = apply_act(hacc[c], a.head_act);
             }
         }
     }
@@ -435,10 +475,17 @@ int resblock_stream32_launch(const void* u, B32Args& a, cudaStream_t stream) {
     const bool gelu = a.act_inner == BNERV_ACT_GELU;
     KernelFn fn;
     int slot;
-    if (pairs <= 11)      { fn = gelu ? resblock_stream32_kernel<BNERV_ACT_GELU, 11> : resblock_stream32_kernel<-1, 11>; slot = 0 + gelu; }
-    else if (pairs <= 12) { fn = gelu ? resblock_stream32_kernel<BNERV_ACT_GELU, 12> : resblock_stream32_kernel<-1, 12>; slot = 2 + gelu; }
-    else                  { fn = gelu ? resblock_stream32_kernel<BNERV_ACT_GELU, 16> : resblock_stream32_kernel<-1, 16>; slot = 4 + gelu; }
-    static bool attr_set[6][32] = {};
+    const bool head = a.img != nullptr;
+    if (pairs <= 11)      { fn = gelu ? resblock_stream32_kernel<BNERV_ACT_GELU, 11, false> : resblock_stream32_kernel<-1, 11, false>; slot = 0 + gelu; }
+    else if (pairs <= 12) { fn = gelu ? resblock_stream32_kernel<BNERV_ACT_GELU, 12, false> : resblock_stream32_kernel<-1, 12, false>; slot = 2 + gelu; }
+    else                  { fn = gelu ? resblock_stream32_kernel<BNERV_ACT_GELU, 16, false> : resblock_stream32_kernel<-1, 16, false>; slot = 4 + gelu; }
+    if (head) {           // + 1x1 head conv + OutImg in the back warpgroup (GELU blocks: every shipped preset)
+        if (!gelu) return set_error(BNERV_E_UNSUPPORTED, "resblock_stream_head: inner activation %d (GELU only)", a.act_inner);
+        if (pairs <= 11)      { fn = resblock_stream32_kernel<BNERV_ACT_GELU, 11, true>; slot = 6; }
+        else if (pairs <= 12) { fn = resblock_stream32_kernel<BNERV_ACT_GELU, 12, true>; slot = 7; }
+        else                  { fn = resblock_stream32_kernel<BNERV_ACT_GELU, 16, true>; slot = 8; }
+    }
+    static bool attr_set[9][32] = {};
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     const size_t smem = sizeof(B32Smem) + 1024;
@@ -473,8 +520,9 @@ int resblock_stream32_launch(const void* u, B32Args& a, cudaStream_t stream) {
 // called by bnerv_resblock_stream (block_stream.cu) for 17..32 channels
 int resblock_stream32(const void* u, const void* x0, int B, int C, int H, int W, const void* w_c0, const float* b_c0,
                       const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1, void* out,
-                      cudaStream_t stream) {
+                      const float* head_w, const float* head_b, int head_cout, int head_act, float* img, cudaStream_t stream) {
     B32Args a{};
+    a.head_w = head_w; a.head_b = head_b; a.head_cout = head_cout; a.head_act = head_act; a.img = img;
     a.B = B; a.H = H; a.W = W; a.C = C; a.act_inner = act_inner;
     a.w_c0 = static_cast<const __half*>(w_c0); a.w_c1 = static_cast<const __half*>(w_c1);
     a.b_c0 = b_c0; a.b_c1 = b_c1; a.g1p = g1p; a.beta1 = beta1;

@@ -171,6 +171,14 @@ int bnerv_resblock_stream(const void* u, const void* x0, int B, int C, int H, in
                           const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1,
                           void* out, void* stream);
 
+/* bnerv_resblock_stream (17..32 channels) with the model's 1x1 head conv and OutImg (model_enerv.py:311-313 / model_nerv.py:56-57,
+ * model_blocks.py:57-63) folded into the last warpgroup: img[b][c][h][w] = act(head_b[c] + sum_k head_w[c][k] * f16(out[k])), f32
+ * NCHW, head_w = the raw f32 [head_cout][C] weights, head_cout <= 4.  The block output is not stored (it would be written once
+ * and read once by bnerv_head_conv1); the image is bit-identical to that two-launch sequence.  act_inner must be GELU. */
+int bnerv_resblock_stream_head(const void* u, const void* x0, int B, int C, int H, int W, const void* w_c0, const float* b_c0,
+                               const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1,
+                               const float* head_w, const float* head_b, int head_cout, int head_act, float* img, void* stream);
+
 /* Bring-up instrumentation for the fused-block kernel: device buffer of n_ctas*4*12 int64 receiving clock64 phase stamps of
  * the first 4 regions of the first n_ctas CTAs of subsequent launches (slot 11 = SM id); NULL switches it off. */
 int bnerv_debug_set_buffer(void* buf, int n_ctas);

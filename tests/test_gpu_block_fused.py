@@ -141,6 +141,31 @@ def test_stream_resblock_32_channels_is_bit_identical_to_two_launches(ops, case,
                              f"(max |ref| {ref.float().abs().max().item():.3e}); first [b, group, y, x, c]: {bad.nonzero()[:8].tolist()}")
 
 
+@pytest.mark.parametrize("case", [(1, 21, 64, 96, 3), (2, 21, 37, 131, 3), (1, 30, 45, 80, 3), (1, 32, 20, 122, 4), (1, 24, 9, 250, 1)],
+                         ids=lambda c: "B%d_C%d_%dx%d_head%d" % c)
+def test_stream_resblock_with_fused_head_gives_the_two_launch_image_bit_for_bit(ops, case):
+    """bnerv_resblock_stream_head: ResBlock_SFT half + 1x1 head conv + OutImg in one kernel against bnerv_resblock_stream followed
+    by bnerv_head_conv1 - the image must be identical (same f16 rounding of the block output, same FMA order in the head)."""
+    B, C, H, W, cout = case
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, B, C, C, H, W, 1)
+    mk = lambda: torch.empty(ops.c8_shape(B, C, H, W), dtype=torch.float16, device="cuda")
+    x0, u = mk(), mk()
+    ops.conv_fused(x, up, C, H, W, act="sin", g1p=g0, beta=b0, out_pre=x0, out_aff=u)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    head = ops.PackedHead1(torch.randn(cout, C, 1, 1, device="cuda", generator=gen) / C ** 0.5, torch.randn(cout, device="cuda", generator=gen) * 0.1)
+    out = ops.resblock_fused(u, x0, c0, c1, C, H, W, "gelu", g1, b1, form="stream")
+    ref = torch.empty(B, cout, H, W, device="cuda")
+    ops.conv_fused(out, head, C, H, W, act="tanh01", out_nchw=ref)
+    img = torch.full_like(ref, float("nan"))
+    assert ops.resblock_head_fused(u, x0, c0, c1, C, H, W, "gelu", g1, b1, head, img) is not None
+    torch.cuda.synchronize()
+    assert torch.equal(img, ref), f"max |diff| {(img - ref).abs().max().item():.3e}"
+    small = ops.PackedHead1(torch.zeros(3, 12, 1, 1, device="cuda"), None)
+    x12, up12, c012, c112, (_, _, g12, b12) = make_block(ops, 1, 12, 12, 16, 16, 1)
+    u12 = torch.zeros(ops.c8_shape(1, 12, 16, 16), dtype=torch.float16, device="cuda")
+    assert ops.resblock_head_fused(u12, u12, c012, c112, 12, 16, 16, "gelu", g12, b12, small, torch.zeros(1, 3, 16, 16, device="cuda")) is None
+
+
 def test_stream_block_refuses_what_it_does_not_implement(ops):
     x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 12, 12, 20, 24, 3)           # PixelShuffle(3)
     assert ops.nerv_block_fused(x, up, c0, c1, 12, 20, 24, "sin", "gelu", g0, b0, g1, b1, form="stream") is None
