@@ -509,6 +509,14 @@ class DecoderEngine:
                 ops.conv_fused(wbuf, blk.c1.packed(split_in=True), 3 * cp, Ho, Wo, act="none", resid=x0, out_pre=out,
                                split=2 | (1 if out_split else 0))
                 done = True
+            # (bnerv_nerv_block_stream_head - the last NeRV-Boost block with the 1x1 head inside - exists and is bit-identical, but its
+            #  single back warpgroup becomes the critical stage: NeRV-S 5056 -> 4961 frames/s.  BNERV_HEAD_FUSION16=1 selects it.)
+            if (fuse is not None and fuse == ("stream", "block") and bi + 1 == nb and self.head.head1 and keep is not True
+                    and blk.up.s == 1 and blk.act == "sin" and blk.inner_act == "gelu" and os.environ.get("BNERV_HEAD_FUSION16")):
+                img = torch.empty((B, self.head.cout, Ho, Wo), dtype=torch.float32, device=dev)
+                if ops.nerv_block_head_fused(cur, blk.up.packed(), blk.c0.packed(), blk.c1.packed(), cin, H, W, g0, b0, g1, b1,
+                                             self.head.packed(), img) is not None:
+                    return img, outs
             if fuse is not None and fuse[1] == "block":
                 done = ops.nerv_block_fused(cur, blk.up.packed(), blk.c0.packed(), blk.c1.packed(), cin, H, W, blk.act,
                                             blk.inner_act, g0, b0, g1, b1, out=out, form=fuse[0])

@@ -311,6 +311,23 @@ def resblock_head_fused(u_c8, x0_c8, c0, c1, C, H, W, act_inner, g1p, beta1, hea
     return img
 
 
+def nerv_block_head_fused(x_c8, up, c0, c1, cin, H, W, g0p, beta0, g1p, beta1, head, img, head_act="tanh01"):
+    """bnerv_nerv_block_stream_head: a whole sin / GELU NeRVBlock (3x3 up-conv, no PixelShuffle, <= 16 channels) + the 1x1 head
+    conv + OutImg in one kernel.  None = unsupported shape (nothing launched)."""
+    _need_cuda(x_c8, img)
+    assert isinstance(head, PackedHead1) and head.cin == up.cout and img.dtype == torch.float32 and img.is_contiguous()
+    if up.k != 3 or up.s != 1:
+        return None
+    B = x_c8.shape[0]
+    rc = lib.bnerv_nerv_block_stream_head(ptr(x_c8), B, cin, H, W, ptr(up.w), ptr(up.b), ptr(c0.w), ptr(c0.b), ptr(c1.w), ptr(c1.b),
+                                          up.cout, ptr(g0p), ptr(beta0), ptr(g1p), ptr(beta1), ptr(head.w), ptr(head.b), head.cout,
+                                          ACT_CODES[head_act], ptr(img), _stream())
+    if rc == _capi.E_UNSUPPORTED:
+        return None
+    check("bnerv_nerv_block_stream_head", rc)
+    return img
+
+
 class SftTable:
     """Device-side array of bnerv_sft_layer descriptors + the g1p/beta output tables for a batch size."""
 

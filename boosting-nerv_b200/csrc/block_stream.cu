@@ -69,7 +69,7 @@ template <bool S2> struct BsRing {
 constexpr int BS_ROW_B = 2 * 128 * 16;        // one input row in shared memory: [2 groups][128 px][16 B]
 constexpr int BS_XROW_B = 2 * 130 * 16;       // one exchange row: [2 groups][130 px][16 B] (px 0 and 129 stay zero)
 
-struct BsCst { float b_up[64], b_c0[16], b_c1[16], g0p[16], beta0[16], g1p[16], beta1[16]; };
+struct BsCst { float b_up[64], b_c0[16], b_c1[16], g0p[16], beta0[16], g1p[16], beta1[16]; float head_w[4][16], head_b[4]; };
 
 struct BsBars {
     uint64_t in_full[BS_NI], in_empty[BS_NI];
@@ -101,6 +101,10 @@ struct BsArgs {
     const __half* resid;
     __half* out;
     long long* dbg;              // bring-up: CTA 0 records clock64 stamps [role < 9][iteration < 32][4] (bnerv_debug_set_buffer)
+    // fused 1x1 head conv + OutImg (HEAD instantiations): img = act(head_w . f16(out) + head_b), NCHW f32; `out` is not stored
+    const float *head_w, *head_b;
+    float* img;
+    int head_cout, head_act;
 };
 
 #define BS_STAMP(role, it, k) do { if (DBG && a.dbg && blockIdx.x == 0 && (threadIdx.x & 127) == 0 && (it) < 32) \
@@ -172,7 +176,7 @@ __device__ __forceinline__ void bs_stage_weights(uint8_t* dst, const __half* src
 // NP: float2 channel pairs that carry data (6 when C <= 12: the 4 pad channels are exact zeros through sin / GELU / ReLU and
 // are not evaluated); DBG: records BS_STAMPs.
 // S2: the up-conv carries PixelShuffle(2) - it runs on input rows (half resolution), see the front warpgroups.
-template <int ACT_UP, int ACT_IN, int NP, bool DBG, bool S2>
+template <int ACT_UP, int ACT_IN, int NP, bool DBG, bool S2, bool HEAD = false>
 __global__ void __launch_bounds__(BS_THREADS, 1)
 block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -235,6 +239,11 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
             sm.cst.b_c0[i] = __ldg(a.b_c0 + i);
             sm.cst.b_c1[i] = __ldg(a.b_c1 + i);
         }
+    }
+    if (HEAD && threadIdx.x >= 64 && threadIdx.x < 128) {        // head weights [Cout][C] -> [4][16], zero beyond (Cout, C)
+        const int c = (threadIdx.x - 64) >> 4, k = threadIdx.x & 15;
+        sm.cst.head_w[c][k] = (c < a.head_cout && k < a.C) ? __ldg(a.head_w + c * a.C + k) : 0.0f;
+        if (k == 0) sm.cst.head_b[c] = (c < a.head_cout && a.head_b) ? __ldg(a.head_b + c) : 0.0f;
     }
     for (int i = threadIdx.x; i < static_cast<int>(sizeof(sm.u_ring) / 16); i += BS_THREADS)      // exchange rows: the edge pixels stay zero
         reinterpret_cast<uint4*>(sm.u_ring)[i] = make_uint4(0, 0, 0, 0);
@@ -547,9 +556,35 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
             x[2] = add2(x[2], unpack_h2(r0.z)); x[3] = add2(x[3], unpack_h2(r0.w));
             x[4] = add2(x[4], unpack_h2(r1.x)); x[5] = add2(x[5], unpack_h2(r1.y));
             x[6] = add2(x[6], unpack_h2(r1.z)); x[7] = add2(x[7], unpack_h2(r1.w));
-            if (lane_valid) {
-                *reinterpret_cast<uint4*>(a.out + goff) = bs_pack8(x);
-                *reinterpret_cast<uint4*>(a.out + goff + plane) = bs_pack8(x + 4);
+            if (!HEAD) {
+                if (lane_valid) {
+                    *reinterpret_cast<uint4*>(a.out + goff) = bs_pack8(x);
+                    *reinterpret_cast<uint4*>(a.out + goff + plane) = bs_pack8(x + 4);
+                }
+            } else if (lane_valid) {
+                // bnerv_head_conv1's arithmetic on the f16 values the map would have held (bias, then one FMA per channel in
+                // channel order): the image is bit-identical to the separate head launch
+                const uint4 o0 = bs_pack8(x), o1 = bs_pack8(x + 4);
+                const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+                float hacc[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) hacc[c] = sm.cst.head_b[c];
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    if (p < NP) {
+                        const float2 v = unpack_h2(ow[p]);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            hacc[c] = fmaf(v.x, sm.cst.head_w[c][2 * p], hacc[c]);
+                            hacc[c] = fmaf(v.y, sm.cst.head_w[c][2 * p + 1], hacc[c]);
+                        }
+                    }
+                }
+                const size_t hw = static_cast<size_t>(a.H) * a.W;
+                const size_t pix = static_cast<size_t>(h) * a.W + col;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < a.head_cout) a.img[(static_cast<size_t>(fb) * a.head_cout + c) * hw + pix] = apply_act(hacc[c], a.head_act);
             }
             BS_STAMP(wg, k, 3);
         }
@@ -621,12 +656,17 @@ static int bs_launch(const void* x_in, BsArgs& a, cudaStream_t stream) {
     const bool s2 = a.has_up && a.s == 2;
     KernelFn fn;
     int slot;
-    if (a.dbg && !s2) { fn = block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 6, true, false>; slot = 8; }     // bring-up stamps: the 12-channel sin/GELU form
+    if (a.dbg && !s2 && !a.img) { fn = block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 6, true, false>; slot = 8; }     // bring-up stamps: the 12-channel sin/GELU form
     else if (spec && np6) { fn = s2 ? block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 6, false, true> : block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 6, false, false>; slot = 0 + s2; }
     else if (spec) { fn = s2 ? block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 8, false, true> : block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 8, false, false>; slot = 2 + s2; }
     else if (np6) { fn = s2 ? block_stream_kernel<-1, -1, 6, false, true> : block_stream_kernel<-1, -1, 6, false, false>; slot = 4 + s2; }
     else { fn = s2 ? block_stream_kernel<-1, -1, 8, false, true> : block_stream_kernel<-1, -1, 8, false, false>; slot = 6 + s2; }
-    static bool attr_set[9][32] = {};
+    if (a.img) {          // + 1x1 head conv + OutImg in the back warpgroup: the sin / GELU, s = 1 forms (the last block of NeRV-Boost)
+        if (!spec || s2) return set_error(BNERV_E_UNSUPPORTED, "block_stream_head: only the sin / GELU, s = 1 form");
+        if (np6) { fn = block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 6, false, false, true>; slot = 9; }
+        else     { fn = block_stream_kernel<BNERV_ACT_SIN, BNERV_ACT_GELU, 8, false, false, true>; slot = 10; }
+    }
+    static bool attr_set[11][32] = {};
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     const size_t smem = sizeof(BsSmem) + 1024;
@@ -728,4 +768,27 @@ extern "C" int bnerv_resblock_stream_head(const void* u, const void* x0, int B, 
     if (align_or & 15) return set_error(BNERV_E_BADARG, "resblock_stream_head: pointers must be 16-byte aligned");
     return resblock_stream32(u, x0, B, C, H, W, w_c0, b_c0, w_c1, b_c1, act_inner, g1p, beta1, nullptr, head_w, head_b, head_cout,
                              head_act, img, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bnerv_nerv_block_stream_head(const void* x, int B, int Cin, int H, int W, const void* w_up, const float* b_up,
+                                            const void* w_c0, const float* b_c0, const void* w_c1, const float* b_c1, int C,
+                                            const float* g0p, const float* beta0, const float* g1p, const float* beta1,
+                                            const float* head_w, const float* head_b, int head_cout, int head_act, float* img,
+                                            void* stream) {
+    if (!x || !w_up || !b_up || !w_c0 || !b_c0 || !w_c1 || !b_c1 || !head_w || !img) return set_error(BNERV_E_BADARG, "nerv_block_stream_head: null pointer");
+    if (!g0p || !beta0 || !g1p || !beta1) return set_error(BNERV_E_BADARG, "nerv_block_stream_head: the four TAT tables are required");
+    if (B <= 0 || Cin <= 0 || C <= 0 || H <= 0 || W <= 0) return set_error(BNERV_E_BADARG, "nerv_block_stream_head: non-positive size");
+    if (C > 16 || Cin > 16) return set_error(BNERV_E_UNSUPPORTED, "nerv_block_stream_head: C = %d / Cin = %d (at most 16 channels)", C, Cin);
+    if (head_cout < 1 || head_cout > 4) return set_error(BNERV_E_UNSUPPORTED, "nerv_block_stream_head: %d head channels (1..4)", head_cout);
+    if (head_act < BNERV_ACT_NONE || head_act > BNERV_ACT_TANH01) return set_error(BNERV_E_UNSUPPORTED, "nerv_block_stream_head: activation code");
+    const uintptr_t align_or = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_up) | reinterpret_cast<uintptr_t>(w_c0) |
+                               reinterpret_cast<uintptr_t>(w_c1);
+    if (align_or & 15) return set_error(BNERV_E_BADARG, "nerv_block_stream_head: pointers must be 16-byte aligned");
+    BsArgs a{};
+    a.B = B; a.H = H; a.W = W; a.C = C; a.s = 1; a.has_up = 1; a.act_up = BNERV_ACT_SIN; a.act_inner = BNERV_ACT_GELU;
+    a.w_up = static_cast<const __half*>(w_up); a.w_c0 = static_cast<const __half*>(w_c0); a.w_c1 = static_cast<const __half*>(w_c1);
+    a.b_up = b_up; a.b_c0 = b_c0; a.b_c1 = b_c1;
+    a.g0p = g0p; a.beta0 = beta0; a.g1p = g1p; a.beta1 = beta1;
+    a.head_w = head_w; a.head_b = head_b; a.head_cout = head_cout; a.head_act = head_act; a.img = img;
+    return bs_launch(x, a, static_cast<cudaStream_t>(stream));
 }

@@ -179,6 +179,15 @@ int bnerv_resblock_stream_head(const void* u, const void* x0, int B, int C, int 
                                const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1,
                                const float* head_w, const float* head_b, int head_cout, int head_act, float* img, void* stream);
 
+/* The same for a whole 12..16-channel NeRVBlock (3x3 up-conv without PixelShuffle, sin, GELU: the last block of NeRV-Boost,
+ * model_nerv.py:53-57): bnerv_nerv_block_stream + the 1x1 head conv + OutImg, one kernel from the block input to the image.
+ * Bit-identical to the two launches; measured 2 % SLOWER in a NeRV-S frame (the one back warpgroup becomes the critical stage of
+ * the 720p block), so the engine keeps the separate head launch for <= 16 channels. */
+int bnerv_nerv_block_stream_head(const void* x, int B, int Cin, int H, int W, const void* w_up, const float* b_up,
+                                 const void* w_c0, const float* b_c0, const void* w_c1, const float* b_c1, int C,
+                                 const float* g0p, const float* beta0, const float* g1p, const float* beta1,
+                                 const float* head_w, const float* head_b, int head_cout, int head_act, float* img, void* stream);
+
 /* Bring-up instrumentation for the fused-block kernel: device buffer of n_ctas*4*12 int64 receiving clock64 phase stamps of
  * the first 4 regions of the first n_ctas CTAs of subsequent launches (slot 11 = SM id); NULL switches it off. */
 int bnerv_debug_set_buffer(void* buf, int n_ctas);

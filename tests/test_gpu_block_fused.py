@@ -166,6 +166,24 @@ def test_stream_resblock_with_fused_head_gives_the_two_launch_image_bit_for_bit(
     assert ops.resblock_head_fused(u12, u12, c012, c112, 12, 16, 16, "gelu", g12, b12, small, torch.zeros(1, 3, 16, 16, device="cuda")) is None
 
 
+@pytest.mark.parametrize("case", [(1, 12, 12, 64, 96, 3), (2, 12, 12, 37, 131, 3), (1, 15, 15, 20, 28, 3), (1, 16, 16, 33, 123, 4),
+                                  (1, 9, 12, 180, 320, 1)], ids=lambda c: "B%d_%dto%d_%dx%d_head%d" % c)
+def test_stream_block_with_fused_head_gives_the_two_launch_image_bit_for_bit(ops, case):
+    """bnerv_nerv_block_stream_head (a whole NeRVBlock + 1x1 head conv + OutImg, the tail of a NeRV-Boost frame) against
+    bnerv_nerv_block_stream followed by bnerv_head_conv1: identical image."""
+    B, cin, C, H, W, cout = case
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, B, cin, C, H, W, 1)
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    head = ops.PackedHead1(torch.randn(cout, C, 1, 1, device="cuda", generator=gen) / C ** 0.5, torch.randn(cout, device="cuda", generator=gen) * 0.1)
+    out = ops.nerv_block_fused(x, up, c0, c1, cin, H, W, "sin", "gelu", g0, b0, g1, b1, form="stream")
+    ref = torch.empty(B, cout, H, W, device="cuda")
+    ops.conv_fused(out, head, C, H, W, act="tanh01", out_nchw=ref)
+    img = torch.full_like(ref, float("nan"))
+    assert ops.nerv_block_head_fused(x, up, c0, c1, cin, H, W, g0, b0, g1, b1, head, img) is not None
+    torch.cuda.synchronize()
+    assert torch.equal(img, ref), f"max |diff| {(img - ref).abs().max().item():.3e}"
+
+
 def test_stream_block_refuses_what_it_does_not_implement(ops):
     x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 12, 12, 20, 24, 3)           # PixelShuffle(3)
     assert ops.nerv_block_fused(x, up, c0, c1, 12, 20, 24, "sin", "gelu", g0, b0, g1, b1, form="stream") is None
