@@ -8,7 +8,7 @@
 //     TMA warp    : u rows -> shared-memory ring (6 slots)
 //     front  WG   : builds A_c0(h) from the u rows
 //     middle WGs  : 4; epilogue of D_c0(h): w = act(. + b0)*g1p + beta1 -> exchange row in shared memory -> builds A_c1(h)
-//     back   WG   : epilogue of D_c1(h): out = . + b1 + x0 (x0 read from global) -> global
+//     back   WGs  : 2 (one per accumulator slot); epilogue of D_c1(h): out = . + b1 + x0 (x0 prefetched from global) -> global
 //     MMA warps   : one issuer per conv; per output row 3 ring rows x 3 shifts x 2 K steps = 18 MMAs (M = 128, N = 32, K = 16)
 //
 // One thing differs from block_stream.cu: the two accumulator slots of conv0 are shared by FOUR consumer warpgroups.  A
@@ -35,8 +35,9 @@ PFN_encodeTiled get_encode_tiled();          // conv_tc.cu
 
 constexpr int B32_CG = 4;                     // channel groups of 8 (Cp = 32)
 constexpr int B32_WG_M = 4;                   // middle warpgroups
-constexpr int B32_WARP_M = 4, B32_WARP_B = 4 + 4 * B32_WG_M, B32_WARP_MMA = B32_WARP_B + 4;   // + 2 issuers + TMA
-constexpr int B32_THREADS = (B32_WARP_MMA + 3) * 32;                 // 27 warps
+constexpr int B32_WG_B = 2;                   // back warpgroups (one per accumulator slot of conv1)
+constexpr int B32_WARP_M = 4, B32_WARP_B = 4 + 4 * B32_WG_M, B32_WARP_MMA = B32_WARP_B + 4 * B32_WG_B;   // + 2 issuers + TMA
+constexpr int B32_THREADS = (B32_WARP_MMA + 3) * 32;                 // 31 warps: <= 64 registers per thread
 constexpr int B32_NA = 4;                     // A-row ring slots per conv (TMEM)
 constexpr int B32_ND = 2;                     // accumulator slots per conv (TMEM)
 constexpr int B32_NX = 4;                     // residual (x0) rows in flight: the global-load latency is ~1 row period
@@ -65,7 +66,7 @@ struct B32Smem {
     uint8_t w_c[2][B32_W_B];
     uint8_t in_ring[B32_NI][B32_ROW_B];
     uint8_t w_ring[B32_WG_M][2][B32_XROW_B];
-    uint8_t x0_ring[B32_NX][B32_ROW_B];       // residual rows, prefetched by the back warpgroup's own lanes (cp.async)
+    uint8_t x0_ring[B32_WG_B][B32_NX][B32_ROW_B];   // residual rows, prefetched by each back warpgroup's own lanes (cp.async)
     B32Cst cst;
     B32Bars bars;
 };
@@ -208,22 +209,25 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
     auto build_a = [&](int S, int iA, const uint8_t* row, int pitch, int px_max) {
         const int as = iA % B32_NA;
         const uint32_t t = lane_base + (S ? B32_A1 : B32_A0) + as * B32_ACOLS;
-        uint4 g[3][B32_CG];
-#pragma unroll
-        for (int sx = 0; sx < 3; ++sx) {
+        auto load = [&](int sx, uint4 (&g)[B32_CG]) {
             int px = m + sx;
             px = px > px_max ? px_max : px;                  // lanes >= 126 of an input row: not valid lanes, any finite data
 #pragma unroll
             for (int c = 0; c < B32_CG; ++c)
-                g[sx][c] = *reinterpret_cast<const uint4*>(row + static_cast<size_t>(c * pitch + px) * 16);
-        }
+                g[c] = *reinterpret_cast<const uint4*>(row + static_cast<size_t>(c * pitch + px) * 16);
+        };
+        uint4 g[B32_CG], gn[B32_CG];                         // one shift in flight ahead of the stores (64 registers per thread)
+        load(0, g);
         mbar_wait(smem_u32(&sm.bars.a_empty[S][as]), ((iA / B32_NA) & 1) ^ 1);
         tc_fence_after();
-#pragma unroll
-        for (int sx = 0; sx < 3; ++sx) {
-            b32_tmem_st8(t + (sx * 2 + 0) * 8, g[sx][0], g[sx][1]);
-            b32_tmem_st8(t + (sx * 2 + 1) * 8, g[sx][2], g[sx][3]);
-        }
+        load(1, gn);
+        b32_tmem_st8(t + 0 * 8, g[0], g[1]);
+        b32_tmem_st8(t + 1 * 8, g[2], g[3]);
+        load(2, g);
+        b32_tmem_st8(t + 2 * 8, gn[0], gn[1]);
+        b32_tmem_st8(t + 3 * 8, gn[2], gn[3]);
+        b32_tmem_st8(t + 4 * 8, g[0], g[1]);
+        b32_tmem_st8(t + 5 * 8, g[2], g[3]);
         b32_tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -329,27 +333,30 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
         // =============================== back warpgroup: conv1 epilogue + residual -> global ===============================
         const size_t plane = static_cast<size_t>(a.H) * a.W * 8;
         const bool lane_valid = (m >= 2) && (m < 2 + B32_VALID) && col_in;
+        const int bpar = (warp - B32_WARP_B) >> 2;        // this warpgroup's rows: k = bpar (mod 2) - exactly the uses of slot bpar
         // x0 rows come from global memory; a load issued when its row is needed would expose the DRAM latency once per row (it
-        // was the whole row period).  Every lane copies ITS OWN 16-byte pieces B32_NX - 1 rows ahead with cp.async into a
+        // was the whole row period).  Every lane copies ITS OWN 16-byte pieces B32_NX - 1 of its rows ahead with cp.async into a
         // shared-memory ring and reads them back itself: no cross-thread hand-off, only cp.async.wait_group.
-        auto prefetch = [&](int k) {
+        auto prefetch = [&](int it) {                      // it: index among this warpgroup's rows
+            const int k = bpar + B32_WG_B * it;
             if (k < rows && lane_valid) {
                 const size_t g = ((static_cast<size_t>(fb) * B32_CG) * a.H + (y0 + k)) * static_cast<size_t>(a.W) * 8 + static_cast<size_t>(col) * 8;
 #pragma unroll
                 for (int c = 0; c < B32_CG; ++c)
                     if (4 * c < NPAIR) {
-                        const uint32_t dst = smem_u32(sm.x0_ring[k % B32_NX] + static_cast<size_t>(c * 128 + m) * 16);
+                        const uint32_t dst = smem_u32(sm.x0_ring[bpar][it % B32_NX] + static_cast<size_t>(c * 128 + m) * 16);
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(a.resid + g + c * plane) : "memory");
                     }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
 #pragma unroll
-        for (int k = 0; k < B32_NX - 1; ++k) prefetch(k);
-        for (int k = 0; k < rows; ++k) {
+        for (int it = 0; it < B32_NX - 1; ++it) prefetch(it);
+        int it = 0;
+        for (int k = bpar; k < rows; k += B32_WG_B, ++it) {
             const int h = y0 + k;
             const size_t goff = ((static_cast<size_t>(fb) * B32_CG) * a.H + h) * static_cast<size_t>(a.W) * 8 + static_cast<size_t>(col) * 8;
-            prefetch(k + B32_NX - 1);
+            prefetch(it + B32_NX - 1);
             const int ds = k % B32_ND;
             mbar_wait(smem_u32(&sm.bars.d_full1[ds]), (k / B32_ND) & 1);
             tc_fence_after();
@@ -364,7 +371,7 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
             uint4 r[B32_CG];
 #pragma unroll
             for (int c = 0; c < B32_CG; ++c)
-                r[c] = (lane_valid && 4 * c < NPAIR) ? *reinterpret_cast<const uint4*>(sm.x0_ring[k % B32_NX] + static_cast<size_t>(c * 128 + m) * 16)
+                r[c] = (lane_valid && 4 * c < NPAIR) ? *reinterpret_cast<const uint4*>(sm.x0_ring[bpar][it % B32_NX] + static_cast<size_t>(c * 128 + m) * 16)
                                                      : make_uint4(0, 0, 0, 0);
             float hacc[4];
             if (HEAD) {
