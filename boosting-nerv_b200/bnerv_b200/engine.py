@@ -523,7 +523,12 @@ class DecoderEngine:
             if done is None:
                 x0 = view(ws["x0"], blk.cout, Ho, Wo)
                 u = view(ws["u"], blk.cout, Ho, Wo)
-                ops.conv_fused(cur, blk.up.packed(), cin, H, W, act=blk.act, g1p=g0, beta=b0, out_pre=x0, out_aff=u)
+                streamed = None
+                if (fuse is not None and fuse[0] == "stream" and cp == 32 and ops.round_up(cin, 16) == 32 and Ho * Wo >= 65536
+                        and blk.up.k == 3 and blk.up.s == 1):       # 17..32 -> 17..32 channels at a large map: the streaming up-conv
+                    streamed = ops.upconv_stream(cur, blk.up.packed(), cin, H, W, blk.act, g0, b0, x0, u)
+                if streamed is None:
+                    ops.conv_fused(cur, blk.up.packed(), cin, H, W, act=blk.act, g1p=g0, beta=b0, out_pre=x0, out_aff=u)
                 if fuse is not None and (cp <= 16 or Ho * Wo >= 65536):      # the 32-channel form pays off on large maps only
                     if (bi + 1 == nb and cp == 32 and fuse[0] == "stream" and self.head.head1 and keep is not True
                             and blk.inner_act == "gelu" and not os.environ.get("BNERV_NO_HEAD_FUSION")):

@@ -296,6 +296,20 @@ def linear_pair(specs, B):
     check("bnerv_linear_pair", lib.bnerv_linear_pair(arr, B, _stream()))
 
 
+def upconv_stream(x_c8, up, cin, H, W, act, g0p, beta0, x0, u):
+    """bnerv_upconv_stream: a 17..32-channel block's 3x3 up-conv (no PixelShuffle) + activation + TAT affine in the row-streaming
+    form; writes x0 and u.  None = unsupported shape (nothing launched)."""
+    _need_cuda(x_c8, x0, u)
+    if up.k != 3 or up.s != 1 or not isinstance(up, PackedConv) or up.cin != cin:
+        return None
+    rc = lib.bnerv_upconv_stream(ptr(x_c8), x_c8.shape[0], cin, H, W, ptr(up.w), ptr(up.b), up.cout, ACT_CODES[act], ptr(g0p), ptr(beta0),
+                                 ptr(x0), ptr(u), _stream())
+    if rc == _capi.E_UNSUPPORTED:
+        return None
+    check("bnerv_upconv_stream", rc)
+    return x0
+
+
 def resblock_head_fused(u_c8, x0_c8, c0, c1, C, H, W, act_inner, g1p, beta1, head, img, head_act="tanh01"):
     """bnerv_resblock_stream_head: the last block's ResBlock_SFT half + the 1x1 head conv + OutImg in one kernel; `head` is a
     PackedHead1, `img` the [B, Cout, H, W] f32 output.  None = unsupported shape (nothing launched)."""

@@ -703,9 +703,23 @@ int resblock_stream32(const void* u, const void* x0, int B, int C, int H, int W,
                       const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1, void* out,
                       const float* head_w, const float* head_b, int head_cout, int head_act, float* img, cudaStream_t stream);
 
+int upconv_stream32(const void* x, int B, int C, int H, int W, const void* w_up, const float* b_up, int act_up, const float* g0p,
+                    const float* beta0, void* x0, void* u, cudaStream_t stream);
+
 }  // namespace bnerv
 
 using namespace bnerv;
+
+extern "C" int bnerv_upconv_stream(const void* x, int B, int Cin, int H, int W, const void* w_up, const float* b_up, int C, int act_up,
+                                   const float* g0p, const float* beta0, void* x0, void* u, void* stream) {
+    if (!x || !w_up || !b_up || !g0p || !beta0 || !x0 || !u) return set_error(BNERV_E_BADARG, "upconv_stream: null pointer");
+    if (B <= 0 || Cin <= 0 || C <= 0 || H <= 0 || W <= 0) return set_error(BNERV_E_BADARG, "upconv_stream: non-positive size");
+    if (Cin <= 16 || Cin > 32 || C <= 16 || C > 32) return set_error(BNERV_E_UNSUPPORTED, "upconv_stream: Cin = %d, C = %d (17..32 channels each)", Cin, C);
+    if (act_up < BNERV_ACT_NONE || act_up >= BNERV_ACT_TANH01) return set_error(BNERV_E_UNSUPPORTED, "upconv_stream: activation code");
+    const uintptr_t align_or = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_up) | reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(u);
+    if (align_or & 15) return set_error(BNERV_E_BADARG, "upconv_stream: pointers must be 16-byte aligned");
+    return upconv_stream32(x, B, C, H, W, w_up, b_up, act_up, g0p, beta0, x0, u, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int bnerv_nerv_block_stream(const void* x, int B, int Cin, int H, int W, const void* w_up, const float* b_up, int k_up,
                                        int s, int act_up, const void* w_c0, const float* b_c0, const void* w_c1, const float* b_c1,

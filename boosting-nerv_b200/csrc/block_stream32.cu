@@ -79,6 +79,7 @@ struct B32Args {
     const float *b_c0, *b_c1, *g1p, *beta1;
     const __half* resid;
     __half* out;
+    __half* out2;               // UP form: the affine output u
     // fused 1x1 head conv + OutImg (HEAD instantiations): img = act(head_w . f16(out) + head_b), NCHW f32; `out` is not stored
     const float *head_w, *head_b;
     float* img;
@@ -139,7 +140,9 @@ __device__ __forceinline__ void b32_affine8(const float2* x, const float* g, con
 // NPAIR: channel pairs that carry data (11: C <= 22, 12: C <= 24, 16: all).  A pad channel's conv0 output is exactly 0 (zero
 // weight rows, zero bias) and every block activation maps 0 to 0, so a skipped pair is set to the 0 it would have computed and
 // goes through the same affine; conv1 has zero weights for pad input channels either way.
-template <int ACT_IN, int NPAIR, bool HEAD>
+// UP: the same pipeline cut after its first conv - conv0 is a block's 3x3 up-conv (no PixelShuffle), its epilogue stores
+// x0 = act(. + b) to `out` and u = x0*g + beta to `out2` (model_blocks.py:37,216-217 + :105); no conv1, the back warpgroups idle.
+template <int ACT_IN, int NPAIR, bool HEAD, bool UP = false>
 __global__ void __launch_bounds__(B32_THREADS, 1)
 resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -159,8 +162,9 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
     const int col = sx0 + m;
     const bool col_in = (col >= 0) && (col < a.W);
     // conv0 output rows y0-1 .. y1 (rows + 2), its A rows (u) y0-2 .. y1+1 (rows + 4); conv1 output rows y0 .. y1-1
-    const int n_in = rows + 4, n_c0 = rows + 2;
-    const int in_row0 = y0 - 2, in_x0 = sx0 - 1;
+    const int n_in = UP ? rows + 2 : rows + 4, n_c0 = UP ? rows : rows + 2;
+    const int rows1 = UP ? 0 : rows;                  // conv1 / output rows
+    const int in_row0 = UP ? y0 - 1 : y0 - 2, in_x0 = sx0 - 1;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < B32_NI; ++i) { mbar_init(smem_u32(&sm.bars.in_full[i]), 1); mbar_init(smem_u32(&sm.bars.in_empty[i]), 4); }
@@ -179,11 +183,11 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
         const uint4* s1 = reinterpret_cast<const uint4*>(a.w_c1);
         uint4* d0 = reinterpret_cast<uint4*>(sm.w_c[0]);
         uint4* d1 = reinterpret_cast<uint4*>(sm.w_c[1]);
-        for (int i = threadIdx.x; i < B32_W_B / 16; i += B32_THREADS) { d0[i] = __ldg(s0 + i); d1[i] = __ldg(s1 + i); }
+        for (int i = threadIdx.x; i < B32_W_B / 16; i += B32_THREADS) { d0[i] = __ldg(s0 + i); if (!UP) d1[i] = __ldg(s1 + i); }
     }
     if (threadIdx.x < 32) {
         sm.cst.b_c0[threadIdx.x] = __ldg(a.b_c0 + threadIdx.x);
-        sm.cst.b_c1[threadIdx.x] = __ldg(a.b_c1 + threadIdx.x);
+        sm.cst.b_c1[threadIdx.x] = UP ? 0.0f : __ldg(a.b_c1 + threadIdx.x);
     }
     if (HEAD && threadIdx.x < 128) {                 // head weights [Cout][C] -> [4][32], zero beyond (Cout, C)
         const int c = threadIdx.x >> 5, k = threadIdx.x & 31;
@@ -254,7 +258,7 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
         const uint32_t b_lo = static_cast<uint32_t>(b_d) | ((smem_u32(sm.w_c[S]) & 0x3FFFFu) >> 4);
         const uint32_t d_base = tmem_base + (S ? B32_D1 : B32_D0);
         const uint32_t a_base = tmem_base + (S ? B32_A1 : B32_A0);
-        const int n = S ? rows : n_c0;
+        const int n = S ? rows1 : n_c0;
         int a_waited = 0;
         for (int j = 0; j < n; ++j) {
             while (a_waited <= j + 2) {                             // A rows j, j+1, j+2 (image rows h-1, h, h+1)
@@ -295,7 +299,7 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
         const int par = (warp - B32_WARP_M) >> 2;
         int it = 0;
         for (int k = par; k < n_c0; k += B32_WG_M, ++it) {
-            const int h = y0 - 1 + k;
+            const int h = UP ? y0 + k : y0 - 1 + k;
             const int ds = k % B32_ND;
             const bool inside = col_in && (h >= 0) && (h < a.H);
             uint8_t* wrow = sm.w_ring[par][it & 1];
@@ -321,10 +325,22 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
                 w0 = b32_pack8(y);
                 b32_affine8(x + 4, sm.cst.g1p + 16 * half + 8, sm.cst.beta1 + 16 * half + 8, y);
                 w1 = b32_pack8(y);
+                if (UP) {                                            // x0 and u straight to global memory
+                    if (inside && m >= 2 && m < 2 + B32_VALID) {
+                        const size_t plane = static_cast<size_t>(a.H) * a.W * 8;
+                        const size_t goff = ((static_cast<size_t>(fb) * B32_CG + 2 * half) * a.H + h) * static_cast<size_t>(a.W) * 8 + static_cast<size_t>(col) * 8;
+                        *reinterpret_cast<uint4*>(a.out + goff) = b32_pack8(x);
+                        *reinterpret_cast<uint4*>(a.out + goff + plane) = b32_pack8(x + 4);
+                        *reinterpret_cast<uint4*>(a.out2 + goff) = w0;
+                        *reinterpret_cast<uint4*>(a.out2 + goff + plane) = w1;
+                    }
+                    continue;
+                }
                 if (!inside) { w0 = make_uint4(0, 0, 0, 0); w1 = w0; }
                 *reinterpret_cast<uint4*>(wrow + static_cast<size_t>((2 * half) * 130 + m + 1) * 16) = w0;
                 *reinterpret_cast<uint4*>(wrow + static_cast<size_t>((2 * half + 1) * 130 + m + 1) * 16) = w1;
             }
+            if (UP) continue;
             named_bar_sync(1 + par, 128);                            // the w row is complete
             build_a(1, k, wrow, 130, 129);
             // the next iteration but one rewrites this exchange row: every thread has passed the next barrier by then
@@ -339,7 +355,7 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
         // shared-memory ring and reads them back itself: no cross-thread hand-off, only cp.async.wait_group.
         auto prefetch = [&](int it) {                      // it: index among this warpgroup's rows
             const int k = bpar + B32_WG_B * it;
-            if (k < rows && lane_valid) {
+            if (k < rows1 && lane_valid) {
                 const size_t g = ((static_cast<size_t>(fb) * B32_CG) * a.H + (y0 + k)) * static_cast<size_t>(a.W) * 8 + static_cast<size_t>(col) * 8;
 #pragma unroll
                 for (int c = 0; c < B32_CG; ++c)
@@ -353,7 +369,7 @@ resblock_stream32_kernel(const __grid_constant__ CUtensorMap tmIn, const B32Args
 #pragma unroll
         for (int it = 0; it < B32_NX - 1; ++it) prefetch(it);
         int it = 0;
-        for (int k = bpar; k < rows; k += B32_WG_B, ++it) {
+        for (int k = bpar; k < rows1; k += B32_WG_B, ++it) {
             const int h = y0 + k;
             const size_t goff = ((static_cast<size_t>(fb) * B32_CG) * a.H + h) * static_cast<size_t>(a.W) * 8 + static_cast<size_t>(col) * 8;
             prefetch(it + B32_NX - 1);
@@ -486,13 +502,19 @@ int resblock_stream32_launch(const void* u, B32Args& a, cudaStream_t stream) {
     if (pairs <= 11)      { fn = gelu ? resblock_stream32_kernel<BNERV_ACT_GELU, 11, false> : resblock_stream32_kernel<-1, 11, false>; slot = 0 + gelu; }
     else if (pairs <= 12) { fn = gelu ? resblock_stream32_kernel<BNERV_ACT_GELU, 12, false> : resblock_stream32_kernel<-1, 12, false>; slot = 2 + gelu; }
     else                  { fn = gelu ? resblock_stream32_kernel<BNERV_ACT_GELU, 16, false> : resblock_stream32_kernel<-1, 16, false>; slot = 4 + gelu; }
+    if (a.out2) {         // UP form: a block's 3x3 up-conv + activation + affine, two outputs
+        const bool sin = a.act_inner == BNERV_ACT_SIN;
+        if (pairs <= 11)      { fn = sin ? resblock_stream32_kernel<BNERV_ACT_SIN, 11, false, true> : resblock_stream32_kernel<-1, 11, false, true>; slot = 9 + sin; }
+        else if (pairs <= 12) { fn = sin ? resblock_stream32_kernel<BNERV_ACT_SIN, 12, false, true> : resblock_stream32_kernel<-1, 12, false, true>; slot = 11 + sin; }
+        else                  { fn = sin ? resblock_stream32_kernel<BNERV_ACT_SIN, 16, false, true> : resblock_stream32_kernel<-1, 16, false, true>; slot = 13 + sin; }
+    }
     if (head) {           // + 1x1 head conv + OutImg in the back warpgroup (GELU blocks: every shipped preset)
         if (!gelu) return set_error(BNERV_E_UNSUPPORTED, "resblock_stream_head: inner activation %d (GELU only)", a.act_inner);
         if (pairs <= 11)      { fn = resblock_stream32_kernel<BNERV_ACT_GELU, 11, true>; slot = 6; }
         else if (pairs <= 12) { fn = resblock_stream32_kernel<BNERV_ACT_GELU, 12, true>; slot = 7; }
         else                  { fn = resblock_stream32_kernel<BNERV_ACT_GELU, 16, true>; slot = 8; }
     }
-    static bool attr_set[9][32] = {};
+    static bool attr_set[15][32] = {};
     int cur_dev = 0;
     cudaGetDevice(&cur_dev);
     const size_t smem = sizeof(B32Smem) + 1024;
@@ -536,6 +558,17 @@ int resblock_stream32(const void* u, const void* x0, int B, int C, int H, int W,
     a.resid = static_cast<const __half*>(x0);
     a.out = static_cast<__half*>(out);
     return resblock_stream32_launch(u, a, stream);
+}
+
+// called by bnerv_upconv_stream (block_stream.cu): x0 = act(conv3(x) + b), u = x0*g0p + beta0 for 17..32 input and output channels
+int upconv_stream32(const void* x, int B, int C, int H, int W, const void* w_up, const float* b_up, int act_up, const float* g0p,
+                    const float* beta0, void* x0, void* u, cudaStream_t stream) {
+    B32Args a{};
+    a.B = B; a.H = H; a.W = W; a.C = C; a.act_inner = act_up;
+    a.w_c0 = static_cast<const __half*>(w_up); a.b_c0 = b_up; a.g1p = g0p; a.beta1 = beta0;
+    a.out = static_cast<__half*>(x0);
+    a.out2 = static_cast<__half*>(u);
+    return resblock_stream32_launch(x, a, stream);
 }
 
 }  // namespace bnerv

@@ -171,6 +171,12 @@ int bnerv_resblock_stream(const void* u, const void* x0, int B, int C, int H, in
                           const void* w_c1, const float* b_c1, int act_inner, const float* g1p, const float* beta1,
                           void* out, void* stream);
 
+/* The up-conv half of a 17..32-channel NeRVBlock in the same row-streaming form (k = 3, no PixelShuffle, 17..32 input channels):
+ * x0 = act_up(conv3(x) + b_up), u = x0*g0p + beta0 - what bnerv_conv_fused does for this layer (bit-identical), at the MMA-issue
+ * floor instead of the generic epilogue's instruction count.  x, x0, u: C8 f16 maps of 32 padded channels. */
+int bnerv_upconv_stream(const void* x, int B, int Cin, int H, int W, const void* w_up, const float* b_up, int C, int act_up,
+                        const float* g0p, const float* beta0, void* x0, void* u, void* stream);
+
 /* bnerv_resblock_stream (17..32 channels) with the model's 1x1 head conv and OutImg (model_enerv.py:311-313 / model_nerv.py:56-57,
  * model_blocks.py:57-63) folded into the last warpgroup: img[b][c][h][w] = act(head_b[c] + sum_k head_w[c][k] * f16(out[k])), f32
  * NCHW, head_w = the raw f32 [head_cout][C] weights, head_cout <= 4.  The block output is not stored (it would be written once

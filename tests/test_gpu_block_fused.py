@@ -184,6 +184,25 @@ def test_stream_block_with_fused_head_gives_the_two_launch_image_bit_for_bit(ops
     assert torch.equal(img, ref), f"max |diff| {(img - ref).abs().max().item():.3e}"
 
 
+@pytest.mark.parametrize("case", [(1, 21, 21, 64, 96), (2, 21, 21, 37, 131), (1, 30, 17, 45, 80), (1, 32, 32, 20, 122), (1, 24, 21, 9, 250),
+                                  (1, 21, 21, 270, 480)], ids=lambda c: "B%d_%dto%d_%dx%d" % c)
+@pytest.mark.parametrize("act", ["sin", "relu"])
+def test_stream_upconv_32_channels_is_bit_identical_to_the_fused_conv(ops, case, act):
+    """bnerv_upconv_stream (3x3 up-conv + activation + TAT affine, two outputs, 17..32 channels) against bnerv_conv_fused."""
+    B, cin, C, H, W = case
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, B, cin, C, H, W, 1)
+    mk = lambda: torch.full(ops.c8_shape(B, C, H, W), float("nan"), dtype=torch.float16, device="cuda")
+    x0r, ur, x0, u = mk(), mk(), mk(), mk()
+    ops.conv_fused(x, up, cin, H, W, act=act, g1p=g0, beta=b0, out_pre=x0r, out_aff=ur)
+    assert ops.upconv_stream(x, up, cin, H, W, act, g0, b0, x0, u) is not None
+    torch.cuda.synchronize()
+    assert torch.equal(x0, x0r), f"x0: max |diff| {(x0.float() - x0r.float()).abs().max().item():.3e}"
+    assert torch.equal(u, ur), f"u: max |diff| {(u.float() - ur.float()).abs().max().item():.3e}"
+    x12, up12, _, _, (g12, b12, _, _) = make_block(ops, 1, 12, 12, 16, 16, 1)
+    o = torch.zeros(ops.c8_shape(1, 12, 16, 16), dtype=torch.float16, device="cuda")
+    assert ops.upconv_stream(x12, up12, 12, 16, 16, "sin", g12, b12, o, o.clone()) is None
+
+
 def test_stream_block_refuses_what_it_does_not_implement(ops):
     x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 12, 12, 20, 24, 3)           # PixelShuffle(3)
     assert ops.nerv_block_fused(x, up, c0, c1, 12, 20, 24, "sin", "gelu", g0, b0, g1, b1, form="stream") is None
