@@ -266,11 +266,12 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
     // builds A row `iA` of stage S from a [2 groups][pitch px][16 B] shared-memory row: lane m <- pixels m+px0 .. m+px0+2
-    auto build_a = [&](int S, int iA, const uint8_t* row, int pitch, int px0, int px_max) {
+    // (lane_mask: 127 = every lane its own pixel; 63 = lanes 64..127 repeat lanes 0..63, the S2 up-conv rows)
+    auto build_a = [&](int S, int iA, const uint8_t* row, int pitch, int px0, int px_max, int lane_mask = 127) {
         uint4 g0[3], g1[3];
 #pragma unroll
         for (int sx = 0; sx < 3; ++sx) {
-            int px = m + px0 + sx;
+            int px = (m & lane_mask) + px0 + sx;
             px = px > px_max ? px_max : px;                  // lanes >= 126 of an input row: not valid lanes, any finite data
             g0[sx] = *reinterpret_cast<const uint4*>(row + static_cast<size_t>(px) * 16);
             g1[sx] = *reinterpret_cast<const uint4*>(row + static_cast<size_t>(pitch + px) * 16);
@@ -361,14 +362,18 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
             // (bnerv_pack_conv_weight, s = 2): 16-column group i*2+G holds output row 2hi+i, channel group G, both output
             // columns 2*(sx0/2 + l) + j.  The sin epilogue therefore runs on lanes 0..63 (warps 0, 1 of the warpgroup); all
             // four warps build the two A_c0 rows afterwards.
+            // The 64 input columns of the strip are REPEATED in lanes 64..127 of the A_up rows, so the accumulator rows hold every
+            // value twice and all four warps of the warpgroup share the epilogue: lanes 0..63 take output row 2hi (groups 0, 1),
+            // lanes 64..127 output row 2hi + 1 (groups 2, 3).  (The MMA is M = 128 either way.)
             auto build_up = [&](int i) {
                 const int seq = i / NFRONT;
                 const int slot = par * BS_NIK + (seq % BS_NIK);
                 mbar_wait(smem_u32(&sm.bars.in_full[slot]), (seq / BS_NIK) & 1);
-                build_a(0, i, sm.in_ring[slot], 128, 0, 127);
+                build_a(0, i, sm.in_ring[slot], 128, 0, 127, 63);
                 if (lane == 0) mbar_arrive(smem_u32(&sm.bars.in_empty[slot]));
             };
             if (par < n_in) build_up(par);
+            const int lc = m & 63, i_row = m >> 6;                       // input column of this lane, output-row parity it handles
             int it = 0;
             for (int j = par; j < n_out[0]; j += nwg, ++it) {
                 if (j + nwg < n_in) build_up(j + nwg);
@@ -376,10 +381,10 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
                 mbar_wait(smem_u32(&sm.bars.d_full[0][ds]), (j / R::ND0) & 1);
                 tc_fence_after();
                 uint8_t* ubuf = sm.u_ring[par][it & 1][0];               // two exchange rows: + i * BS_XROW_B
-                if (m < 64) {
+                {
 #pragma unroll 1
-                    for (int g = 0; g < 4; ++g) {                        // g = i*2 + G
-                        const int i = g >> 1, G = g & 1;
+                    for (int G = 0; G < 2; ++G) {
+                        const int i = i_row, g = i_row * 2 + G;          // g = i*2 + G
                         uint32_t v[16];
                         tmem_ld16(lane_base + R::D0 + ds * 64 + g * 16, v);
                         tmem_ld_wait();
@@ -394,7 +399,7 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
                         const int k = ia - 2;
 #pragma unroll
                         for (int jj = 0; jj < 2; ++jj) {
-                            const int lane_o = 2 * m + jj;               // output lane of the strip
+                            const int lane_o = 2 * lc + jj;              // output lane of the strip
                             const int ocol = sx0 + lane_o;
                             const bool inside = (ocol >= 0) && (ocol < a.W) && (h >= 0) && (h < a.H);
                             float2 y[4];
