@@ -186,11 +186,13 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
     const int wg = warp >> 2;                         // 0-2 front, 3-4 middle, 5 back, 6 = MMA / TMA warps
     const int stage_of_wg = wg < BS_WG_F ? 0 : (wg < BS_WG_F + BS_WG_M ? 1 : 2);
     const int par = stage_of_wg == 0 ? wg : (stage_of_wg == 1 ? wg - BS_WG_F : wg - BS_WG_F - BS_WG_M);   // row residue this warpgroup handles
-    // S2: two front warpgroups.  A warpgroup may only wait on ring slots whose EVERY use it sees or whose previous use is implied
-    // complete by its own previous row (mbarrier waits test a phase parity: "one use behind" and "done" look alike).  With
-    // the 2 accumulator slots TMEM leaves for the 64-column up-conv rows, a third warpgroup's first wait would be for the
-    // second use of a slot.  With two, each warpgroup owns one slot.
-    constexpr int NFRONT = S2 ? 2 : BS_WG_F;
+    // A warpgroup may only wait on ring slots whose EVERY use it sees or whose previous use is implied complete by its own
+    // previous row (mbarrier waits test a phase parity: "one use behind" and "done" look alike): the row stride of a stage's
+    // warpgroups must not exceed its ring depth.  S2 leaves only 2 accumulator slots for the 64-column up-conv rows, fewer than
+    // the three front warpgroups - so there the "full" signal of the up-conv goes to a barrier per CONSUMER WARPGROUP (which sees
+    // every phase of it; row j+3 cannot complete before every warp has released row j, the slot chain j -> j+2 and the in-order
+    // MMA issue see to that), while "empty" stays per slot for its single waiter, the MMA issuer.
+    constexpr int NFRONT = BS_WG_F;
     const int nwg = stage_of_wg == 0 ? NFRONT : (stage_of_wg == 1 ? BS_WG_M : BS_WG_B);
     const int q = warp & 3;
     const int m = q * 32 + lane;                      // TMEM lane == column of the strip
@@ -336,15 +338,13 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
                         for (int sx = 0; sx < 3; ++sx)
                             umma_f16_ts(d, at + sx * 8, b_lo + (r * 3 + sx) * tap16, b_hi, idesc, (r | sx) ? 1u : 0u);
                     }
-                    umma_commit(smem_u32(&sm.bars.d_full[S][ds]));
+                    umma_commit(smem_u32(&sm.bars.d_full[S][(S2 && S == 0) ? j % NFRONT : ds]));
                     umma_commit(smem_u32(&sm.bars.a_empty[S][j % BS_NA]));      // A row j has had its last reader
                 }
                 __syncwarp();
                 BS_STAMP1(6 + S, j, 3);
             }
         }
-    } else if (stage_of_wg == 0 && par >= NFRONT) {
-        // (S2 form: the third front warpgroup has no rows)
     } else if (stage_of_wg == 0) {
         // =============================== front warpgroups (rows j = par mod nwg) ===============================
         if (!a.has_up) {
@@ -377,8 +377,8 @@ block_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const BsArgs a) {
             int it = 0;
             for (int j = par; j < n_out[0]; j += nwg, ++it) {
                 if (j + nwg < n_in) build_up(j + nwg);
-                const int ds = j % R::ND0;                               // == par: this warpgroup's own slot
-                mbar_wait(smem_u32(&sm.bars.d_full[0][ds]), (j / R::ND0) & 1);
+                const int ds = j % R::ND0;
+                mbar_wait(smem_u32(&sm.bars.d_full[0][par]), it & 1);     // this warpgroup's own "full" barrier (see NFRONT)
                 tc_fence_after();
                 uint8_t* ubuf = sm.u_ring[par][it & 1][0];               // two exchange rows: + i * BS_XROW_B
                 {
