@@ -18,6 +18,7 @@ e2e   : the same through model.forward_decoder() (the call the reference's evalu
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -470,9 +471,95 @@ def run_b200(opt):
             line["ptq"] = ptq_extra(opt.config, dev)
         except Exception as ex:
             line["ptq"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+        try:
+            line["compression_path"] = compression_extra(opt.config, dev)
+        except Exception as ex:
+            line["compression_path"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _gaussian_bits(code, quant):
+    """DiffEntropyModel.cal_global_bitrate, eval branch, restated (lib/entropy_model.py:20-44): the codes' mean / std
+    parametrise a Gaussian, bits = sum max(0, -log2(cdf(q + .5) - cdf(q - .5) + 1e-5))."""
+    mean, std = code.mean(), code.std().clamp(1e-5, 1e10)
+    cdf = lambda v: 0.5 * (1 + torch.erf((v - mean) * std.reciprocal() / math.sqrt(2.0)))
+    probs = cdf(quant + 0.5) - cdf(quant - 0.5)
+    return torch.clamp(-torch.log(probs + 1e-5) / math.log(2.0), min=0).sum()
+
+
+def compression_extra(cfg_name, dev, frames=50):
+    """BASELINE.json configs[4] (compression path, scripts/compression/hnerv_boost.sh: --quant, `scale` quantisers for weights and
+    biases, `scalebeta` for the embedding, 8 bits, DiffEntropyModel): what `cal_params` leaves behind - dequant_w / dequant_b on
+    every decoder layer (Scale_T.forward, lib/transform_ops.py:246-250, with the scales of init_data(), :221-237) - decoded on the
+    native kernels, and the entropy model's bit estimate for weights + biases + embeddings -> bits per pixel.  The reference's own
+    quantiser / entropy-model classes are not on the GPU box; they are exercised against the drop-in in
+    tests/test_compression_path_cpu.py - here their arithmetic is restated in torch on random-init weights."""
+    from bnerv_b200 import ops
+    model, args = build_model(cfg_name)
+    model = model.to(dev).eval()
+    ref_model, _ = build_model(cfg_name)
+    ref_model = ref_model.to(dev).eval()
+    ref_model.load_state_dict(model.state_dict())
+    is_h = args.model == "HNeRV_Boost"
+    fh, fw = [int(v) for v in args.fc_hw.split("_")]
+    emb = torch.rand(N_FRAMES, 16, fh, fw, device=dev, generator=torch.Generator(device=dev).manual_seed(7)) if is_h else None
+    enc = getattr(model, "encoder", None)
+    skip = set() if enc is None else {id(m) for m in enc.modules()}
+    bits = torch.zeros((), device=dev)
+    n_sym = 0
+    with torch.no_grad():
+        for m in model.modules():
+            if id(m) in skip or not hasattr(m, "dequant_w") or getattr(m, "weight", None) is None:
+                continue
+            for name in ("weight", "bias"):
+                w = getattr(m, name, None)
+                if w is None:
+                    continue
+                scale = (w.max() - w.min()) / 255.0                      # Scale_T.init_data, 8 bits
+                code = w / scale
+                quant = torch.round(code)
+                setattr(m, "dequant_w" if name == "weight" else "dequant_b", quant * scale)
+                bits = bits + _gaussian_bits(code, quant)
+                n_sym += w.numel()
+        deq_emb = None
+        if is_h:                                                         # ScaleBeta_T on the embeddings (:264-286)
+            beta, scale = emb.min(), (emb.max() - emb.min()) / 255.0
+            code = (emb - beta) / scale
+            quant = torch.round(code)
+            deq_emb = quant * scale + beta
+            bits = bits + _gaussian_bits(code, quant)
+            n_sym += emb.numel()
+    model.engine().invalidate()
+    t = torch.tensor([norm_index_(i) for i in range(frames + 5)], dtype=torch.float64, device=dev)
+    psnr = []
+    with torch.no_grad():
+        for i in range(5):
+            model.decode(deq_emb[i:i + 1], t[i:i + 1]) if is_h else model.decode(t[i:i + 1])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(5, frames + 5):
+            model.decode(deq_emb[i:i + 1], t[i:i + 1]) if is_h else model.decode(t[i:i + 1])
+        e1.record()
+        torch.cuda.synchronize()
+        for i in (5, 6, 7):
+            a = (model.decode(deq_emb[i:i + 1], t[i:i + 1]) if is_h else model.decode(t[i:i + 1])).clone()
+            b = ref_model.decode(emb[i:i + 1], t[i:i + 1]) if is_h else ref_model.decode(t[i:i + 1])
+            psnr.append(float(ops.frame_metrics(a, b)[0, 2]))
+    pixels = fh * fw
+    for s_ in args.dec_strds:
+        pixels *= s_ * s_
+    total_bits = float(bits)
+    out = {"what": "BASELINE configs[4]: decoder with dequant_w / dequant_b as cal_params() sets them (8-bit `scale` quantisers at their "
+                   "init_data() scales, `scalebeta` embeddings), decoded on the native kernels; bits = the Gaussian entropy model's "
+                   "estimate (lib/entropy_model.py:20-44 restated); random-init weights",
+           "decode_frames_per_s": 1e3 * frames / e0.elapsed_time(e1), "estimated_bits_per_param": total_bits / n_sym,
+           "estimated_bpp": total_bits / pixels / N_FRAMES, "psnr_vs_unquantised_db": sum(psnr) / len(psnr)}
+    del model, ref_model
+    torch.cuda.empty_cache()
+    return out
 
 
 def ptq_extra(cfg_name, dev, frames=50):
