@@ -18,7 +18,7 @@ EXPORTS = [
     "bnerv_conv_fused_f32", "bnerv_sft_affine", "bnerv_linear_act", "bnerv_nchw_to_c8", "bnerv_c8_to_nchw",
     "bnerv_pixel_shuffle", "bnerv_c8_numel", "bnerv_packed_weight_numel", "bnerv_packed_bias_numel",
     # backward of the cascade (ABI version 2)
-    "bnerv_conv_fused_ex", "bnerv_conv_fused_split", "bnerv_pe_linear_pair", "bnerv_linear_pair", "bnerv_resblock_stream_head", "bnerv_upconv_stream", "bnerv_nerv_block_stream_head", "bnerv_head_bwd", "bnerv_pack_conv_weight_dgrad", "bnerv_conv_wgrad", "bnerv_wgrad_acc_numel",
+    "bnerv_conv_fused_ex", "bnerv_conv_fused_split", "bnerv_pe_linear_pair", "bnerv_linear_pair", "bnerv_resblock_stream_head", "bnerv_upconv_stream", "bnerv_conv_stream", "bnerv_nerv_block_stream_head", "bnerv_head_bwd", "bnerv_pack_conv_weight_dgrad", "bnerv_conv_wgrad", "bnerv_wgrad_acc_numel",
     "bnerv_wgrad_finalize", "bnerv_bias_finalize", "bnerv_channel_sum", "bnerv_resblock_mid_bwd", "bnerv_block_front_bwd",
     "bnerv_unshuffle_c8", "bnerv_pack_conv_weight_q", "bnerv_frame_metrics", "bnerv_frame_metrics_scratch_doubles",
     "bnerv_pack_head_weight", "bnerv_head_conv3", "bnerv_nerv_block_fwd", "bnerv_head_conv1",
@@ -121,6 +121,7 @@ def _load():
     lib.bnerv_ptq_quant_tensor.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp]
     lib.bnerv_resblock_stream_head.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, vp, i, vp, vp, vp, vp, i, i, vp, vp]
     lib.bnerv_nerv_block_stream_head.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, vp, vp]
+    lib.bnerv_conv_stream.argtypes = [vp, i, i, i, i, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
     lib.bnerv_upconv_stream.argtypes = [vp, i, i, i, i, vp, vp, i, i, vp, vp, vp, vp, vp]
     lib.bnerv_pe_linear_pair.argtypes = [vp, i, vp, i, vp, vp]
     lib.bnerv_linear_pair.argtypes = [vp, i, vp]

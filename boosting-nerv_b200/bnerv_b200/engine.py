@@ -527,6 +527,10 @@ class DecoderEngine:
                 if (fuse is not None and fuse[0] == "stream" and cp == 32 and ops.round_up(cin, 16) == 32 and Ho * Wo >= 65536
                         and blk.up.k == 3 and blk.up.s == 1):       # 17..32 -> 17..32 channels at a large map: the streaming up-conv
                     streamed = ops.upconv_stream(cur, blk.up.packed(), cin, H, W, blk.act, g0, b0, x0, u)
+                # 33..48 channels at a large map (E-NeRV-M's 540p stages): each conv in the single-conv streaming form
+                wide48 = (cp == 48 and Ho * Wo >= 65536 and self.fuse_blocks and not os.environ.get("BNERV_NO_CONV_STREAM"))
+                if streamed is None and wide48 and blk.up.k == 3 and blk.up.s == 1:
+                    streamed = ops.conv_stream(cur, blk.up.packed(), cin, H, W, act=blk.act, g1p=g0, beta=b0, out_pre=x0, out_aff=u)
                 if streamed is None:
                     ops.conv_fused(cur, blk.up.packed(), cin, H, W, act=blk.act, g1p=g0, beta=b0, out_pre=x0, out_aff=u)
                 if fuse is not None and (cp <= 16 or Ho * Wo >= 65536):      # the 32-channel form pays off on large maps only
@@ -541,9 +545,11 @@ class DecoderEngine:
                                               out=out, form=fuse[0])
                 if done is None:
                     wbuf = view(ws["w"], blk.cout, Ho, Wo)
-                    ops.conv_fused(u, blk.c0.packed(), blk.cout, Ho, Wo, act=blk.inner_act, g1p=g1, beta=b1, out_aff=wbuf)
-                    ops.conv_fused(wbuf, blk.c1.packed(), blk.cout, Ho, Wo, act="none", resid=x0, out_pre=out,
-                                   split=1 if out_split else 0)
+                    if not (wide48 and ops.conv_stream(u, blk.c0.packed(), blk.cout, Ho, Wo, act=blk.inner_act, g1p=g1, beta=b1, out_aff=wbuf)):
+                        ops.conv_fused(u, blk.c0.packed(), blk.cout, Ho, Wo, act=blk.inner_act, g1p=g1, beta=b1, out_aff=wbuf)
+                    if not (wide48 and not out_split and ops.conv_stream(wbuf, blk.c1.packed(), blk.cout, Ho, Wo, act="none", resid=x0, out_pre=out)):
+                        ops.conv_fused(wbuf, blk.c1.packed(), blk.cout, Ho, Wo, act="none", resid=x0, out_pre=out,
+                                       split=1 if out_split else 0)
             if keep is True or (keep == "first" and bi == 0):
                 if out_split:               # hi + lo of the split map
                     g = cp // 8

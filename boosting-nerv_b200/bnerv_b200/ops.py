@@ -296,6 +296,20 @@ def linear_pair(specs, B):
     check("bnerv_linear_pair", lib.bnerv_linear_pair(arr, B, _stream()))
 
 
+def conv_stream(x_c8, pc, cin, H, W, act="none", resid=None, g1p=None, beta=None, out_pre=None, out_aff=None):
+    """bnerv_conv_stream: conv_fused for 3x3 / stride 1 / equal padded widths of 32 or 48 channels in the row-streaming form.
+    Returns True when launched, None for shapes outside that class (nothing launched)."""
+    _need_cuda(x_c8)
+    if not isinstance(pc, PackedConv) or pc.k != 3 or pc.s != 1 or pc.cin != cin:
+        return None
+    rc = lib.bnerv_conv_stream(ptr(x_c8), x_c8.shape[0], cin, H, W, ptr(pc.w), ptr(pc.b), pc.cout, ACT_CODES[act], ptr(resid), ptr(g1p),
+                               ptr(beta), ptr(out_pre), ptr(out_aff), _stream())
+    if rc == _capi.E_UNSUPPORTED:
+        return None
+    check("bnerv_conv_stream", rc)
+    return True
+
+
 def upconv_stream(x_c8, up, cin, H, W, act, g0p, beta0, x0, u):
     """bnerv_upconv_stream: a 17..32-channel block's 3x3 up-conv (no PixelShuffle) + activation + TAT affine in the row-streaming
     form; writes x0 and u.  None = unsupported shape (nothing launched)."""

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbnerv_b200.so")
-SOURCES = ["capi.cu", "ops.cu", "conv_tc.cu", "block_fused.cu", "block_stream.cu", "block_stream32.cu", "conv_wgrad.cu", "bwd_ops.cu", "loss_ops.cu", "ptq_ops.cu", "encoder_ops.cu"]
+SOURCES = ["capi.cu", "ops.cu", "conv_tc.cu", "block_fused.cu", "block_stream.cu", "block_stream32.cu", "conv_stream.cu", "conv_wgrad.cu", "bwd_ops.cu", "loss_ops.cu", "ptq_ops.cu", "encoder_ops.cu"]
 FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
          "-std=c++17", "--cudart", "static"]
 

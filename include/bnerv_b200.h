@@ -177,6 +177,13 @@ int bnerv_resblock_stream(const void* u, const void* x0, int B, int C, int H, in
 int bnerv_upconv_stream(const void* x, int B, int Cin, int H, int W, const void* w_up, const float* b_up, int C, int act_up,
                         const float* g0p, const float* beta0, void* x0, void* u, void* stream);
 
+/* bnerv_conv_fused for one shape class - 3x3, stride 1, no PixelShuffle, equal padded widths of 32 or 48 channels (Cin, Cout in
+ * 17..32 or 33..48) - in the row-streaming form: A rows in tensor memory, one launch = one conv with the same epilogue
+ * (bias, activation, residual, TAT affine, out_pre and / or out_aff) and bit-identical results.  For E-NeRV-Boost M's 43-channel
+ * 540p layers, where bnerv_conv_fused is bound by its epilogue's instruction count.  Other shapes: BNERV_E_UNSUPPORTED. */
+int bnerv_conv_stream(const void* x, int B, int Cin, int H, int W, const void* w_packed, const float* bias_packed, int Cout,
+                      int act, const void* resid, const float* g1p, const float* beta, void* out_pre, void* out_aff, void* stream);
+
 /* bnerv_resblock_stream (17..32 channels) with the model's 1x1 head conv and OutImg (model_enerv.py:311-313 / model_nerv.py:56-57,
  * model_blocks.py:57-63) folded into the last warpgroup: img[b][c][h][w] = act(head_b[c] + sum_k head_w[c][k] * f16(out[k])), f32
  * NCHW, head_w = the raw f32 [head_cout][C] weights, head_cout <= 4.  The block output is not stored (it would be written once

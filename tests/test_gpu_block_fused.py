@@ -203,6 +203,30 @@ def test_stream_upconv_32_channels_is_bit_identical_to_the_fused_conv(ops, case,
     assert ops.upconv_stream(x12, up12, 12, 16, 16, "sin", g12, b12, o, o.clone()) is None
 
 
+@pytest.mark.parametrize("case", [(1, 43, 43, 64, 96), (2, 43, 43, 37, 131), (1, 33, 48, 20, 126), (1, 48, 40, 9, 253), (1, 43, 43, 270, 480),
+                                  (1, 21, 21, 40, 130), (1, 30, 17, 5, 9)], ids=lambda c: "B%d_%dto%d_%dx%d" % c)
+@pytest.mark.parametrize("form", ["up_sin", "c0_gelu", "c1_resid", "relu_both"])
+def test_conv_stream_is_bit_identical_to_the_fused_conv(ops, case, form):
+    """bnerv_conv_stream (one 3x3 conv of 17..48 channels in the row-streaming form) against bnerv_conv_fused for the epilogue
+    shapes of a NeRVBlock: up-conv (sin, x0 + u), conv0 (GELU, affine output only), conv1 (residual), and a run-time activation."""
+    B, cin, C, H, W = case
+    x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, B, cin, C, H, W, 1)
+    mk = lambda: torch.full(ops.c8_shape(B, C, H, W), float("nan"), dtype=torch.float16, device="cuda")
+    res = ops.nchw_to_c8(torch.randn(B, C, H, W, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)))
+    kw = {"up_sin": dict(act="sin", g1p=g0, beta=b0, out_pre=True, out_aff=True), "c0_gelu": dict(act="gelu", g1p=g1, beta=b1, out_aff=True),
+          "c1_resid": dict(act="none", resid=res, out_pre=True), "relu_both": dict(act="relu", resid=res, g1p=g1, beta=b1, out_pre=True, out_aff=True)}[form]
+    outs_r = {k: mk() for k in ("out_pre", "out_aff") if kw.get(k)}
+    outs_s = {k: mk() for k in outs_r}
+    base = {k: v for k, v in kw.items() if k not in ("out_pre", "out_aff")}
+    ops.conv_fused(x, up, cin, H, W, **base, **outs_r)
+    assert ops.conv_stream(x, up, cin, H, W, **base, **outs_s) is True
+    torch.cuda.synchronize()
+    for k in outs_r:
+        assert torch.equal(outs_s[k], outs_r[k]), f"{k}: max |diff| {(outs_s[k].float() - outs_r[k].float()).abs().max().item():.3e}"
+    x12, up12, _, _, _ = make_block(ops, 1, 12, 12, 16, 16, 1)
+    assert ops.conv_stream(x12, up12, 12, 16, 16, out_pre=torch.zeros(ops.c8_shape(1, 12, 16, 16), dtype=torch.float16, device="cuda")) is None
+
+
 def test_stream_block_refuses_what_it_does_not_implement(ops):
     x, up, c0, c1, (g0, b0, g1, b1) = make_block(ops, 1, 12, 12, 20, 24, 3)           # PixelShuffle(3)
     assert ops.nerv_block_fused(x, up, c0, c1, 12, 20, 24, "sin", "gelu", g0, b0, g1, b1, form="stream") is None
