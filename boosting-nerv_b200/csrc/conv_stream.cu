@@ -200,18 +200,25 @@ conv_stream_kernel(const __grid_constant__ CUtensorMap tmIn, const CsArgs a) {
             const uint8_t* row = sm.in_ring[slot];
             const int as = i % CS_NA;
             const uint32_t t = lane_base + as * Cfg::ACOLS;
-            mbar_wait(smem_u32(&sm.a_empty[as]), ((i / CS_NA) & 1) ^ 1);
-            tc_fence_after();
-#pragma unroll
-            for (int sx = 0; sx < 3; ++sx) {
+            auto load = [&](int sx, uint4 (&g)[CG]) {
                 int px = m + sx;
                 px = px > 127 ? 127 : px;                            // lanes 126, 127: not valid lanes, any finite data
-                uint4 g[CG];
 #pragma unroll
                 for (int c = 0; c < CG; ++c) g[c] = *reinterpret_cast<const uint4*>(row + static_cast<size_t>(c * 128 + px) * 16);
+            };
+            auto store = [&](int sx, const uint4 (&g)[CG]) {
 #pragma unroll
                 for (int ks = 0; ks < Cfg::KS; ++ks) cs_tmem_st8(t + (sx * Cfg::KS + ks) * 8, g[2 * ks], g[2 * ks + 1]);
-            }
+            };
+            uint4 g[CG], gn[CG];                                     // one shift in flight ahead of the stores
+            load(0, g);
+            mbar_wait(smem_u32(&sm.a_empty[as]), ((i / CS_NA) & 1) ^ 1);
+            tc_fence_after();
+            load(1, gn);
+            store(0, g);
+            load(2, g);
+            store(1, gn);
+            store(2, g);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
