@@ -350,7 +350,7 @@ def test_enerv_frame_independent_stem_half_follows_the_weights():
     sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
     ref, _ = orc.forward("ENeRV_Boost", sd, cfg, t.cpu())
     assert max_rel(img1.cpu(), ref) < REL
-    assert max_rel(img0.cpu(), ref) > 10 * max_rel(img1.cpu(), ref)       # the first decode used the old weights
+    assert max_rel(img0.cpu(), ref) > max(5 * max_rel(img1.cpu(), ref), 3e-3)       # the first decode used the old weights
 
 
 @pytest.mark.parametrize("name,steps", [("nerv_s", 300), ("enerv_m", 300), ("hnerv_l", 300)])
