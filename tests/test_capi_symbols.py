@@ -46,4 +46,16 @@ def test_sizes_and_argument_errors_without_a_gpu():
     assert lib.bnerv_channel_sum(one, 1, 12, 4, 4, 0, one, None) == -1
     rc = lib.bnerv_conv_fused_ex(one, 1, 8, 4, 4, one, one, 8, 3, 1, 0, one, None, None, one, None, None, one, None)
     assert rc == -1 and b"out_deriv" in lib.bnerv_last_error()
+    # round-2 entry points: streaming kernels, split conv, paired linear layers, multi-tensor PTQ
+    assert lib.bnerv_conv_stream(None, 1, 43, 8, 8, one, one, 43, 0, None, None, None, one, None, None) == -1
+    assert lib.bnerv_conv_stream(one, 1, 43, 8, 8, one, one, 21, 0, None, None, None, one, None, None) == -2 and b"equal padded widths" in lib.bnerv_last_error()
+    assert lib.bnerv_conv_stream(one, 1, 43, 8, 8, one, one, 43, 0, None, one, None, one, None, None) == -1       # g1p without beta / out_aff
+    assert lib.bnerv_upconv_stream(one, 1, 12, 8, 8, one, one, 12, 1, one, one, one, one, None) == -2
+    assert lib.bnerv_resblock_stream(one, one, 1, 64, 8, 8, one, one, one, one, 2, one, one, one, None) == -2
+    assert lib.bnerv_resblock_stream_head(one, one, 1, 21, 8, 8, one, one, one, one, 2, one, one, one, one, 5, 4, one, None) == -2
+    assert lib.bnerv_nerv_block_stream(one, 1, 12, 8, 8, one, one, 3, 3, 1, one, one, one, one, 12, 2, one, one, one, one, one, None) == -2
+    assert lib.bnerv_conv_fused_split(one, 1, 48, 4, 4, one, one, 16, 3, 1, 0, None, None, None, one, None, None, 2, None) == -1
+    assert lib.bnerv_linear_pair(None, 1, None) == -1
+    assert lib.bnerv_ptq_quant_tensors(None, 0, 8, None, 0, None) == -1
+    assert lib.bnerv_ptq_quant_tensors_scratch_bytes(None, 0) == 0
     assert lib.bnerv_launch_count() == 0
